@@ -1,0 +1,199 @@
+/*
+ * parametron_b200.h -- C ABI of the B200-native replacement for Parametron.jl's
+ * parameter-update hot path (`update!` + coefficient assembly).
+ *
+ * The reference (pure Julia) has no FFI of its own; the seams this library sits
+ * behind are listed per entry point as `ref:` citations into /root/reference/src.
+ * A Julia `ccall` shim that binds exactly these symbols is shown in INTEGRATION.md;
+ * the Python ctypes binding in parametron.jl_b200/_capi.py is the one exercised by tests.
+ *
+ * Conventions
+ *   - every call returns PMB_OK (0) or a negative PMB_E* status; pmb_last_error(ctx) holds the
+ *     message (the Julia shim rethrows: `error(...)`, DimensionMismatch, ArgumentError).
+ *   - matrices are COLUMN-MAJOR fp64 (Julia `Matrix{Float64}`); variable indices are 1-based
+ *     int64 (ref: functions.jl:96-98, model.jl:49-53).
+ *   - a context owns one CUDA stream's worth of work and is NOT re-entrant, like the reference's
+ *     preallocated `dest` buffers (ref: lazyexpression.jl:202, test/lazyexpression.jl:73).
+ *   - `batch` > 1 stacks `batch` independent instances of the same model: every Parameter buffer
+ *     gets a leading instance stride, every output too (instance-shard data parallelism).
+ *   - build-phase calls after pmb_initialize() fail with PMB_EINITIALIZED
+ *     (ref: model.jl:50,61,69 "Model has already been initialized").
+ *   - pmb_update() performs no allocation and, for device-resident Parameters, no host<->device
+ *     copy (ref: `@allocated solve!(model) == 0`, test/model.jl:117-122).
+ */
+#ifndef PARAMETRON_B200_H
+#define PARAMETRON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmb_ctx pmb_ctx;
+typedef int32_t pmb_node; /* handle of a DAG node (>= 0) */
+
+enum {
+    PMB_OK = 0,
+    PMB_EINVAL = -1,       /* ArgumentError */
+    PMB_EDIM = -2,         /* DimensionMismatch (ref: functions.jl:669,755,780-781,845,877) */
+    PMB_EINITIALIZED = -3, /* build call after initialize (ref: model.jl:50,61,69) */
+    PMB_ENOTINIT = -4,
+    PMB_ECUDA = -5,
+    PMB_EUNSUPPORTED = -6, /* expression shape with no device lowering ("Unhandled ...", model.jl:139) */
+    PMB_ENOMEM = -7
+};
+
+/* value kinds of DAG nodes == Julia types of evaluated expressions */
+enum {
+    PMB_KIND_NUM_SCALAR = 0, /* T                          */
+    PMB_KIND_NUM_VECTOR = 1, /* Vector{T}                  */
+    PMB_KIND_NUM_MATRIX = 2, /* Matrix{T}                  */
+    PMB_KIND_VARVEC = 3,     /* Vector{Variable}           */
+    PMB_KIND_AFFVEC = 4,     /* Vector{AffineFunction{T}}  */
+    PMB_KIND_AFF = 5,        /* AffineFunction{T}          */
+    PMB_KIND_QUAD = 6,       /* QuadraticFunction{T}       */
+    PMB_KIND_ADJVEC = 7      /* Adjoint/Transpose of a vector (numeric or Variables) */
+};
+
+enum { PMB_MINIMIZE = 0, PMB_MAXIMIZE = 1 }; /* ref: Parametron.jl:50 `Sense` */
+
+/* constraint sets; scalar kinds for AFF/QUAD nodes, vector kinds for AFFVEC nodes
+ * (ref: model.jl:75-95, bucket order moi_interop.jl:180-193) */
+enum {
+    PMB_SET_NONNEGATIVE = 0, /* expr >= 0 : GreaterThan(0) / Nonnegatives(n) */
+    PMB_SET_NONPOSITIVE = 1, /* expr <= 0 : LessThan(0)    / Nonpositives(n) */
+    PMB_SET_ZERO = 2         /* expr == 0 : EqualTo(0)     / Zeros(n)        */
+};
+
+/* Parameter modes (ref: parameter.jl:48,57,88) */
+enum {
+    PMB_PARAM_DEVICE = 0,  /* manual mode: caller-owned DEVICE buffer, written by the caller before update
+                              (ref: Parameter(model; val=buf), parameter.jl:88) */
+    PMB_PARAM_HOST = 1,    /* caller-owned HOST buffer (+ optional host callback run once per update, then one
+                              H2D copy) (ref: in-place Parameter(f, val, model), parameter.jl:57,101) */
+    PMB_PARAM_UNIFORM = 2  /* built-in device generator: scale * U[0,1) from Philox4x32-10 keyed by
+                              (seed, instance, update counter) (ref: Parameter(rand!, zeros(n,n), model), README.md:36-43) */
+};
+
+typedef void (*pmb_host_callback)(double* val, int64_t rows, int64_t cols, int64_t batch, void* user);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* ref: Model(optimizer) model.jl:10-30.  `stream` is a cudaStream_t (NULL = the library creates its own). */
+int pmb_ctx_create(int device, void* stream, int64_t batch, pmb_ctx** out);
+int pmb_ctx_destroy(pmb_ctx* ctx);
+const char* pmb_last_error(const pmb_ctx* ctx);
+const char* pmb_version(void);
+
+/* ---- variables / parameters / constants (build phase) ------------------------------------------ */
+/* ref: Variable(m::Model) model.jl:49-53 -- returns the 1-based index of the first new variable. */
+int pmb_add_variables(pmb_ctx* ctx, int64_t n, int64_t* first_index);
+int pmb_num_variables(const pmb_ctx* ctx, int64_t* n);
+
+/* ref: Parameter constructors parameter.jl:48-88.  rows x cols fp64; cols == 0 -> vector; rows == cols == 0 -> scalar. */
+int pmb_param_create(pmb_ctx* ctx, int64_t rows, int64_t cols, int mode, pmb_node* out);
+int pmb_param_set_device_ptr(pmb_ctx* ctx, pmb_node p, const double* dptr);           /* PMB_PARAM_DEVICE */
+int pmb_param_set_host_ptr(pmb_ctx* ctx, pmb_node p, double* hptr,
+                           pmb_host_callback f, void* user);                          /* PMB_PARAM_HOST */
+int pmb_param_set_uniform(pmb_ctx* ctx, pmb_node p, uint64_t seed, double scale);     /* PMB_PARAM_UNIFORM */
+/* stream-ordered host -> device copy of a whole Parameter value (batch * rows * max(cols,1) doubles); usable after
+ * pmb_initialize for PMB_PARAM_DEVICE parameters whose buffer the library owns (no pmb_param_set_device_ptr call). */
+int pmb_param_upload(pmb_ctx* ctx, pmb_node p, const double* host_values);
+/* device address of the Parameter's current value (batch-major: instance stride = rows*max(cols,1)) */
+int pmb_param_device_ptr(pmb_ctx* ctx, pmb_node p, double** dptr);
+
+/* constants folded at build time (ref: optimize_toplevel constant folding, lazyexpression.jl:189-192) */
+int pmb_const_numeric(pmb_ctx* ctx, int64_t rows, int64_t cols, const double* host_values, pmb_node* out);
+/* Vector{Variable} from 1-based indices */
+int pmb_varvec(pmb_ctx* ctx, int64_t n, const int64_t* var_indices, pmb_node* out);
+/* constant symbolic values (terms given in reference order): scalar affine / quadratic, affine vector */
+int pmb_const_affine(pmb_ctx* ctx, int64_t nterms, const double* coeffs, const int64_t* vars, double constant, pmb_node* out);
+int pmb_const_quadratic(pmb_ctx* ctx, int64_t nquad, const double* qcoeffs, const int64_t* rowvars, const int64_t* colvars,
+                        int64_t nlin, const double* lcoeffs, const int64_t* lvars, double constant, pmb_node* out);
+
+/* ---- expression DAG: one builder per rewrite rule of lazyexpression.jl:198-302 ---------------- */
+int pmb_op_matvec(pmb_ctx* ctx, pmb_node A, pmb_node x, pmb_node* out);   /* A*x   -> matvecmul!  :200-204, functions.jl:775-829 */
+int pmb_op_adjoint(pmb_ctx* ctx, pmb_node A, pmb_node* out);              /* A' / transpose :206-217 */
+int pmb_op_bilinear(pmb_ctx* ctx, pmb_node xT, pmb_node Q, pmb_node y, pmb_node* out); /* x'Qy -> bilinearmul! :219-226, functions.jl:840-858 */
+int pmb_op_dot(pmb_ctx* ctx, pmb_node x, pmb_node y, pmb_node* out);      /* x . y -> vecdot!     :228-232, functions.jl:665-731 */
+int pmb_op_add(pmb_ctx* ctx, pmb_node x, pmb_node y, pmb_node* out);      /* x + y -> add!/vecadd!           :238-247 */
+int pmb_op_sub(pmb_ctx* ctx, pmb_node x, pmb_node y, pmb_node* out);      /* x - y -> subtract!/vecsubtract! :249-258 */
+int pmb_op_mul(pmb_ctx* ctx, pmb_node x, pmb_node y, pmb_node* out);      /* scalar*fn -> mul! :260-274; number*vector -> scale! :284-290 */
+int pmb_op_vcat(pmb_ctx* ctx, int32_t n, const pmb_node* parts, pmb_node* out); /* vcat! :276-278, functions.jl:969-994 */
+int pmb_op_vect(pmb_ctx* ctx, pmb_node x, pmb_node* out);                 /* [x]   :292-298 */
+int pmb_node_info(pmb_ctx* ctx, pmb_node n, int32_t* kind, int64_t* rows, int64_t* cols, int32_t* is_constant);
+
+/* ---- model ------------------------------------------------------------------------------------ */
+/* ref: setobjective! model.jl:60-66 / @objective :267-271.  node kind: AFF, QUAD (or NUM_SCALAR). */
+int pmb_set_objective(pmb_ctx* ctx, int sense, pmb_node expr);
+/* ref: add_*_constraint! model.jl:75-98 / @constraint :224-249 (expr = lhs - rhs).  Returns the block id. */
+int pmb_add_constraint(pmb_ctx* ctx, pmb_node expr, int set_kind, int32_t* block_id);
+/* ref: initialize! model.jl:117-122 + mapindices! :100-107.  varmap[i-1] = optimizer index of model variable i
+ * (NULL = identity); plans launches, allocates all device buffers, captures the CUDA graph. */
+int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap);
+/* ref: update!(m::Model) model.jl:132-143: mark all Parameters dirty, evaluate each once, re-assemble the objective
+ * (Q, q, c0) then every non-constant constraint block in bucket order (moi_interop.jl:180-193, 236-247).
+ * Asynchronous on the context's stream. */
+int pmb_update(pmb_ctx* ctx);
+int pmb_synchronize(pmb_ctx* ctx);
+int pmb_update_count(const pmb_ctx* ctx, int64_t* n);
+
+/* ---- device-resident handoff (replaces MOI.set, moi_interop.jl:134,171) ------------------------- */
+typedef struct {
+    int32_t kind;        /* PMB_KIND_AFF or PMB_KIND_QUAD */
+    int32_t sense;
+    int32_t is_constant; /* skipped by update (ref: isconstant, moi_interop.jl:123,132) */
+    int64_t nvars;       /* N: Q is N x N column-major (ld = N), symmetric = MOI Hessian of 1/2 x'Qx + q'x + c0 */
+    double* Q;           /* device, batch stride N*N; NULL for affine objectives */
+    double* q;           /* device, batch stride N */
+    double* c0;          /* device, batch stride 1 */
+} pmb_objective_view;
+
+typedef struct {
+    int32_t set_kind;    /* PMB_SET_* */
+    int32_t is_scalar;   /* 1: scalar (Aff/Quad in GreaterThan/LessThan/EqualTo), 0: vector set */
+    int32_t is_constant;
+    int32_t bucket;      /* index into the reference's fixed bucket order (moi_interop.jl:180-193) */
+    int64_t rows;        /* m_i */
+    int64_t nvars;       /* N */
+    double* C;           /* device, m_i x N column-major (ld = m_i), batch stride m_i*N; columns are OPTIMIZER indices */
+    double* d;           /* device, m_i, batch stride m_i   (the block is  C x + d  in the set) */
+    int64_t nterms;      /* number of reference LinearTerms per instance (static sparsity bookkeeping) */
+} pmb_block_view;
+
+int pmb_get_objective(pmb_ctx* ctx, pmb_objective_view* out);
+int pmb_num_blocks(const pmb_ctx* ctx, int32_t* n);
+/* blocks are numbered in UPDATE order: bucket order, insertion order within a bucket */
+int pmb_get_block(pmb_ctx* ctx, int32_t update_pos, pmb_block_view* out);
+/* Static index bookkeeping, bit-exact with the reference's MOI.VectorAffineTerm list after `update!`
+ * (row-outer / term-inner, varmap applied; moi_interop.jl:64-81).  `src` gives, for term t, the offset
+ * (column-major, within one instance) of the dense C entry its coefficient is summed into. */
+int pmb_block_term_index(pmb_ctx* ctx, int32_t update_pos, int64_t capacity, int64_t* rows, int64_t* vars, int64_t* src);
+
+/* ---- host staging helpers (pinned memory + stream-ordered copies; the e2e path of bench.py and the ctypes tests) -- */
+int pmb_host_alloc(pmb_ctx* ctx, size_t bytes, void** out);   /* cudaHostAlloc; freed by pmb_host_free or pmb_ctx_destroy */
+int pmb_host_free(pmb_ctx* ctx, void* p);
+int pmb_memcpy_d2h(pmb_ctx* ctx, void* host, const void* dev, size_t bytes);  /* async on the context stream */
+int pmb_memcpy_h2d(pmb_ctx* ctx, void* dev, const void* host, size_t bytes);  /* async on the context stream */
+
+/* ---- introspection for tests / bench --------------------------------------------------------- */
+typedef struct {
+    int64_t kernel_launches_per_update; /* launches of THIS library's kernels in one update */
+    int64_t memcpy_nodes_per_update;    /* H2D staging copies (PMB_PARAM_HOST only) */
+    int64_t device_bytes_allocated;
+    int64_t uses_cuda_graph;
+    int64_t affine_algorithmic_bytes;   /* 16 B per stored coefficient + 16 B per row, all blocks, one instance */
+    int64_t gram_algorithmic_flops;     /* SYRK count k*N*(N+1) + 2kN + 2k per Gram term, one instance */
+} pmb_stats;
+int pmb_get_stats(pmb_ctx* ctx, pmb_stats* out);
+/* time (ms, CUDA events on the context stream) of the most recent launch of each kernel class; class names via pmb_kernel_class_name */
+int pmb_enable_kernel_timing(pmb_ctx* ctx, int enable);
+int pmb_kernel_class_count(void);
+const char* pmb_kernel_class_name(int cls);
+int pmb_kernel_time_ms(pmb_ctx* ctx, int cls, double* total_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARAMETRON_B200_H */

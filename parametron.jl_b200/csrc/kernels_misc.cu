@@ -1,0 +1,309 @@
+// Small kernels around the two hot kernels: Parameter generators, numeric prologue ops, reductions for the affine
+// offsets / linear objective part (warp-shuffle), scatter of the rarely used quadratic shapes.
+#include "pmb_kernels.h"
+
+namespace pmb {
+
+__device__ __forceinline__ double alpha_val(const AlphaDev& a, int64_t inst) {
+    return a.ptr ? a.c * a.ptr[inst * a.bstride] : a.c;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum for 256 threads; result valid in thread 0
+__device__ __forceinline__ double block_sum_256(double v) {
+    __shared__ double part[8];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < 8 ? part[threadIdx.x] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+// ---------------- update counter -------------------------------------------------------------
+__global__ void tick_kernel(unsigned long long* c) { *c += 1ULL; }
+void launch_tick(unsigned long long* counter, cudaStream_t stream) { tick_kernel<<<1, 1, 0, stream>>>(counter); }
+
+// ---------------- Philox4x32-10 ----------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__global__ void __launch_bounds__(256) philox_uniform_kernel(double* out, int64_t numel, int64_t batch, uint64_t seed, double scale,
+                                                             const unsigned long long* update_counter) {
+    const uint32_t upd = (uint32_t)(*update_counter);
+    const int64_t pairs = (numel + 1) / 2;
+    const bool vec_ok = (numel % 2 == 0) && (((uintptr_t)out & 15) == 0);
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        double* o = out + inst * numel;
+        for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * blockDim.x) {
+            uint32_t c[4] = {(uint32_t)p, (uint32_t)((uint64_t)p >> 32), (uint32_t)inst, upd};
+            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+            double d0 = (double)((((uint64_t)c[1] << 32) | c[0]) >> 11) * (1.0 / 9007199254740992.0) * scale;
+            double d1 = (double)((((uint64_t)c[3] << 32) | c[2]) >> 11) * (1.0 / 9007199254740992.0) * scale;
+            if (vec_ok) {
+                *reinterpret_cast<double2*>(o + 2 * p) = make_double2(d0, d1);
+            } else {
+                o[2 * p] = d0;
+                if (2 * p + 1 < numel) o[2 * p + 1] = d1;
+            }
+        }
+    }
+}
+void launch_philox_uniform(double* out, int64_t numel, int64_t batch, uint64_t seed, double scale,
+                           const unsigned long long* update_counter, int sm_count, cudaStream_t stream) {
+    if (numel == 0) return;
+    int64_t pairs = (numel + 1) / 2;
+    int64_t bx = (pairs + 255) / 256;
+    int64_t cap = (int64_t)sm_count * 16;
+    if (bx > cap) bx = cap;
+    int64_t by = batch < 65535 ? batch : 65535;
+    if (bx * by > cap * 4 && by > 1) { bx = bx * 1; }
+    philox_uniform_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(out, numel, batch, seed, scale, update_counter);
+}
+
+// ---------------- numeric prologue ---------------------------------------------------------------
+__global__ void lincomb_kernel(double* out, int64_t out_bstride, int64_t n, const LinCombTermDev* terms, int nterms, const double* cst,
+                               int64_t batch) {
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            double acc = cst ? cst[i] : 0.0;
+            for (int t = 0; t < nterms; ++t)
+                acc += alpha_val(terms[t].alpha, inst) * terms[t].src[inst * terms[t].src_bstride + terms[t].src_off + i];
+            out[inst * out_bstride + i] = acc;
+        }
+}
+void launch_lincomb(double* out, int64_t out_bstride, int64_t n, const LinCombTermDev* terms, int nterms, const double* cst,
+                    int64_t batch, cudaStream_t stream) {
+    if (n == 0) return;
+    int64_t bx = (n + 255) / 256; if (bx > 2048) bx = 2048;
+    int64_t by = batch < 65535 ? batch : 65535;
+    lincomb_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(out, out_bstride, n, terms, nterms, cst, batch);
+}
+
+__global__ void transpose_kernel(double* out, int64_t out_bstride, const double* in, int64_t in_bstride, int64_t rows, int64_t cols) {
+    __shared__ double tile[32][33];
+    const double* src = in + (int64_t)blockIdx.z * in_bstride;
+    double* dst = out + (int64_t)blockIdx.z * out_bstride;
+    int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int64_t r = r0 + threadIdx.x, c = c0 + j;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = src[r + c * rows];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int64_t c = c0 + threadIdx.x, r = r0 + j;  // out is cols x rows: out[c + r*cols] = in[r + c*rows]
+        if (r < rows && c < cols) dst[c + r * cols] = tile[threadIdx.x][j];
+    }
+}
+void launch_transpose(double* out, int64_t out_bstride, const double* in, int64_t in_bstride, int64_t rows, int64_t cols, int64_t batch,
+                      cudaStream_t stream) {
+    if (rows == 0 || cols == 0) return;
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+        int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32), (unsigned)nb);
+        transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(out + b0 * out_bstride, out_bstride, in + b0 * in_bstride, in_bstride, rows, cols);
+    }
+}
+
+// y = A'v : one warp per column, rows contiguous -> coalesced, warp-shuffle reduction
+__global__ void __launch_bounds__(256) gemv_t_kernel(GemvArgs a, int64_t batch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        const double* A = a.A + inst * a.a_bstride;
+        const double* v = a.v + inst * a.v_bstride + a.v_off;
+        for (int64_t col = (int64_t)blockIdx.x * 8 + warp; col < a.cols; col += (int64_t)gridDim.x * 8) {
+            const double* ac = A + col * a.lda;
+            double acc = 0.0;
+            for (int64_t r = lane; r < a.rows; r += 32) acc += ac[r] * v[r];
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                double val = alpha_val(a.scale, inst) * acc;
+                double* dst = a.y + inst * a.y_bstride + (a.map ? a.map[col] : col);
+                if (a.accumulate) *dst += val; else *dst = val;
+            }
+        }
+    }
+}
+// y = A v : 32 rows per CTA, 8 column slices reduced through shared memory
+__global__ void __launch_bounds__(256) gemv_n_kernel(GemvArgs a, int64_t batch) {
+    __shared__ double red[8][33];
+    const int rl = threadIdx.x & 31, cs = threadIdx.x >> 5;
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        const double* A = a.A + inst * a.a_bstride;
+        const double* v = a.v + inst * a.v_bstride + a.v_off;
+        for (int64_t r0 = (int64_t)blockIdx.x * 32; r0 < a.rows; r0 += (int64_t)gridDim.x * 32) {
+            int64_t r = r0 + rl;
+            double acc = 0.0;
+            if (r < a.rows)
+                for (int64_t c = cs; c < a.cols; c += 8) acc += A[r + c * a.lda] * v[c];
+            red[cs][rl] = acc;
+            __syncthreads();
+            if (cs == 0 && r < a.rows) {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s += red[i][rl];
+                double val = alpha_val(a.scale, inst) * s;
+                double* dst = a.y + inst * a.y_bstride + (a.map ? a.map[r] : r);
+                if (a.accumulate) *dst += val; else *dst = val;
+            }
+            __syncthreads();
+        }
+    }
+}
+void launch_gemv(const GemvArgs& a, int64_t batch, cudaStream_t stream) {
+    int64_t outlen = a.trans ? a.cols : a.rows;
+    if (outlen == 0) return;
+    int64_t by = batch < 65535 ? batch : 65535;
+    if (a.trans) {
+        int64_t bx = (a.cols + 7) / 8; if (bx > 4096) bx = 4096;
+        gemv_t_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(a, batch);
+    } else {
+        int64_t bx = (a.rows + 31) / 32; if (bx > 4096) bx = 4096;
+        gemv_n_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(a, batch);
+    }
+}
+
+__global__ void __launch_bounds__(256) dot_kernel(DotArgs a, int64_t batch) {
+    for (int64_t inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+        const double* x = a.x + inst * a.x_bstride + a.x_off;
+        const double* y = a.y + inst * a.y_bstride + a.y_off;
+        double acc = 0.0;
+        for (int64_t i = threadIdx.x; i < a.n; i += 256) acc += x[i] * y[i];
+        acc = block_sum_256(acc);
+        if (threadIdx.x == 0) {
+            double val = alpha_val(a.scale, inst) * acc;
+            double* dst = a.out + inst * a.out_bstride;
+            if (a.accumulate) *dst += val; else *dst = val;
+        }
+    }
+}
+void launch_dot(const DotArgs& a, int64_t batch, cudaStream_t stream) {
+    int64_t bx = batch < 65535 ? batch : 65535;
+    dot_kernel<<<(unsigned)bx, 256, 0, stream>>>(a, batch);
+}
+
+__global__ void scalar_prod_kernel(double* out, int64_t out_bstride, double c, const double* s0, int64_t s0_bstride, const double* s1,
+                                   int64_t s1_bstride, int64_t batch) {
+    for (int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; inst < batch; inst += (int64_t)gridDim.x * blockDim.x) {
+        double v = c;
+        if (s0) v *= s0[inst * s0_bstride];
+        if (s1) v *= s1[inst * s1_bstride];
+        out[inst * out_bstride] = v;
+    }
+}
+void launch_scalar_prod(double* out, int64_t out_bstride, double c, const double* s0, int64_t s0_bstride, const double* s1,
+                        int64_t s1_bstride, int64_t batch, cudaStream_t stream) {
+    int64_t bx = (batch + 255) / 256; if (bx > 1024) bx = 1024;
+    scalar_prod_kernel<<<(unsigned)bx, 256, 0, stream>>>(out, out_bstride, c, s0, s0_bstride, s1, s1_bstride, batch);
+}
+
+__global__ void scatter_vec_kernel(ScatterVecArgs a, int64_t batch) {
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        const double al = alpha_val(a.alpha, inst);
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += (int64_t)gridDim.x * blockDim.x) {
+            double val = al * a.v[inst * a.v_bstride + a.v_off + j];
+            double* dst = a.q + inst * a.q_bstride + (a.map ? a.map[j] : j);
+            if (a.accumulate) atomicAdd(dst, val); else *dst = val;
+        }
+    }
+}
+void launch_scatter_vec(const ScatterVecArgs& a, int64_t batch, cudaStream_t stream) {
+    if (a.n == 0) return;
+    int64_t bx = (a.n + 255) / 256; if (bx > 2048) bx = 2048;
+    int64_t by = batch < 65535 ? batch : 65535;
+    scatter_vec_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(a, batch);
+}
+
+__global__ void bilinear_scatter_kernel(BilinearArgs a, int64_t batch) {
+    const int64_t total = a.nx * a.ny;
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        const double al = alpha_val(a.alpha, inst);
+        const double* Q = a.Q + inst * a.q_bstride;
+        double* H = a.H + inst * a.h_bstride;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+            // e is Q's column-major linear index == the reference's running k: (row, col) = (e / ny, e % ny)   functions.jl:849-856
+            int64_t qi = e % a.nx, qj = e / a.nx;
+            int64_t row = e / a.ny, col = e % a.ny;
+            double v = al * Q[qi + qj * a.ldq];
+            int64_t hi = a.xmap[row], hj = a.ymap[col];
+            atomicAdd(H + hi + hj * a.ldh, v);
+            atomicAdd(H + hj + hi * a.ldh, v);
+        }
+    }
+}
+void launch_bilinear_scatter(const BilinearArgs& a, int64_t batch, cudaStream_t stream) {
+    int64_t total = a.nx * a.ny;
+    if (total == 0) return;
+    int64_t bx = (total + 255) / 256; if (bx > 4096) bx = 4096;
+    int64_t by = batch < 65535 ? batch : 65535;
+    bilinear_scatter_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(a, batch);
+}
+
+__global__ void coo_quad_kernel(CooQuadArgs a, int64_t batch) {
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        const double al = alpha_val(a.alpha, inst);
+        double* H = a.H + inst * a.h_bstride;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.nnz; e += (int64_t)gridDim.x * blockDim.x) {
+            double v = al * a.c[e];
+            atomicAdd(H + a.i[e] + (int64_t)a.j[e] * a.ldh, v);
+            atomicAdd(H + a.j[e] + (int64_t)a.i[e] * a.ldh, v);
+        }
+    }
+}
+void launch_coo_quad(const CooQuadArgs& a, int64_t batch, cudaStream_t stream) {
+    if (a.nnz == 0) return;
+    int64_t bx = (a.nnz + 255) / 256; if (bx > 2048) bx = 2048;
+    int64_t by = batch < 65535 ? batch : 65535;
+    coo_quad_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(a, batch);
+}
+
+__global__ void scatter_sym_kernel(ScatterSymArgs a, int64_t batch) {
+    const int64_t total = a.n * a.p;
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        const double al = alpha_val(a.alpha, inst);
+        const double* M = a.M + inst * a.m_bstride;
+        double* H = a.H + inst * a.h_bstride;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+            int64_t i = e % a.n, j = e / a.n;
+            double v = al * M[i + j * a.ldm];
+            int64_t hi = a.xmap ? a.xmap[i] : i, hj = a.ymap ? a.ymap[j] : j;
+            atomicAdd(H + hi + hj * a.ldh, v);
+            atomicAdd(H + hj + hi * a.ldh, v);
+        }
+    }
+}
+void launch_scatter_sym(const ScatterSymArgs& a, int64_t batch, cudaStream_t stream) {
+    int64_t total = a.n * a.p;
+    if (total == 0) return;
+    int64_t bx = (total + 255) / 256; if (bx > 4096) bx = 4096;
+    int64_t by = batch < 65535 ? batch : 65535;
+    scatter_sym_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(a, batch);
+}
+
+__global__ void fill_kernel(double* p, int64_t n, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill(double* p, int64_t n, double v, cudaStream_t stream) {
+    if (n == 0) return;
+    int64_t bx = (n + 255) / 256; if (bx > 4096) bx = 4096;
+    fill_kernel<<<(unsigned)bx, 256, 0, stream>>>(p, n, v);
+}
+
+}  // namespace pmb

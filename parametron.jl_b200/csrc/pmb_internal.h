@@ -1,0 +1,202 @@
+// Host-side data model of the device expression DAG (the restatement of src/lazyexpression.jl's LazyExpression tree
+// and of the term-list value types of src/functions.jl as static "linear forms" over Parameter buffers).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/parametron_b200.h"
+#include "pmb_kernels.h"
+
+namespace pmb {
+
+// alpha = c * (node >= 0 ? value of scalar numeric node : 1)
+struct Alpha {
+    double c = 1.0;
+    int node = -1;
+};
+
+// G[row_off + i, var(vars[j])] += alpha * M[i, src_col_off + j]     i < rows, j < cols      (matvecmul!, functions.jl:775-798)
+struct MatTerm {
+    Alpha a;
+    int mat = -1;
+    int64_t src_col_off = 0, row_off = 0, rows = 0, cols = 0;
+    std::vector<int64_t> vars;  // 1-based model variable indices, length cols
+};
+// G[row_off + i, var(vars[i])] += alpha                                               (Vector{Variable} operand)
+struct UnitTerm {
+    Alpha a;
+    int64_t row_off = 0, rows = 0;
+    std::vector<int64_t> vars;
+};
+// g[row_off + i] += alpha * v[src_off + i]                                             (add!/subtract! of numbers)
+struct OffTerm {
+    Alpha a;
+    int vec = -1;
+    int64_t src_off = 0, row_off = 0, rows = 0;
+};
+struct OrdSeg {
+    int is_unit = 0;
+    std::vector<int> idx;  // indices into mats (members share row_off/rows/cols) or a single index into units
+};
+// Vector{AffineFunction} (or a scalar AffineFunction when rows == 1 && scalar)
+struct AffForm {
+    int64_t rows = 0;
+    std::vector<MatTerm> mats;
+    std::vector<UnitTerm> units;
+    std::vector<OffTerm> offs;
+    std::vector<double> coff;                  // folded constant offsets (size rows, or empty == zeros)
+    // Reference term-append order, per row: segments are visited in order; a matrix segment with several members emits
+    // its members interleaved per source column (matvecmul! over Vector{AffineFunction}, functions.jl:800-822).
+    std::vector<OrdSeg> order;
+    bool order_exact = true;                   // false when the reference's per-row term order is not expressible by `order`
+};
+struct GramTerm {  // alpha * sum_r f_r * h_r        (vecdot! on two affine vectors, functions.jl:702-709)
+    Alpha a;
+    AffForm f, h;
+    bool same = false;
+};
+struct BilinTerm {  // alpha * x' Q y                 (bilinearmul!, functions.jl:840-858)
+    Alpha a;
+    int mat = -1;
+    std::vector<int64_t> xv, yv;
+};
+struct CooTerm {  // alpha * sum_e c_e * x_{i_e} * x_{j_e}   (folded constant QuadraticTerms)
+    Alpha a;
+    std::vector<int64_t> i, j;
+    std::vector<double> c;
+};
+struct QuadForm {
+    std::vector<GramTerm> grams;
+    std::vector<BilinTerm> bilins;
+    std::vector<CooTerm> coos;
+    AffForm aff;  // rows == 1
+};
+
+enum NumOp { NOP_NONE = -1, NOP_PARAM, NOP_CONST, NOP_TRANSPOSE, NOP_LINCOMB, NOP_GEMV, NOP_DOT, NOP_SPROD, NOP_GEMM_TN };
+
+struct LinTermH {
+    Alpha a;
+    int src;
+    int64_t src_off;
+};
+
+struct Node {
+    int kind = -1;
+    int64_t rows = 0, cols = 0;  // numeric: rows x cols (vector: cols == 0; scalar: rows == cols == 0)
+    bool is_const = true;
+    // numeric nodes
+    int nop = NOP_NONE;
+    std::vector<int> in;
+    std::vector<LinTermH> lin;
+    std::vector<double> cvals;
+    int gemv_trans = 0;
+    int64_t gemv_col_off = 0, gemv_cols = 0, gemv_row_off = 0, gemv_rows = 0, gemv_v_off = 0;
+    int64_t dot_xoff = 0, dot_yoff = 0, dot_n = 0;
+    int64_t gm_xoff = 0, gm_yoff = 0, gm_k = 0;  // NOP_GEMM_TN: node (rows x cols) = X[xoff.., :]' * Y[:, yoff..] over gm_k rows
+    double sprod_c = 1.0;
+    // parameters
+    int pmode = -1;
+    uint64_t seed = 0;
+    double scale = 1.0;
+    double* hptr = nullptr;
+    pmb_host_callback cb = nullptr;
+    void* user = nullptr;
+    const double* ext = nullptr;
+    // device storage
+    double* dptr = nullptr;
+    int64_t numel = 0, bstride = 0;
+    bool owned = false, needed = false;
+    // symbolic nodes
+    std::vector<int64_t> vars;
+    int adj_parent = -1;
+    std::shared_ptr<AffForm> aff;
+    std::shared_ptr<QuadForm> quad;
+};
+
+enum KernelClass { KC_AFFINE = 0, KC_GRAM, KC_GEMM, KC_PHILOX, KC_H2D, KC_REDUCE, KC_MISC, KC_COUNT };
+
+enum StepType {
+    ST_TICK, ST_PHILOX, ST_H2D, ST_MEMSET, ST_LINCOMB, ST_TRANSPOSE, ST_GEMV, ST_DOT, ST_SPROD, ST_AFFINE, ST_GRAM, ST_GEMM,
+    ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM
+};
+
+struct Step {
+    int type = 0, cls = KC_MISC;
+    int64_t batch = 1;
+    // generic pointer/size slots
+    double* out = nullptr;
+    const double* src = nullptr;
+    int64_t n = 0, n2 = 0, out_bstride = 0, src_bstride = 0;
+    uint64_t seed = 0;
+    double scale = 1.0;
+    const LinCombTermDev* lterms = nullptr;
+    int nl = 0;
+    const double* cst = nullptr;
+    const double* s0 = nullptr; int64_t s0_bs = 0;
+    const double* s1 = nullptr; int64_t s1_bs = 0;
+    AffBlockDev aff{};
+    GramArgs gram{};
+    GemmTNArgs gemm{};
+    GemvArgs gemv{};
+    DotArgs dot{};
+    ScatterVecArgs sv{};
+    BilinearArgs bl{};
+    CooQuadArgs coo{};
+    ScatterSymArgs ss{};
+};
+
+struct Constraint {
+    int node = -1;
+    int set_kind = 0;
+    int bucket = 0;
+    bool is_scalar = false, is_const = false;
+    int64_t rows = 0;
+    double* C = nullptr;
+    double* d = nullptr;
+    int64_t nterms = 0;
+    AffForm form;
+};
+
+}  // namespace pmb
+
+struct pmb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t batch = 1;
+    int64_t nvars = 0;
+    bool initialized = false;
+    std::string err;
+    std::vector<pmb::Node> nodes;
+    // objective
+    int obj_node = -1;
+    int obj_sense = PMB_MINIMIZE;
+    bool obj_const = true;
+    int obj_kind = PMB_KIND_AFF;
+    double *Q = nullptr, *q = nullptr, *c0 = nullptr;
+    std::vector<pmb::Constraint> cons;   // insertion order
+    std::vector<int> update_order;       // indices into cons, bucket order then insertion order
+    std::vector<int64_t> varmap;         // model var (1-based) -> optimizer var (1-based)
+    // plan
+    std::vector<pmb::Step> steps;        // one update
+    std::vector<pmb::Step> init_steps;   // constants, run once
+    std::vector<void*> pinned;           // pmb_host_alloc blocks still owned by the context
+    std::vector<void*> allocs;
+    int64_t bytes_alloc = 0;
+    unsigned long long* d_counter = nullptr;
+    int64_t updates = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    bool use_graph = false;
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;         // 2 per step
+    bool ev_pending = false;
+    double cls_ms[pmb::KC_COUNT] = {0};
+    int64_t cls_launches[pmb::KC_COUNT] = {0};
+    int64_t launches_per_update = 0, memcpy_per_update = 0;
+    int64_t affine_bytes = 0, gram_flops = 0;
+};

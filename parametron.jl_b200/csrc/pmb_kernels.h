@@ -1,0 +1,141 @@
+// Device-side argument structs and host launchers of the hand-written sm_100a kernels.
+// Host code (pmb_api.cu) only sees these launchers; every launcher enqueues on `stream` and never allocates.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pmb {
+
+// alpha = c * (ptr ? ptr[instance * bstride] : 1)     -- dynamic scalar multipliers (scale!/mul!, functions.jl:578,873-925)
+struct AlphaDev {
+    double c;
+    const double* ptr;
+    int64_t bstride;
+};
+
+// ---------------- K1: batched affine-coefficient assembly ------------------------------------
+// One coefficient source of a block:  G[row_off + i, outcol] += alpha * src[i + srccol * ld]   (matvecmul!, functions.jl:775-798)
+struct AffMatTermDev {
+    const double* src;
+    int64_t src_bstride;  // elements between instances (0: shared constant)
+    int64_t ld;
+    int64_t row_off, rows;
+    AlphaDev alpha;
+};
+// identity-like source: G[row, outcol] += alpha  for the single row stored in the column entry (Vector{Variable} operands)
+struct AffUnitTermDev {
+    AlphaDev alpha;
+};
+struct AffColEntry {  // one contribution to one output column
+    int32_t term;     // >= 0: index into mats[];  < 0: ~term indexes units[]
+    int32_t src;      // mats: source column;  units: the (block) row that receives alpha
+};
+// offset source: d[row_off + i] += alpha * v[src_off + i]        (subtract!/add! of numbers, functions.jl:452,474)
+struct AffOffTermDev {
+    const double* src;
+    int64_t src_bstride;
+    int64_t src_off, row_off, rows;
+    AlphaDev alpha;
+};
+struct AffBlockDev {
+    double* C;            // rows x N column-major, ld = rows
+    double* d;            // rows
+    int64_t C_bstride, d_bstride;
+    int64_t rows;
+    int32_t ntouched;     // number of output columns with at least one contribution (the others stay 0 forever)
+    const int32_t* col_out;   // [ntouched] output column (0-based optimizer variable index)
+    const int32_t* col_ptr;   // [ntouched + 1] CSR pointer into entries
+    const AffColEntry* entries;
+    const AffMatTermDev* mats;
+    const AffUnitTermDev* units;
+    int32_t noffs;
+    const AffOffTermDev* offs;
+    const double* d_const;    // [rows] folded constant part of the offsets (may be null)
+    int32_t simple;           // every touched column has exactly one matrix entry from mats[0] covering all rows
+    const int32_t* col_src;   // [ntouched] source column (simple path)
+    int32_t vec2;             // 16-byte path legal (even rows/ld/strides, aligned bases)
+};
+void launch_affine_assemble(const AffBlockDev& blk, int64_t batch, int sm_count, cudaStream_t stream);
+
+// ---------------- K2: fp64 Gram (SYRK-shaped) on the DMMA tensor pipe ---------------------------
+// H[map[i], map[j]] (=|+=) scale * sum_r X[r, i] * X[r, j]   for i, j in [0, n), both triangles written
+// (vecdot! + muladd!, functions.jl:548-576,702-709, followed by the diag x2 / symmetric MOI Hessian of moi_interop.jl:45-62)
+struct GramArgs {
+    const double* X;       // k x n column-major
+    int64_t ldx, x_bstride;
+    int64_t k, n;
+    double* H;             // N x N column-major
+    int64_t ldh, h_bstride;
+    const int32_t* map;    // [n] 0-based output index of source column i; null = identity
+    AlphaDev scale;
+    int32_t accumulate;    // 0: overwrite, 1: +=
+};
+void launch_gram_syrk(const GramArgs& a, int64_t batch, int sm_count, cudaStream_t stream);
+// general TN product  M (n x p, ld) = X' * Y  (scratch for dot(f, h) with f != h and for A * Vector{AffineFunction})
+struct GemmTNArgs {
+    const double* X; int64_t ldx, x_bstride;
+    const double* Y; int64_t ldy, y_bstride;
+    int64_t k, n, p;
+    double* M; int64_t ldm, m_bstride;
+};
+void launch_gemm_tn(const GemmTNArgs& a, int64_t batch, int sm_count, cudaStream_t stream);
+
+// ---------------- small kernels ---------------------------------------------------------------
+void launch_tick(unsigned long long* counter, cudaStream_t stream);
+// Philox4x32-10 uniform fill: out[b*numel + e] = scale * U[0,1), counter = (pair index, instance, update counter), key = seed
+void launch_philox_uniform(double* out, int64_t numel, int64_t batch, uint64_t seed, double scale,
+                           const unsigned long long* update_counter, int sm_count, cudaStream_t stream);
+// out[i] = cst[i] + sum_t alpha_t * src_t[off_t + i]
+struct LinCombTermDev { const double* src; int64_t src_bstride; int64_t src_off; AlphaDev alpha; };
+void launch_lincomb(double* out, int64_t out_bstride, int64_t n, const LinCombTermDev* terms, int nterms,
+                    const double* cst, int64_t batch, cudaStream_t stream);
+// out (cols x rows) = in (rows x cols)'       (adjoint buffer, lazyexpression.jl:206-217)
+void launch_transpose(double* out, int64_t out_bstride, const double* in, int64_t in_bstride, int64_t rows, int64_t cols,
+                      int64_t batch, cudaStream_t stream);
+// y = A v (trans = 0, len rows) or y = A' v (trans = 1, len cols); optional scatter: y[map[i]] (=|+=) scale * value
+struct GemvArgs {
+    const double* A; int64_t lda, a_bstride; int64_t rows, cols; int32_t trans;
+    const double* v; int64_t v_bstride; int64_t v_off;
+    double* y; int64_t y_bstride;
+    const int32_t* map; AlphaDev scale; int32_t accumulate;
+};
+void launch_gemv(const GemvArgs& a, int64_t batch, cudaStream_t stream);
+// out[0] (=|+=) scale * sum_i x[xoff+i] * y[yoff+i]
+struct DotArgs {
+    const double* x; int64_t x_bstride, x_off;
+    const double* y; int64_t y_bstride, y_off;
+    int64_t n; double* out; int64_t out_bstride; AlphaDev scale; int32_t accumulate;
+};
+void launch_dot(const DotArgs& a, int64_t batch, cudaStream_t stream);
+// scalar chain: out = c * prod_i s_i
+void launch_scalar_prod(double* out, int64_t out_bstride, double c, const double* s0, int64_t s0_bstride,
+                        const double* s1, int64_t s1_bstride, int64_t batch, cudaStream_t stream);
+// q[map[j]] (=|+=) alpha * v[off + j]   (dot(numbers, variables), functions.jl:676-687)
+struct ScatterVecArgs {
+    const double* v; int64_t v_bstride, v_off; int64_t n; const int32_t* map;
+    double* q; int64_t q_bstride; AlphaDev alpha; int32_t accumulate;
+};
+void launch_scatter_vec(const ScatterVecArgs& a, int64_t batch, cudaStream_t stream);
+// bilinearmul! (functions.jl:840-858) + symmetric MOI Hessian:  H[xm[r], ym[c]] += a*Q[c,r];  H[ym[c], xm[r]] += a*Q[c,r]
+struct BilinearArgs {
+    const double* Q; int64_t ldq, q_bstride; int64_t nx, ny;
+    const int32_t* xmap; const int32_t* ymap;
+    double* H; int64_t ldh, h_bstride; AlphaDev alpha;
+};
+void launch_bilinear_scatter(const BilinearArgs& a, int64_t batch, cudaStream_t stream);
+// constant quadratic terms: H[i,j] += a*c ; H[j,i] += a*c  (i == j: += 2ac, moi_interop.jl:58)
+struct CooQuadArgs {
+    const int32_t* i; const int32_t* j; const double* c; int64_t nnz;
+    double* H; int64_t ldh, h_bstride; AlphaDev alpha;
+};
+void launch_coo_quad(const CooQuadArgs& a, int64_t batch, cudaStream_t stream);
+// general scatter of a scratch product into the symmetric Hessian: H[xm[i], ym[j]] += a*M[i,j]; H[ym[j], xm[i]] += a*M[i,j]
+struct ScatterSymArgs {
+    const double* M; int64_t ldm, m_bstride; int64_t n, p;
+    const int32_t* xmap; const int32_t* ymap;
+    double* H; int64_t ldh, h_bstride; AlphaDev alpha;
+};
+void launch_scatter_sym(const ScatterSymArgs& a, int64_t batch, cudaStream_t stream);
+void launch_fill(double* p, int64_t n, double v, cudaStream_t stream);
+
+}  // namespace pmb

@@ -1,0 +1,788 @@
+// Launch planner and run loop of the C ABI: the device restatement of
+//   initialize!(m)  model.jl:117-122 (+ mapindices! :100-107)   -> pmb_initialize: static index tables, buffers, CUDA graph
+//   update!(m)      model.jl:132-143                             -> pmb_update: every Parameter once, objective, then the
+//                                                                   constraint blocks in bucket order (moi_interop.jl:180-193,236-247)
+//   MOI.set(...)    moi_interop.jl:134,171                       -> pmb_get_objective / pmb_get_block device views
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "pmb_host.h"
+
+namespace pmb {
+
+void configure_gram_kernels();  // kernels_gram.cu
+
+// ---- device memory ---------------------------------------------------------------------------
+template <class T>
+static T* dalloc(pmb_ctx* c, int64_t count, bool zero = false) {
+    if (count <= 0) return nullptr;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)count * sizeof(T));
+    if (e != cudaSuccess) fail(PMB_ENOMEM, "cudaMalloc of %lld bytes failed: %s", (long long)(count * sizeof(T)), cudaGetErrorString(e));
+    c->allocs.push_back(p);
+    c->bytes_alloc += count * (int64_t)sizeof(T);
+    if (zero) CK(cudaMemsetAsync(p, 0, (size_t)count * sizeof(T), c->stream));
+    return (T*)p;
+}
+
+template <class T>
+static T* upload(pmb_ctx* c, const std::vector<T>& v) {
+    if (v.empty()) return nullptr;
+    T* d = dalloc<T>(c, (int64_t)v.size());
+    // synchronous copy: `v` is usually a temporary
+    CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+static AlphaDev alpha_dev(pmb_ctx* c, const Alpha& a) {
+    AlphaDev d;
+    d.c = a.c; d.ptr = nullptr; d.bstride = 0;
+    if (a.node >= 0) {
+        const Node& n = c->nodes[a.node];
+        d.ptr = n.dptr; d.bstride = n.bstride;
+    }
+    return d;
+}
+
+static int32_t optcol(pmb_ctx* c, int64_t var) { return (int32_t)(c->varmap[(size_t)(var - 1)] - 1); }
+
+// ---- reachability ----------------------------------------------------------------------------
+static void mark(pmb_ctx* c, int id) {
+    if (id < 0) return;
+    Node& n = c->nodes[id];
+    if (n.needed) return;
+    n.needed = true;
+    for (int i : n.in) mark(c, i);
+    for (auto& t : n.lin) { mark(c, t.src); mark(c, t.a.node); }
+}
+static void mark_aff(pmb_ctx* c, const AffForm& f) {
+    for (auto& t : f.mats) { mark(c, t.mat); mark(c, t.a.node); }
+    for (auto& t : f.units) mark(c, t.a.node);
+    for (auto& t : f.offs) { mark(c, t.vec); mark(c, t.a.node); }
+}
+static void mark_quad(pmb_ctx* c, const QuadForm& q) {
+    for (auto& g : q.grams) { mark(c, g.a.node); mark_aff(c, g.f); mark_aff(c, g.h); }
+    for (auto& b : q.bilins) { mark(c, b.a.node); mark(c, b.mat); }
+    for (auto& t : q.coos) mark(c, t.a.node);
+    mark_aff(c, q.aff);
+}
+
+// ---- numeric nodes -> buffers + steps -----------------------------------------------------------
+static int64_t src_ld(const Node& n) { return n.kind == PMB_KIND_NUM_MATRIX ? n.rows : 1; }
+
+static void plan_numeric(pmb_ctx* c, int id) {
+    Node& n = c->nodes[id];
+    n.numel = numel_of(n);
+    std::vector<Step>& dst = n.is_const ? c->init_steps : c->steps;
+    const int64_t nb = n.is_const ? 1 : c->batch;
+    if (n.nop == NOP_CONST) {
+        n.dptr = upload(c, n.cvals);
+        n.bstride = 0; n.owned = true;
+        return;
+    }
+    if (n.nop == NOP_PARAM) {
+        n.bstride = n.numel;
+        if (n.pmode == PMB_PARAM_DEVICE && n.ext) {
+            n.dptr = const_cast<double*>(n.ext);
+        } else {
+            n.dptr = dalloc<double>(c, c->batch * n.numel, true);
+            n.owned = true;
+        }
+        if (n.pmode == PMB_PARAM_UNIFORM) {
+            Step s;
+            s.type = ST_PHILOX; s.cls = KC_PHILOX; s.batch = c->batch;
+            s.out = n.dptr; s.n = n.numel; s.seed = n.seed; s.scale = n.scale;
+            c->steps.push_back(s);
+        }
+        return;
+    }
+    n.dptr = dalloc<double>(c, nb * n.numel);
+    n.bstride = n.is_const ? 0 : n.numel;
+    n.owned = true;
+    Step s;
+    s.batch = nb;
+    switch (n.nop) {
+        case NOP_LINCOMB: {
+            std::vector<LinCombTermDev> lt;
+            for (auto& t : n.lin) {
+                const Node& sn = c->nodes[t.src];
+                lt.push_back(LinCombTermDev{sn.dptr, sn.bstride, t.src_off, alpha_dev(c, t.a)});
+            }
+            s.type = ST_LINCOMB; s.cls = KC_MISC;
+            s.out = n.dptr; s.out_bstride = n.bstride; s.n = n.numel;
+            s.lterms = upload(c, lt); s.nl = (int)lt.size(); s.cst = nullptr;
+            break;
+        }
+        case NOP_TRANSPOSE: {
+            const Node& a = c->nodes[n.in[0]];
+            s.type = ST_TRANSPOSE; s.cls = KC_MISC;
+            s.out = n.dptr; s.out_bstride = n.bstride; s.src = a.dptr; s.src_bstride = a.bstride; s.n = a.rows; s.n2 = a.cols;
+            break;
+        }
+        case NOP_GEMV: {
+            const Node& a = c->nodes[n.in[0]];
+            const Node& v = c->nodes[n.in[1]];
+            s.type = ST_GEMV; s.cls = KC_REDUCE;
+            GemvArgs g{};
+            g.A = a.dptr + n.gemv_col_off * a.rows; g.lda = a.rows; g.a_bstride = a.bstride;
+            g.rows = a.rows; g.cols = n.gemv_cols; g.trans = n.gemv_trans;
+            g.v = v.dptr; g.v_bstride = v.bstride; g.v_off = n.gemv_v_off;
+            g.y = n.dptr; g.y_bstride = n.bstride; g.map = nullptr; g.scale = AlphaDev{1.0, nullptr, 0}; g.accumulate = 0;
+            s.gemv = g;
+            break;
+        }
+        case NOP_DOT: {
+            const Node& x = c->nodes[n.in[0]];
+            const Node& y = c->nodes[n.in[1]];
+            s.type = ST_DOT; s.cls = KC_REDUCE;
+            DotArgs d{};
+            d.x = x.dptr; d.x_bstride = x.bstride; d.x_off = n.dot_xoff;
+            d.y = y.dptr; d.y_bstride = y.bstride; d.y_off = n.dot_yoff;
+            d.n = n.dot_n; d.out = n.dptr; d.out_bstride = n.bstride; d.scale = AlphaDev{1.0, nullptr, 0}; d.accumulate = 0;
+            s.dot = d;
+            break;
+        }
+        case NOP_SPROD: {
+            s.type = ST_SPROD; s.cls = KC_MISC;
+            s.out = n.dptr; s.out_bstride = n.bstride; s.scale = n.sprod_c;
+            const Node& a = c->nodes[n.in[0]];
+            s.s0 = a.dptr; s.s0_bs = a.bstride;
+            if (n.in.size() > 1) { const Node& b = c->nodes[n.in[1]]; s.s1 = b.dptr; s.s1_bs = b.bstride; }
+            break;
+        }
+        case NOP_GEMM_TN: {
+            const Node& x = c->nodes[n.in[0]];  // X (k_total x n), rows [gm_xoff, gm_xoff + gm_k)
+            const Node& y = c->nodes[n.in[1]];  // Y (gm_k x *), columns [gm_yoff, gm_yoff + p)
+            s.type = ST_GEMM; s.cls = KC_GEMM;
+            GemmTNArgs g{};
+            g.X = x.dptr + n.gm_xoff; g.ldx = x.rows; g.x_bstride = x.bstride;
+            g.Y = y.dptr + n.gm_yoff * y.rows; g.ldy = y.rows; g.y_bstride = y.bstride;
+            g.k = n.gm_k; g.n = n.rows; g.p = n.cols;
+            g.M = n.dptr; g.ldm = n.rows; g.m_bstride = n.bstride;
+            s.gemm = g;
+            break;
+        }
+        default: fail(PMB_EINVAL, "internal: numeric node %d has no plan", id);
+    }
+    dst.push_back(s);
+}
+
+// ---- AffForm -> AffBlockDev ------------------------------------------------------------------
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// compact == true: output columns are the ranks of the touched optimizer columns (scratch operand of a Gram);
+// *touched receives the touched optimizer columns (ascending).
+static AffBlockDev lower_aff(pmb_ctx* c, const AffForm& f, double* C, int64_t C_bstride, double* d, int64_t d_bstride, bool compact,
+                             std::vector<int32_t>* touched) {
+    std::map<int32_t, std::vector<AffColEntry>> cols;
+    for (size_t t = 0; t < f.mats.size(); ++t) {
+        const MatTerm& m = f.mats[t];
+        for (int64_t j = 0; j < m.cols; ++j) cols[optcol(c, m.vars[(size_t)j])].push_back(AffColEntry{(int32_t)t, (int32_t)(m.src_col_off + j)});
+    }
+    for (size_t u = 0; u < f.units.size(); ++u) {
+        const UnitTerm& ut = f.units[u];
+        for (int64_t r = 0; r < ut.rows; ++r) cols[optcol(c, ut.vars[(size_t)r])].push_back(AffColEntry{~(int32_t)u, (int32_t)(ut.row_off + r)});
+    }
+    std::vector<int32_t> col_out, col_ptr{0}, col_src;
+    std::vector<AffColEntry> entries;
+    bool simple = f.mats.size() == 1 && f.units.empty() && f.mats[0].row_off == 0 && f.mats[0].rows == f.rows;
+    int32_t rank = 0;
+    for (auto& kv : cols) {
+        col_out.push_back(compact ? rank : kv.first);
+        if (touched) touched->push_back(kv.first);
+        for (auto& e : kv.second) entries.push_back(e);
+        col_ptr.push_back((int32_t)entries.size());
+        if (kv.second.size() != 1) simple = false;
+        col_src.push_back(kv.second[0].src);
+        ++rank;
+    }
+    std::vector<AffMatTermDev> mats;
+    for (auto& m : f.mats) {
+        const Node& sn = c->nodes[m.mat];
+        mats.push_back(AffMatTermDev{sn.dptr, sn.bstride, src_ld(sn), m.row_off, m.rows, alpha_dev(c, m.a)});
+    }
+    std::vector<AffUnitTermDev> units;
+    for (auto& u : f.units) units.push_back(AffUnitTermDev{alpha_dev(c, u.a)});
+    std::vector<AffOffTermDev> offs;
+    for (auto& o : f.offs) {
+        const Node& sn = c->nodes[o.vec];
+        offs.push_back(AffOffTermDev{sn.dptr, sn.bstride, o.src_off, o.row_off, o.rows, alpha_dev(c, o.a)});
+    }
+    AffBlockDev b{};
+    b.C = C; b.d = d; b.C_bstride = C_bstride; b.d_bstride = d_bstride; b.rows = f.rows;
+    b.ntouched = (int32_t)col_out.size();
+    b.col_out = upload(c, col_out);
+    b.col_ptr = upload(c, col_ptr);
+    b.entries = upload(c, entries);
+    b.mats = upload(c, mats);
+    b.units = upload(c, units);
+    b.noffs = (int32_t)offs.size();
+    b.offs = upload(c, offs);
+    bool anyc = false;
+    for (double v : f.coff) anyc = anyc || v != 0.0;
+    b.d_const = anyc ? upload(c, f.coff) : nullptr;
+    b.simple = simple && b.ntouched > 0 ? 1 : 0;
+    b.col_src = upload(c, col_src);
+    b.vec2 = 0;
+    if (b.simple) {
+        const AffMatTermDev& m = mats[0];
+        b.vec2 = (f.rows % 2 == 0 && m.ld % 2 == 0 && m.src_bstride % 2 == 0 && C_bstride % 2 == 0 && aligned16(m.src) && aligned16(C)) ? 1 : 0;
+    }
+    return b;
+}
+
+static int64_t aff_nterms(const AffForm& f) {
+    int64_t n = 0;
+    for (auto& m : f.mats) n += m.rows * m.cols;
+    for (auto& u : f.units) n += u.rows;
+    return n;
+}
+
+static Step affine_step(const AffBlockDev& b, int64_t batch) {
+    Step s;
+    s.type = ST_AFFINE; s.cls = KC_AFFINE; s.batch = batch; s.aff = b;
+    return s;
+}
+
+// ---- objective ---------------------------------------------------------------------------------
+struct DenseSide {
+    const double* X = nullptr;
+    int64_t ldx = 0, xbs = 0, ncols = 0, k = 0;
+    const int32_t* map = nullptr;
+    const double* g = nullptr;  // offsets (k), null when identically zero
+    int64_t gbs = 0;
+    double cx = 1.0;
+};
+
+static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps, int64_t nb) {
+    DenseSide s;
+    s.k = f.rows;
+    const bool has_off = !f.offs.empty() || std::any_of(f.coff.begin(), f.coff.end(), [](double v) { return v != 0.0; });
+    bool direct = f.mats.size() == 1 && f.units.empty() && f.mats[0].a.node < 0 && f.mats[0].row_off == 0 && f.mats[0].rows == f.rows &&
+                  c->nodes[f.mats[0].mat].kind == PMB_KIND_NUM_MATRIX;
+    std::vector<int32_t> map;
+    if (direct) {
+        for (int64_t v : f.mats[0].vars) map.push_back(optcol(c, v));
+        std::vector<int32_t> sorted = map;
+        std::sort(sorted.begin(), sorted.end());
+        direct = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
+    }
+    double* g = has_off ? dalloc<double>(c, nb * f.rows) : nullptr;
+    if (direct) {
+        const MatTerm& m = f.mats[0];
+        const Node& sn = c->nodes[m.mat];
+        s.X = sn.dptr + m.src_col_off * sn.rows; s.ldx = sn.rows; s.xbs = sn.bstride; s.ncols = m.cols; s.cx = m.a.c;
+        s.map = upload(c, map);
+        if (has_off) {
+            AffForm only_off;
+            only_off.rows = f.rows; only_off.offs = f.offs; only_off.coff = f.coff;
+            steps.push_back(affine_step(lower_aff(c, only_off, nullptr, 0, g, f.rows, true, nullptr), nb));
+        }
+    } else {
+        // materialise the operand as a compact dense block (the affine-assembly kernel sums duplicate variables per column)
+        std::vector<int32_t> touched;
+        int64_t nt = 0;
+        {
+            std::map<int32_t, int> seen;
+            for (auto& m : f.mats) for (int64_t v : m.vars) seen[optcol(c, v)] = 1;
+            for (auto& u : f.units) for (int64_t v : u.vars) seen[optcol(c, v)] = 1;
+            nt = (int64_t)seen.size();
+        }
+        double* X = dalloc<double>(c, nb * f.rows * nt, true);
+        double* gg = g ? g : dalloc<double>(c, nb * f.rows);
+        steps.push_back(affine_step(lower_aff(c, f, X, f.rows * nt, gg, f.rows, true, &touched), nb));
+        s.X = X; s.ldx = f.rows; s.xbs = f.rows * nt; s.ncols = nt; s.cx = 1.0;
+        s.map = upload(c, touched);
+    }
+    s.g = g; s.gbs = f.rows;
+    return s;
+}
+
+static AlphaDev scaled(AlphaDev a, double k) { a.c *= k; return a; }
+
+static void plan_objective(pmb_ctx* c) {
+    const int64_t N = c->nvars, nb = c->batch;
+    double* qc = dalloc<double>(c, nb * (N + 1), true);
+    c->q = qc;
+    c->c0 = qc + nb * N;
+    if (c->obj_node < 0) { c->obj_const = true; c->obj_kind = PMB_KIND_AFF; return; }  // default objective: zero AffineFunction (model.jl:18)
+    QuadForm qf = quad_of(c, c->obj_node);
+    std::vector<Step>& st = c->obj_const ? c->init_steps : c->steps;
+    const bool has_quad = !qf.grams.empty() || !qf.bilins.empty() || !qf.coos.empty();
+    if (c->obj_kind == PMB_KIND_QUAD) c->Q = dalloc<double>(c, nb * N * N, true);
+    // (q, c0) <- 0, then the affine part overwrites its touched columns, then the quadratic terms accumulate
+    Step z;
+    z.type = ST_MEMSET; z.cls = KC_MISC; z.out = qc; z.n = nb * (N + 1);
+    st.push_back(z);
+    if (qf.aff.rows == 0) qf.aff.rows = 1;
+    if (!qf.aff.mats.empty() || !qf.aff.units.empty() || !qf.aff.offs.empty() || !qf.aff.coff.empty())
+        st.push_back(affine_step(lower_aff(c, qf.aff, c->q, N, c->c0, 1, false, nullptr), nb));
+    if (!has_quad) return;
+    const bool overwrite = qf.grams.size() == 1 && qf.grams[0].same && qf.bilins.empty() && qf.coos.empty();
+    if (!overwrite) {
+        Step zq;
+        zq.type = ST_MEMSET; zq.cls = KC_MISC; zq.out = c->Q; zq.n = nb * N * N;
+        st.push_back(zq);
+    }
+    for (auto& gt : qf.grams) {
+        const AlphaDev a = alpha_dev(c, gt.a);
+        if (gt.f.rows != gt.h.rows) fail(PMB_EDIM, "DimensionMismatch in dot");
+        DenseSide F = densify(c, gt.f, st, nb);
+        if (gt.same) {
+            // H[map, map] (+)= 2 a cx^2 X'X ;  q[map] += 2 a cx X'g ;  c0 += a g.g
+            Step s;
+            s.type = ST_GRAM; s.cls = KC_GRAM; s.batch = nb;
+            GramArgs ga{};
+            ga.X = F.X; ga.ldx = F.ldx; ga.x_bstride = F.xbs; ga.k = F.k; ga.n = F.ncols;
+            ga.H = c->Q; ga.ldh = N; ga.h_bstride = N * N; ga.map = F.map;
+            ga.scale = scaled(a, 2.0 * F.cx * F.cx); ga.accumulate = overwrite ? 0 : 1;
+            s.gram = ga;
+            st.push_back(s);
+            c->gram_flops += F.k * F.ncols * (F.ncols + 1) + 2 * F.k * F.ncols + 2 * F.k;
+            if (F.g) {
+                Step v;
+                v.type = ST_GEMV; v.cls = KC_REDUCE; v.batch = nb;
+                GemvArgs g{};
+                g.A = F.X; g.lda = F.ldx; g.a_bstride = F.xbs; g.rows = F.k; g.cols = F.ncols; g.trans = 1;
+                g.v = F.g; g.v_bstride = F.gbs; g.v_off = 0; g.y = c->q; g.y_bstride = N; g.map = F.map;
+                g.scale = scaled(a, 2.0 * F.cx); g.accumulate = 1;
+                v.gemv = g;
+                st.push_back(v);
+                Step dd;
+                dd.type = ST_DOT; dd.cls = KC_REDUCE; dd.batch = nb;
+                DotArgs d{};
+                d.x = F.g; d.x_bstride = F.gbs; d.y = F.g; d.y_bstride = F.gbs; d.n = F.k; d.out = c->c0; d.out_bstride = 1;
+                d.scale = a; d.accumulate = 1;
+                dd.dot = d;
+                st.push_back(dd);
+            }
+        } else {
+            // M = Xf' Xh (scratch);  H[mf[i], mh[j]] += a M ; H[mh[j], mf[i]] += a M ;  q[mf] += a Xf' gh ; q[mh] += a Xh' gf ; c0 += a gf.gh
+            DenseSide Hs = densify(c, gt.h, st, nb);
+            double* M = dalloc<double>(c, nb * F.ncols * Hs.ncols);
+            Step s;
+            s.type = ST_GEMM; s.cls = KC_GEMM; s.batch = nb;
+            GemmTNArgs gm{};
+            gm.X = F.X; gm.ldx = F.ldx; gm.x_bstride = F.xbs; gm.Y = Hs.X; gm.ldy = Hs.ldx; gm.y_bstride = Hs.xbs;
+            gm.k = F.k; gm.n = F.ncols; gm.p = Hs.ncols; gm.M = M; gm.ldm = F.ncols; gm.m_bstride = F.ncols * Hs.ncols;
+            s.gemm = gm;
+            st.push_back(s);
+            Step sc;
+            sc.type = ST_SCATTER_SYM; sc.cls = KC_MISC; sc.batch = nb;
+            ScatterSymArgs ss{};
+            ss.M = M; ss.ldm = F.ncols; ss.m_bstride = F.ncols * Hs.ncols; ss.n = F.ncols; ss.p = Hs.ncols; ss.xmap = F.map; ss.ymap = Hs.map;
+            ss.H = c->Q; ss.ldh = N; ss.h_bstride = N * N; ss.alpha = scaled(a, F.cx * Hs.cx);
+            sc.ss = ss;
+            st.push_back(sc);
+            c->gram_flops += 2 * F.k * F.ncols * Hs.ncols + 2 * F.k * (F.ncols + Hs.ncols) + 2 * F.k;
+            auto gemv_q = [&](const DenseSide& X, const DenseSide& G) {
+                if (!G.g) return;
+                Step v;
+                v.type = ST_GEMV; v.cls = KC_REDUCE; v.batch = nb;
+                GemvArgs g{};
+                g.A = X.X; g.lda = X.ldx; g.a_bstride = X.xbs; g.rows = X.k; g.cols = X.ncols; g.trans = 1;
+                g.v = G.g; g.v_bstride = G.gbs; g.v_off = 0; g.y = c->q; g.y_bstride = N; g.map = X.map;
+                g.scale = scaled(a, X.cx); g.accumulate = 1;
+                v.gemv = g;
+                st.push_back(v);
+            };
+            gemv_q(F, Hs);
+            gemv_q(Hs, F);
+            if (F.g && Hs.g) {
+                Step dd;
+                dd.type = ST_DOT; dd.cls = KC_REDUCE; dd.batch = nb;
+                DotArgs d{};
+                d.x = F.g; d.x_bstride = F.gbs; d.y = Hs.g; d.y_bstride = Hs.gbs; d.n = F.k; d.out = c->c0; d.out_bstride = 1;
+                d.scale = a; d.accumulate = 1;
+                dd.dot = d;
+                st.push_back(dd);
+            }
+        }
+    }
+    for (auto& bt : qf.bilins) {
+        const Node& qn = c->nodes[bt.mat];
+        std::vector<int32_t> xm, ym;
+        for (int64_t v : bt.xv) xm.push_back(optcol(c, v));
+        for (int64_t v : bt.yv) ym.push_back(optcol(c, v));
+        Step s;
+        s.type = ST_BILINEAR; s.cls = KC_MISC; s.batch = nb;
+        BilinearArgs b{};
+        b.Q = qn.dptr; b.ldq = qn.rows; b.q_bstride = qn.bstride; b.nx = (int64_t)xm.size(); b.ny = (int64_t)ym.size();
+        b.xmap = upload(c, xm); b.ymap = upload(c, ym);
+        b.H = c->Q; b.ldh = N; b.h_bstride = N * N; b.alpha = alpha_dev(c, bt.a);
+        s.bl = b;
+        st.push_back(s);
+    }
+    for (auto& ct : qf.coos) {
+        std::vector<int32_t> ii, jj;
+        for (int64_t v : ct.i) ii.push_back(optcol(c, v));
+        for (int64_t v : ct.j) jj.push_back(optcol(c, v));
+        Step s;
+        s.type = ST_COO; s.cls = KC_MISC; s.batch = nb;
+        CooQuadArgs q{};
+        q.i = upload(c, ii); q.j = upload(c, jj); q.c = upload(c, ct.c); q.nnz = (int64_t)ii.size();
+        q.H = c->Q; q.ldh = N; q.h_bstride = N * N; q.alpha = alpha_dev(c, ct.a);
+        s.coo = q;
+        st.push_back(s);
+    }
+}
+
+// ---- run ---------------------------------------------------------------------------------------
+static void run_step(pmb_ctx* c, const Step& s) {
+    cudaStream_t st = c->stream;
+    switch (s.type) {
+        case ST_TICK: launch_tick(c->d_counter, st); break;
+        case ST_PHILOX: launch_philox_uniform(s.out, s.n, s.batch, s.seed, s.scale, c->d_counter, c->sm_count, st); break;
+        case ST_MEMSET: CK(cudaMemsetAsync(s.out, 0, (size_t)s.n * sizeof(double), st)); break;
+        case ST_LINCOMB: launch_lincomb(s.out, s.out_bstride, s.n, s.lterms, s.nl, s.cst, s.batch, st); break;
+        case ST_TRANSPOSE: launch_transpose(s.out, s.out_bstride, s.src, s.src_bstride, s.n, s.n2, s.batch, st); break;
+        case ST_GEMV: launch_gemv(s.gemv, s.batch, st); break;
+        case ST_DOT: launch_dot(s.dot, s.batch, st); break;
+        case ST_SPROD: launch_scalar_prod(s.out, s.out_bstride, s.scale, s.s0, s.s0_bs, s.s1, s.s1_bs, s.batch, st); break;
+        case ST_AFFINE: launch_affine_assemble(s.aff, s.batch, c->sm_count, st); break;
+        case ST_GRAM: launch_gram_syrk(s.gram, s.batch, c->sm_count, st); break;
+        case ST_GEMM: launch_gemm_tn(s.gemm, s.batch, c->sm_count, st); break;
+        case ST_SCATTER_VEC: launch_scatter_vec(s.sv, s.batch, st); break;
+        case ST_BILINEAR: launch_bilinear_scatter(s.bl, s.batch, st); break;
+        case ST_COO: launch_coo_quad(s.coo, s.batch, st); break;
+        case ST_SCATTER_SYM: launch_scatter_sym(s.ss, s.batch, st); break;
+        default: fail(PMB_EINVAL, "internal: unknown step type %d", s.type);
+    }
+    CK(cudaGetLastError());
+}
+
+static void collect_timing(pmb_ctx* c) {
+    if (!c->ev_pending) return;
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < c->steps.size(); ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]));
+        c->cls_ms[c->steps[i].cls] += ms;
+        c->cls_launches[c->steps[i].cls] += 1;
+    }
+    c->ev_pending = false;
+}
+
+}  // namespace pmb
+
+using namespace pmb;
+
+static const char* kClassNames[KC_COUNT] = {"affine_assemble", "gram_dmma", "gemm_tn_dmma", "philox_uniform", "h2d_stage", "reduce", "misc"};
+
+extern "C" {
+
+const char* pmb_version(void) { return "parametron-b200 0.1 (sm_100a)"; }
+
+int pmb_ctx_create(int device, void* stream, int64_t batch, pmb_ctx** out) {
+    if (!out || batch < 1) return PMB_EINVAL;
+    *out = nullptr;
+    pmb_ctx* c = new (std::nothrow) pmb_ctx();
+    if (!c) return PMB_ENOMEM;
+    auto bail = [&](int code) { delete c; return code; };
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return bail(PMB_ECUDA);  // no silent CPU fallback: fail loudly
+    if (device < 0 || device >= ndev) return bail(PMB_EINVAL);
+    if (cudaSetDevice(device) != cudaSuccess) return bail(PMB_ECUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(PMB_ECUDA);
+    if (prop.major != 10) return bail(PMB_EUNSUPPORTED);  // kernels are sm_100a-only
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->batch = batch;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PMB_ECUDA);
+        c->own_stream = true;
+    }
+    configure_gram_kernels();
+    const char* ng = getenv("PMB_NO_GRAPH");
+    c->use_graph = !(ng && ng[0] == '1');
+    *out = c;
+    return PMB_OK;
+}
+
+int pmb_ctx_destroy(pmb_ctx* c) {
+    if (!c) return PMB_EINVAL;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    for (auto e : c->ev) cudaEventDestroy(e);
+    for (void* p : c->allocs) cudaFree(p);
+    for (void* p : c->pinned) cudaFreeHost(p);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return PMB_OK;
+}
+
+const char* pmb_last_error(const pmb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
+    API_BEGIN(ctx)
+    if (ctx->initialized) fail(PMB_EINITIALIZED, "Model has already been initialized.");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t N = ctx->nvars;
+    // mapindices! (model.jl:100-107): model variable -> optimizer variable; must be a permutation of 1..N
+    ctx->varmap.resize((size_t)N);
+    {
+        std::vector<char> seen((size_t)N, 0);
+        for (int64_t i = 0; i < N; ++i) {
+            int64_t v = varmap ? varmap[i] : i + 1;
+            if (v < 1 || v > N || seen[(size_t)(v - 1)]) fail(PMB_EINVAL, "varmap is not a permutation of 1..%lld", (long long)N);
+            seen[(size_t)(v - 1)] = 1;
+            ctx->varmap[(size_t)i] = v;
+        }
+    }
+    // update order: bucket order, insertion order within a bucket (moi_interop.jl:180-193, 236-247)
+    ctx->update_order.clear();
+    for (int b = 0; b < 9; ++b)
+        for (size_t i = 0; i < ctx->cons.size(); ++i)
+            if (ctx->cons[i].bucket == b) ctx->update_order.push_back((int)i);
+    // which numeric nodes are live
+    if (ctx->obj_node >= 0) mark_quad(ctx, quad_of(ctx, ctx->obj_node));
+    for (auto& con : ctx->cons) mark_aff(ctx, con.form);
+    bool any_uniform = false;
+    for (auto& n : ctx->nodes) any_uniform = any_uniform || (n.needed && n.nop == NOP_PARAM && n.pmode == PMB_PARAM_UNIFORM);
+    ctx->d_counter = (unsigned long long*)dalloc<unsigned long long>(ctx, 1, true);
+    if (any_uniform) {
+        Step s;
+        s.type = ST_TICK; s.cls = KC_MISC;
+        ctx->steps.push_back(s);
+    }
+    const size_t nn = ctx->nodes.size();
+    for (size_t i = 0; i < nn; ++i)
+        if (ctx->nodes[i].needed && is_numeric(ctx->nodes[i].kind)) plan_numeric(ctx, (int)i);
+    plan_objective(ctx);
+    for (int ci : ctx->update_order) {
+        Constraint& con = ctx->cons[(size_t)ci];
+        con.C = dalloc<double>(ctx, ctx->batch * con.rows * N, true);
+        con.d = dalloc<double>(ctx, ctx->batch * con.rows, true);
+        con.nterms = aff_nterms(con.form);
+        AffBlockDev b = lower_aff(ctx, con.form, con.C, con.rows * N, con.d, con.rows, false, nullptr);
+        (con.is_const ? ctx->init_steps : ctx->steps).push_back(affine_step(b, ctx->batch));
+        if (!con.is_const) ctx->affine_bytes += 16 * (int64_t)b.ntouched * con.rows + 16 * con.rows;
+    }
+    ctx->launches_per_update = 0;
+    ctx->memcpy_per_update = 0;
+    for (auto& s : ctx->steps) if (s.type != ST_MEMSET) ctx->launches_per_update += 1;
+    for (auto& n : ctx->nodes) if (n.needed && n.nop == NOP_PARAM && n.pmode == PMB_PARAM_HOST) ctx->memcpy_per_update += 1;
+    // constants: evaluated exactly once (constant folding lazyexpression.jl:189-192; isconstant moi_interop.jl:123,153)
+    for (auto& s : ctx->init_steps) run_step(ctx, s);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->use_graph && !ctx->steps.empty()) {
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            for (auto& s : ctx->steps) run_step(ctx, s);
+        } catch (...) {
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(ctx->stream, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        CK(cudaStreamEndCapture(ctx->stream, &ctx->graph));
+        CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
+    }
+    ctx->initialized = true;
+    API_END(ctx)
+}
+
+int pmb_update(pmb_ctx* ctx) {
+    API_BEGIN(ctx)
+    if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_update before pmb_initialize");
+    // setdirty! + evaluate every Parameter exactly once (model.jl:133, parameter.jl:93-104)
+    for (auto& n : ctx->nodes) {
+        if (!n.needed || n.nop != NOP_PARAM || n.pmode != PMB_PARAM_HOST) continue;
+        if (!n.hptr) fail(PMB_EINVAL, "host Parameter has no buffer (pmb_param_set_host_ptr)");
+        if (n.cb) n.cb(n.hptr, n.rows, n.cols, ctx->batch, n.user);
+        CK(cudaMemcpyAsync(n.dptr, n.hptr, (size_t)(ctx->batch * n.numel) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (ctx->timing) {
+        collect_timing(ctx);
+        for (size_t i = 0; i < ctx->steps.size(); ++i) {
+            CK(cudaEventRecord(ctx->ev[2 * i], ctx->stream));
+            run_step(ctx, ctx->steps[i]);
+            CK(cudaEventRecord(ctx->ev[2 * i + 1], ctx->stream));
+        }
+        ctx->ev_pending = true;
+    } else if (ctx->graph_exec) {
+        CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+    } else {
+        for (auto& s : ctx->steps) run_step(ctx, s);
+    }
+    ctx->updates += 1;
+    API_END(ctx)
+}
+
+int pmb_synchronize(pmb_ctx* ctx) {
+    API_BEGIN(ctx)
+    CK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+int pmb_update_count(const pmb_ctx* ctx, int64_t* n) {
+    if (!ctx || !n) return PMB_EINVAL;
+    *n = ctx->updates;
+    return PMB_OK;
+}
+
+int pmb_param_upload(pmb_ctx* ctx, pmb_node p, const double* host_values) {
+    API_BEGIN(ctx)
+    if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_param_upload before pmb_initialize");
+    Node& n = node_at(ctx, p);
+    if (n.nop != NOP_PARAM || !n.needed || !n.dptr) fail(PMB_EINVAL, "node %d is not a live Parameter", p);
+    CK(cudaMemcpyAsync(n.dptr, host_values, (size_t)(ctx->batch * n.numel) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    API_END(ctx)
+}
+
+int pmb_param_device_ptr(pmb_ctx* ctx, pmb_node p, double** dptr) {
+    API_BEGIN(ctx)
+    if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_param_device_ptr before pmb_initialize");
+    Node& n = node_at(ctx, p);
+    if (n.nop != NOP_PARAM || !dptr) fail(PMB_EINVAL, "node %d is not a Parameter", p);
+    *dptr = n.dptr;  // null when the Parameter is not reachable from the objective or a constraint
+    API_END(ctx)
+}
+
+int pmb_get_objective(pmb_ctx* ctx, pmb_objective_view* out) {
+    API_BEGIN(ctx)
+    if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_get_objective before pmb_initialize");
+    if (!out) fail(PMB_EINVAL, "null out");
+    out->kind = ctx->obj_kind; out->sense = ctx->obj_sense; out->is_constant = ctx->obj_const ? 1 : 0;
+    out->nvars = ctx->nvars; out->Q = ctx->Q; out->q = ctx->q; out->c0 = ctx->c0;
+    API_END(ctx)
+}
+
+int pmb_num_blocks(const pmb_ctx* ctx, int32_t* n) {
+    if (!ctx || !n) return PMB_EINVAL;
+    *n = (int32_t)ctx->cons.size();
+    return PMB_OK;
+}
+
+static Constraint& block_at(pmb_ctx* ctx, int32_t pos) {
+    if (!ctx->initialized) fail(PMB_ENOTINIT, "block query before pmb_initialize");
+    if (pos < 0 || pos >= (int32_t)ctx->update_order.size()) fail(PMB_EINVAL, "block position %d out of range", pos);
+    return ctx->cons[(size_t)ctx->update_order[(size_t)pos]];
+}
+
+int pmb_get_block(pmb_ctx* ctx, int32_t update_pos, pmb_block_view* out) {
+    API_BEGIN(ctx)
+    if (!out) fail(PMB_EINVAL, "null out");
+    Constraint& con = block_at(ctx, update_pos);
+    out->set_kind = con.set_kind; out->is_scalar = con.is_scalar ? 1 : 0; out->is_constant = con.is_const ? 1 : 0;
+    out->bucket = con.bucket; out->rows = con.rows; out->nvars = ctx->nvars; out->C = con.C; out->d = con.d; out->nterms = con.nterms;
+    API_END(ctx)
+}
+
+int pmb_block_term_index(pmb_ctx* ctx, int32_t update_pos, int64_t capacity, int64_t* rows, int64_t* vars, int64_t* src) {
+    API_BEGIN(ctx)
+    Constraint& con = block_at(ctx, update_pos);
+    const AffForm& f = con.form;
+    if (!f.order_exact) fail(PMB_EUNSUPPORTED, "the reference's term order of this block is not reproducible from the device lowering");
+    if (capacity < con.nterms) fail(PMB_EINVAL, "capacity %lld < %lld terms", (long long)capacity, (long long)con.nterms);
+    // update!(::VectorAffineFunction): row-outer, term-inner, varmap applied (moi_interop.jl:64-81)
+    int64_t t = 0;
+    for (int64_t r = 0; r < f.rows; ++r) {
+        for (auto& seg : f.order) {
+            if (seg.is_unit) {
+                const UnitTerm& u = f.units[(size_t)seg.idx[0]];
+                int64_t i = r - u.row_off;
+                if (i < 0 || i >= u.rows) continue;
+                int64_t v = ctx->varmap[(size_t)(u.vars[(size_t)i] - 1)];
+                if (rows) rows[t] = r + 1;
+                if (vars) vars[t] = v;
+                if (src) src[t] = r + (v - 1) * f.rows;
+                ++t;
+            } else {
+                const MatTerm& m0 = f.mats[(size_t)seg.idx[0]];
+                int64_t i = r - m0.row_off;
+                if (i < 0 || i >= m0.rows) continue;
+                for (int64_t j = 0; j < m0.cols; ++j)
+                    for (int mi : seg.idx) {
+                        int64_t v = ctx->varmap[(size_t)(f.mats[(size_t)mi].vars[(size_t)j] - 1)];
+                        if (rows) rows[t] = r + 1;
+                        if (vars) vars[t] = v;
+                        if (src) src[t] = r + (v - 1) * f.rows;
+                        ++t;
+                    }
+            }
+        }
+    }
+    if (t != con.nterms) fail(PMB_EINVAL, "internal: enumerated %lld terms, expected %lld", (long long)t, (long long)con.nterms);
+    API_END(ctx)
+}
+
+int pmb_get_stats(pmb_ctx* ctx, pmb_stats* out) {
+    API_BEGIN(ctx)
+    if (!out) fail(PMB_EINVAL, "null out");
+    out->kernel_launches_per_update = ctx->launches_per_update;
+    out->memcpy_nodes_per_update = ctx->memcpy_per_update;
+    out->device_bytes_allocated = ctx->bytes_alloc;
+    out->uses_cuda_graph = ctx->graph_exec ? 1 : 0;
+    out->affine_algorithmic_bytes = ctx->affine_bytes;
+    out->gram_algorithmic_flops = ctx->gram_flops;
+    API_END(ctx)
+}
+
+int pmb_enable_kernel_timing(pmb_ctx* ctx, int enable) {
+    API_BEGIN(ctx)
+    if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_enable_kernel_timing before pmb_initialize");
+    collect_timing(ctx);
+    if (enable && ctx->ev.empty()) {
+        ctx->ev.resize(2 * ctx->steps.size());
+        for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
+    }
+    if (enable && !ctx->timing) {
+        for (int i = 0; i < KC_COUNT; ++i) { ctx->cls_ms[i] = 0; ctx->cls_launches[i] = 0; }
+    }
+    ctx->timing = enable != 0;
+    API_END(ctx)
+}
+
+int pmb_kernel_class_count(void) { return KC_COUNT; }
+const char* pmb_kernel_class_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? kClassNames[cls] : ""; }
+
+int pmb_kernel_time_ms(pmb_ctx* ctx, int cls, double* total_ms, int64_t* launches) {
+    API_BEGIN(ctx)
+    if (cls < 0 || cls >= KC_COUNT) fail(PMB_EINVAL, "bad kernel class");
+    collect_timing(ctx);
+    if (total_ms) *total_ms = ctx->cls_ms[cls];
+    if (launches) *launches = ctx->cls_launches[cls];
+    API_END(ctx)
+}
+
+int pmb_host_alloc(pmb_ctx* ctx, size_t bytes, void** out) {
+    API_BEGIN(ctx)
+    if (!out) fail(PMB_EINVAL, "null out");
+    void* p = nullptr;
+    if (bytes > 0) CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    ctx->pinned.push_back(p);
+    *out = p;
+    API_END(ctx)
+}
+
+int pmb_host_free(pmb_ctx* ctx, void* p) {
+    API_BEGIN(ctx)
+    auto it = std::find(ctx->pinned.begin(), ctx->pinned.end(), p);
+    if (it == ctx->pinned.end()) fail(PMB_EINVAL, "pointer was not allocated by pmb_host_alloc");
+    ctx->pinned.erase(it);
+    if (p) CK(cudaFreeHost(p));
+    API_END(ctx)
+}
+
+int pmb_memcpy_d2h(pmb_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    API_BEGIN(ctx)
+    if (bytes) CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    API_END(ctx)
+}
+
+int pmb_memcpy_h2d(pmb_ctx* ctx, void* dev, const void* host, size_t bytes) {
+    API_BEGIN(ctx)
+    if (bytes) CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    API_END(ctx)
+}
+
+}  // extern "C"
