@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- QP re-parameterizations/sec (update! + coeff-assemble) at n=4096, m=1024 (BASELINE.json configs[1]).
+
+One "step" = one `update!`: every Parameter (A 4096x4096, b, C 1024x4096, d) re-evaluated once on the device
+(U[0,1) Philox, the stand-in for the reference's `rand!`, README.md:36-43) + one re-assembly of the objective
+(Q = 2A'A, q = -2A'b, c0 = b'b) and of the constraint block (C, -d), all resident in HBM.
+
+  python bench.py [--gpus N --steps K --warmup W]              this implementation (one instance-shard per GPU, weak scaling)
+  python bench.py --impl reference ...                          the reference's CPU path (literal term-list port, 1 thread)
+
+Prints ONE JSON line (rank 0).  `value` = updates/s with inputs resident in HBM; `e2e` = the same through the C ABI with
+pinned HOST Parameter buffers copied H2D every step and (Q, q, c0, C, d) copied D2H every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_VARS, K_ROWS, M_ROWS = 4096, 4096, 1024
+SEED = 1234
+METRIC = "QP re-parameterizations/sec (update!+coeff-assemble) at n=4096,m=1024"
+FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200: profiles/r01_probe_dmma.txt (mma.sync f64, all SMs)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def declare_model(pm, model, mode, host=None):
+    """README Example 1 at n=4096, m=1024: min ||Ax-b||^2 s.t. Cx == d  (README.md:31-56)."""
+    x = model.variables(N_VARS)
+    shapes = {"A": (K_ROWS, N_VARS), "b": (K_ROWS,), "C": (M_ROWS, N_VARS), "d": (M_ROWS,)}
+    P = {}
+    for i, (name, shp) in enumerate(shapes.items()):
+        if mode == "uniform":
+            P[name] = pm.Parameter(model, shape=shp, uniform=(SEED + i, 2.0 if name == "d" else 1.0))
+        else:
+            P[name] = pm.Parameter(model, val=host[name])  # manual mode, pinned host staging, H2D every update
+    residual = P["A"] * x - P["b"]
+    pm.objective(model, pm.Minimize, pm.dot(residual, residual))
+    pm.constraint(model, P["C"] * x, "==", P["d"])
+    return P
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_termlist_sample(rows=2, reps=1):
+    """The reference's own (term-list) update! restated in C (oracle/termlist.c), 1 thread, on a bounded sample: the constraint
+    part in full, the objective on `rows` of the 4096 residual rows (per-row work is identical: n^2 + 2n terms), scaled by k/rows."""
+    from oracle import philox
+    from oracle.termlist import TermListModel
+    A = np.asfortranarray(philox.uniform_matrix(K_ROWS, N_VARS, SEED))
+    b = philox.uniform(K_ROWS, SEED + 1)
+    Cm = np.asfortranarray(philox.uniform_matrix(M_ROWS, N_VARS, SEED + 2))
+    d = philox.uniform(M_ROWS, SEED + 3, 2.0)
+    t = TermListModel(N_VARS, K_ROWS, M_ROWS)
+    t.update(A, b, Cm, d, row_limit=rows, parts=3)  # first call allocates (the reference's zero-alloc steady state excludes it)
+    best_con = best_obj_rows = best_resid = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter(); t.update(A, b, Cm, d, parts=2); best_con = min(best_con, time.perf_counter() - t0)
+        t0 = time.perf_counter(); t.update(A, b, Cm, d, row_limit=rows, parts=1); t_obj = time.perf_counter() - t0
+        # the residual evaluation (2 x matvecmul!+vecsubtract! over all k rows) is not per-sampled-row work: time it apart
+        t0 = time.perf_counter(); t.update(A, b, Cm, d, row_limit=1, parts=1); t_one = time.perf_counter() - t0
+        per_row = max((t_obj - t_one) / max(rows - 1, 1), 0.0)
+        best_obj_rows = min(best_obj_rows, per_row)
+        best_resid = min(best_resid, max(t_one - per_row, 0.0))
+    t.close()
+    sec = best_con + best_resid + best_obj_rows * K_ROWS
+    return {"seconds_per_update": sec, "constraint_s": best_con, "residual_s": best_resid, "objective_s_per_row": best_obj_rows,
+            "rows_sampled": rows}
+
+
+def cpu_dense_blas(reps=2):
+    """Strongest honest CPU comparator (not the reference's algorithm): dense restatement with OpenBLAS dsyrk/dgemv on all cores."""
+    from scipy.linalg import blas
+    from oracle import philox
+    A = np.asfortranarray(philox.uniform_matrix(K_ROWS, N_VARS, SEED))
+    b = philox.uniform(K_ROWS, SEED + 1)
+    Cm = np.asfortranarray(philox.uniform_matrix(M_ROWS, N_VARS, SEED + 2))
+    d = philox.uniform(M_ROWS, SEED + 3, 2.0)
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        Q = blas.dsyrk(2.0, A, trans=1, lower=0)
+        iu = np.triu_indices(N_VARS, 1)
+        Q[(iu[1], iu[0])] = Q[iu]
+        q = blas.dgemv(-2.0, A, b, trans=1)
+        c0 = float(b @ b)
+        Cb = Cm.copy(order="F")
+        db = -d
+        best = min(best, time.perf_counter() - t0)
+    del Q, q, c0, Cb, db
+    return best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    ncpu = os.cpu_count()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    s = cpu_termlist_sample(rows=2, reps=steps)
+    wall = time.perf_counter() - t0
+    val = 1.0 / s["seconds_per_update"]
+    sample = (f"objective: {s['rows_sampled']} of {K_ROWS} residual rows of vecdot!/MOI copy (per-row work identical, scaled linearly) + "
+              f"full residual evaluation; constraint block in full; best of {steps}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "updates/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "ms_per_step": 1e3 * s["seconds_per_update"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": "cfg2: n=4096, m=1024 dense A,b,C,d (README Example 1 shape)", "host_cores_available": ncpu},
+        "cpu_baseline": {"value": val, "unit": "updates/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "the reference is single-threaded Julia and is absent from this image; oracle/termlist.c is its literal C "
+                                 "restatement (24 B QuadraticTerm per (row,i,j): 1.65 TB per update at this shape, hence the row sample)",
+                         "detail": s, "wall_s": wall},
+        "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    import parametron_b200 as pm
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream().cuda_stream  # the library enqueues on torch's current stream so torch events see it
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- device-resident arm: one independent instance of the model per GPU (instance-shard, no collective) ----
+    model = pm.Model(device=local_rank, batch=1, stream=stream)
+    declare_model(pm, model, "uniform")
+    model.initialize()
+    st = model.stats()
+    for _ in range(args.warmup):
+        model.update()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(model.update, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * 1e3 / ms_per_step
+
+    # ---- per-kernel durations, measured live with CUDA events on the launching stream (eager replay of the same steps) ----
+    model.enable_kernel_timing(True)
+    ksteps = min(args.steps, 20)
+    for _ in range(ksteps):
+        model.update()
+    kt = model.kernel_times()
+    model.enable_kernel_timing(False)
+    gram_ms = kt["gram_dmma"][0] / max(kt["gram_dmma"][1], 1)
+    aff_ms = kt["affine_assemble"][0] / max(kt["affine_assemble"][1], 1)
+    peaks, peak_src = measured_peaks()
+    gram_tflops = st["gram_algorithmic_flops"] / (gram_ms * 1e-3) / 1e12
+    kernel_share = {k: v[0] / max(sum(x[0] for x in kt.values()), 1e-12) for k, v in kt.items()}
+    # one affine-class launch per update here: the constraint block (16 B per stored coefficient + 16 B per row)
+    aff_gbs = st["affine_algorithmic_bytes"] / (aff_ms * 1e-3) / 1e9 if aff_ms > 0 else None
+
+    # ---- e2e arm: HOST Parameter buffers (pinned) -> H2D every step -> update -> D2H of (Q, q, c0, C, d) every step ----
+    e2e = None
+    if not args.no_e2e:
+        from oracle import philox  # noqa: F401  (NOT used to compute anything measured: only fills the synthetic host inputs)
+        em = pm.Model(device=local_rank, batch=1, stream=stream)
+        rng = np.random.default_rng(SEED + rank)
+        host = {"A": rng.random((K_ROWS, N_VARS)), "b": rng.random(K_ROWS), "C": rng.random((M_ROWS, N_VARS)), "d": 2 * rng.random(M_ROWS)}
+        EP = declare_model(pm, em, "host", host)
+        em.initialize()
+        ov, bv = em.objective_view(), em.block_view(0)
+        outs = [(ov.Q, N_VARS * N_VARS), (ov.q, N_VARS), (ov.c0, 1), (bv.C, M_ROWS * N_VARS), (bv.d, M_ROWS)]
+        pinned = [em._pinned((n,)) for _, n in outs]
+        import ctypes as C
+
+        def e2e_step():
+            # the user-facing call: Parameters already written into their pinned host buffers by the caller; pmb_update copies
+            # them H2D and assembles; then the results are read back
+            em._ck(em._lib.pmb_update(em._ctx))
+            for (dptr, n), hb in zip(outs, pinned):
+                em._ck(em._lib.pmb_memcpy_d2h(em._ctx, C.c_void_p(hb.ctypes.data), C.c_void_p(dptr), n * 8))
+            em.synchronize()
+        for _ in range(args.warmup):
+            e2e_step()
+        esteps = max(3, min(args.steps, 20))
+        ems = timed(e2e_step, esteps) / esteps
+        h2d = 8 * (K_ROWS * N_VARS + K_ROWS + M_ROWS * N_VARS + M_ROWS)
+        d2h = 8 * sum(n for _, n in outs)
+        e2e = {"value": world * 1e3 / ems, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems,
+               "steps": esteps}
+        # sanity: the e2e result is the dense meaning of the host inputs (spot check on a few entries, fp64)
+        Qh = pinned[0].reshape(N_VARS, N_VARS)
+        i, j = 17, 2049
+        ref = 2.0 * float(host["A"][:, i] @ host["A"][:, j])
+        assert abs(Qh[j, i] - ref) <= 1e-10 * abs(ref), (Qh[j, i], ref)
+        em.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        s = cpu_termlist_sample(rows=2, reps=2)
+        dense_s = cpu_dense_blas(reps=2)
+        cpu = {"value": 1.0 / s["seconds_per_update"], "unit": "updates/s", "cores": 1, "kind": "port",
+               "sample": (f"oracle/termlist.c (literal term-list update!, single-threaded like the reference): objective on {s['rows_sampled']} of "
+                          f"{K_ROWS} residual rows scaled linearly + full residual evaluation + full constraint block; best of 2"),
+               "detail": s,
+               "dense_blas_all_cores": {"value": 1.0 / dense_s, "unit": "updates/s", "cores": os.cpu_count(),
+                                        "what": "OpenBLAS dsyrk+dgemv+copies (oracle dense restatement; NOT the reference's algorithm)"}}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2: n=4096, m=1024 dense A,b,C,d; min ||Ax-b||^2 s.t. Cx==d (README Example 1 shape); one instance per GPU",
+                       "parameters": "U[0,1) Philox4x32-10 regenerated on device every update (inside the timed step)",
+                       "l2": "inputs_exceed_L2 (A 134 MB + Q 134 MB + C 2x33.5 MB per step; fresh inputs every step)",
+                       "parallelism": f"instance-shard x{world}, no collective"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(st["kernel_launches_per_update"]) * args.steps,
+            "launches_per_update": int(st["kernel_launches_per_update"]), "cuda_graph": bool(st["uses_cuda_graph"]),
+            "roofline": {"bound": "tensor", "kernel": "gram_dmma_kernel (Q = 2A'A, fp64 DMMA pipe)", "achieved": gram_tflops,
+                         "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gram_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                         "algorithmic_flops": int(st["gram_algorithmic_flops"]), "avg_launch_ms": gram_ms,
+                         "peak_source": "fp64 mma.sync (DMMA) peak measured on this pool's B200, profiles/r01_probe_dmma.txt; "
+                                        "MEASURED_PEAKS.json has no fp64 entry and tcgen05 has no f64 kind"},
+            "roofline_affine": {"bound": "hbm", "kernel": "affine_assemble_simple (C, -d)", "achieved": aff_gbs, "peak": peaks["hbm_gbs"],
+                                "unit": "GB/s", "frac": (aff_gbs / peaks["hbm_gbs"]) if aff_gbs else None, "traffic": None,
+                                "algorithmic_bytes": int(st["affine_algorithmic_bytes"]), "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+                                "note": "avg over the affine-class launches of one update"},
+            "kernel_ms_per_update": {k: v[0] / max(ksteps, 1) for k, v in kt.items()},
+            "kernel_share": kernel_share,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

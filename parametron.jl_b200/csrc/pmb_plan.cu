@@ -279,7 +279,9 @@ static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps,
         if (has_off) {
             AffForm only_off;
             only_off.rows = f.rows; only_off.offs = f.offs; only_off.coff = f.coff;
-            steps.push_back(affine_step(lower_aff(c, only_off, nullptr, 0, g, f.rows, true, nullptr), nb));
+            Step os = affine_step(lower_aff(c, only_off, nullptr, 0, g, f.rows, true, nullptr), nb);
+            os.cls = KC_MISC;  // offsets only: not a coefficient-assembly launch
+            steps.push_back(os);
         }
     } else {
         // materialise the operand as a compact dense block (the affine-assembly kernel sums duplicate variables per column)

@@ -236,7 +236,7 @@ def test_constant_blocks_are_skipped():
     pm.constraint(m, m.expr(x) + y, ">=", 1.0)
     p = pm.Parameter(m, f=lambda: np.float64(2.0))
     pm.constraint(m, p * m.expr(z), "<=", 1.0)
-    pm.objective(m, pm.Minimize, pm.dot([x, y, z], [x, y, z]))
+    pm.objective(m, pm.Minimize, pm.dot([x, y, z], [x, y, z], model=m))
     m.initialize()
     m.update()
     assert [m.block_view(i).is_constant for i in range(3)] == [1, 1, 0]
@@ -282,7 +282,7 @@ def test_errors_mirror_the_reference():
     with pytest.raises(pm.DimensionMismatch):
         m.expr(x) - b
     with pytest.raises(pm.DimensionMismatch):
-        pm.dot(x, b)
+        pm.dot(x, b, model=m)
     with pytest.raises(pm.DimensionMismatch):
         pm.bilinear(pm.adjoint(x, model=m), A, x)
     m.initialize()
