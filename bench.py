@@ -192,7 +192,12 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.current_stream().cuda_stream  # the library enqueues on torch's current stream so torch events see it
+    # the library enqueues on torch's current stream so that torch.cuda.Event sees its work; the legacy default stream has
+    # handle 0 (= "create your own" in pmb_ctx_create), so make a real stream current for the whole run
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def barrier():
         if world > 1:
