@@ -91,8 +91,9 @@ const char* pmb_version(void);
 int pmb_add_variables(pmb_ctx* ctx, int64_t n, int64_t* first_index);
 int pmb_num_variables(const pmb_ctx* ctx, int64_t* n);
 
-/* ref: Parameter constructors parameter.jl:48-88.  rows x cols fp64; cols == 0 -> vector; rows == cols == 0 -> scalar. */
-int pmb_param_create(pmb_ctx* ctx, int64_t rows, int64_t cols, int mode, pmb_node* out);
+/* ref: Parameter constructors parameter.jl:48-88.  fp64 value of `ndims` dimensions: 0 = scalar (rows, cols ignored),
+ * 1 = vector of length rows (may be 0), 2 = rows x cols column-major matrix. */
+int pmb_param_create(pmb_ctx* ctx, int ndims, int64_t rows, int64_t cols, int mode, pmb_node* out);
 int pmb_param_set_device_ptr(pmb_ctx* ctx, pmb_node p, const double* dptr);           /* PMB_PARAM_DEVICE */
 int pmb_param_set_host_ptr(pmb_ctx* ctx, pmb_node p, double* hptr,
                            pmb_host_callback f, void* user);                          /* PMB_PARAM_HOST */
@@ -104,7 +105,7 @@ int pmb_param_upload(pmb_ctx* ctx, pmb_node p, const double* host_values);
 int pmb_param_device_ptr(pmb_ctx* ctx, pmb_node p, double** dptr);
 
 /* constants folded at build time (ref: optimize_toplevel constant folding, lazyexpression.jl:189-192) */
-int pmb_const_numeric(pmb_ctx* ctx, int64_t rows, int64_t cols, const double* host_values, pmb_node* out);
+int pmb_const_numeric(pmb_ctx* ctx, int ndims, int64_t rows, int64_t cols, const double* host_values, pmb_node* out);
 /* Vector{Variable} from 1-based indices */
 int pmb_varvec(pmb_ctx* ctx, int64_t n, const int64_t* var_indices, pmb_node* out);
 /* constant symbolic values (terms given in reference order): scalar affine / quadratic, affine vector */

@@ -47,13 +47,13 @@ SIGNATURES = {
     "pmb_version": (C.c_char_p, []),
     "pmb_add_variables": (C.c_int, [C.c_void_p, C.c_int64, c_i64p]),
     "pmb_num_variables": (C.c_int, [C.c_void_p, c_i64p]),
-    "pmb_param_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, c_i32p]),
+    "pmb_param_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, c_i32p]),
     "pmb_param_set_device_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "pmb_param_set_host_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmb_param_set_uniform": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_double]),
     "pmb_param_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "pmb_param_device_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
-    "pmb_const_numeric": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, c_i32p]),
+    "pmb_const_numeric": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, c_i32p]),
     "pmb_varvec": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, c_i32p]),
     "pmb_const_affine": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, c_i32p]),
     "pmb_const_quadratic": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kAffThreads) affine_assemble_general(AffBlockD
 
 void launch_affine_assemble(const AffBlockDev& blk, int64_t batch, int sm_count, cudaStream_t stream) {
     if (blk.rows == 0) return;
+    if (blk.tma) { launch_affine_assemble_tma(blk, batch, sm_count, stream); return; }
     const int off_blocks = 1;
     int64_t gy = batch < 65535 ? batch : 65535;
     if (blk.simple) {

@@ -1,0 +1,177 @@
+// K1 (TMA variant) -- batched affine-coefficient assembly as a pipelined bulk-copy ring.
+//
+// Same reference chain as kernels_affine.cu (matvecmul! functions.jl:775-798 -> vecsubtract!/scale! :751-764,873-925 ->
+// update!(::VectorAffineFunction) moi_interop.jl:64-81) for the common "simple" block: every touched output column is
+// alpha x one source column.  The planner (pmb_plan.cu) merges adjacent columns into contiguous segments and packs them into
+// chunks of <= 16 KB; persistent CTAs stream the chunks through a 6-stage shared-memory ring with the bulk-copy engine
+// (cp.async.bulk global->shared completing on an mbarrier, shared->global bulk_group; SASS UBLKCP), so HBM sees long
+// back-to-back bursts with 80 KB in flight per CTA and no register staging.  alpha == 1 (the `C*x - d` block) is pure DMA
+// issued by one warp; otherwise 128 threads scale the stage in place between the load and the store.
+#include "pmb_kernels.h"
+
+namespace pmb {
+
+constexpr int kTmaStages = 6;
+constexpr int kTmaScaleThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ double alpha_at(const AlphaDev& a, int64_t inst) { return a.ptr ? a.c * a.ptr[inst * a.bstride] : a.c; }
+
+// offsets d = const + sum alpha * v (same as kernels_affine.cu), run by the trailing CTAs of the launch
+__device__ void tma_affine_offsets(const AffBlockDev& blk, int64_t batch, int ob, int nob) {
+    for (int64_t inst = ob; inst < batch; inst += nob)
+        for (int64_t i = threadIdx.x; i < blk.rows; i += blockDim.x) {
+            double acc = blk.d_const ? blk.d_const[i] : 0.0;
+            for (int t = 0; t < blk.noffs; ++t) {
+                const AffOffTermDev& o = blk.offs[t];
+                int64_t r = i - o.row_off;
+                if (r >= 0 && r < o.rows) acc += alpha_at(o.alpha, inst) * o.src[inst * o.src_bstride + o.src_off + r];
+            }
+            blk.d[inst * blk.d_bstride + i] = acc;
+        }
+}
+
+template <bool SCALE>
+__global__ void __launch_bounds__(SCALE ? kTmaScaleThreads : 32) affine_assemble_tma(AffBlockDev blk, int64_t batch, int copy_blocks) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kTmaStages];
+    if ((int)blockIdx.x >= copy_blocks) {
+        tma_affine_offsets(blk, batch, blockIdx.x - copy_blocks, gridDim.x - copy_blocks);
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const AffMatTermDev m = blk.mats[0];
+    const int64_t total = (int64_t)blk.nchunks * batch;
+    const int64_t first = blockIdx.x, stride = copy_blocks;
+    const int64_t cnt = first < total ? (total - first + stride - 1) / stride : 0;
+
+    // warp 0 issues every bulk copy; with SCALE the other warps only touch shared memory
+    auto issue_load = [&](int64_t i) {
+        const int64_t c = first + i * stride;
+        const int64_t inst = c / blk.nchunks;
+        const int ch = (int)(c - inst * blk.nchunks);
+        const int s0 = blk.chunk_first[ch], s1 = blk.chunk_first[ch + 1];
+        unsigned char* stage = smem_raw + (size_t)(i % kTmaStages) * kAffStageBytes;
+        uint64_t* bar = &full[i % kTmaStages];
+        if (lane == 0) {
+            const AffSeg last = blk.segs[s1 - 1];
+            mbar_expect_tx(bar, (uint32_t)(last.stage_off + last.bytes));
+        }
+        __syncwarp();
+        const double* src = m.src + inst * m.src_bstride;
+        for (int s = s0 + lane; s < s1; s += 32) {
+            const AffSeg sg = blk.segs[s];
+            bulk_g2s(stage + sg.stage_off, src + sg.src_off, (uint32_t)sg.bytes, bar);
+        }
+    };
+    auto issue_store = [&](int64_t i) {
+        const int64_t c = first + i * stride;
+        const int64_t inst = c / blk.nchunks;
+        const int ch = (int)(c - inst * blk.nchunks);
+        const int s0 = blk.chunk_first[ch], s1 = blk.chunk_first[ch + 1];
+        unsigned char* stage = smem_raw + (size_t)(i % kTmaStages) * kAffStageBytes;
+        double* dst = blk.C + inst * blk.C_bstride;
+        for (int s = s0 + lane; s < s1; s += 32) {
+            const AffSeg sg = blk.segs[s];
+            bulk_s2g(dst + sg.dst_off, stage + sg.stage_off, (uint32_t)sg.bytes);
+        }
+        bulk_commit();
+    };
+
+    if (warp == 0)
+        for (int64_t i = 0; i < cnt && i < kTmaStages - 1; ++i) issue_load(i);
+
+    for (int64_t i = 0; i < cnt; ++i) {
+        const uint32_t parity = (uint32_t)((i / kTmaStages) & 1);
+        if (SCALE) {
+            mbar_wait(&full[i % kTmaStages], parity);
+            const int64_t c = first + i * stride;
+            const int64_t inst = c / blk.nchunks;
+            const int ch = (int)(c - inst * blk.nchunks);
+            const AffSeg last = blk.segs[blk.chunk_first[ch + 1] - 1];
+            const int n2 = (last.stage_off + last.bytes) >> 4;
+            const double a = alpha_at(m.alpha, inst);
+            double2* st = reinterpret_cast<double2*>(smem_raw + (size_t)(i % kTmaStages) * kAffStageBytes);
+            for (int j = threadIdx.x; j < n2; j += kTmaScaleThreads) {
+                double2 v = st[j];
+                v.x *= a; v.y *= a;
+                st[j] = v;
+            }
+            fence_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async proxy) store
+            __syncthreads();
+        } else {
+            mbar_wait(&full[i % kTmaStages], parity);
+        }
+        if (warp == 0) {
+            issue_store(i);
+            // refill the stage drained one iteration ago: its store must have finished READING shared memory
+            bulk_wait_read<1>();
+            __syncwarp();
+            if (i + kTmaStages - 1 < cnt) issue_load(i + kTmaStages - 1);
+        }
+    }
+    if (warp == 0) bulk_wait_all();
+}
+
+void configure_affine_tma_kernels() {
+    cudaFuncSetAttribute(affine_assemble_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaStages * kAffStageBytes);
+    cudaFuncSetAttribute(affine_assemble_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaStages * kAffStageBytes);
+}
+
+void launch_affine_assemble_tma(const AffBlockDev& blk, int64_t batch, int sm_count, cudaStream_t stream) {
+    const int64_t total = (int64_t)blk.nchunks * batch;
+    // two resident CTAs per SM (2 x 96 KB of stages); prefer a grid that divides the chunk count so every CTA does equal work
+    int64_t cap = (int64_t)sm_count * 2;
+    int64_t g = total < cap ? total : cap;
+    if (total > cap)
+        for (int64_t t = cap; t >= cap / 2; --t)
+            if (total % t == 0) { g = t; break; }
+    const int off_blocks = (int)(batch < 32 ? batch : 32);
+    // alpha == 1 with no device scalar: pure DMA
+    // (the host fills blk.tma = 1 for "pure", 2 for "scaled")
+    dim3 grid((unsigned)(g + off_blocks));
+    const size_t smem = (size_t)kTmaStages * kAffStageBytes;
+    if (blk.tma == 1) affine_assemble_tma<false><<<grid, 32, smem, stream>>>(blk, batch, (int)g);
+    else affine_assemble_tma<true><<<grid, kTmaScaleThreads, smem, stream>>>(blk, batch, (int)g);
+}
+
+}  // namespace pmb

@@ -418,13 +418,20 @@ int pmb_num_variables(const pmb_ctx* ctx, int64_t* n) {
     return PMB_OK;
 }
 
-int pmb_param_create(pmb_ctx* ctx, int64_t rows, int64_t cols, int mode, pmb_node* out) {
+static int kind_of_ndims(int ndims, int64_t& rows, int64_t& cols) {
+    if (ndims < 0 || ndims > 2) fail(PMB_EINVAL, "ndims must be 0, 1 or 2");
+    if (ndims == 0) { rows = 0; cols = 0; return PMB_KIND_NUM_SCALAR; }
+    if (ndims == 1) { cols = 0; return PMB_KIND_NUM_VECTOR; }
+    return PMB_KIND_NUM_MATRIX;
+}
+
+int pmb_param_create(pmb_ctx* ctx, int ndims, int64_t rows, int64_t cols, int mode, pmb_node* out) {
     API_BEGIN(ctx)
     need_build_phase(ctx, "Parameter(model)");
     if (rows < 0 || cols < 0 || !out) fail(PMB_EINVAL, "bad Parameter shape");
     if (mode != PMB_PARAM_DEVICE && mode != PMB_PARAM_HOST && mode != PMB_PARAM_UNIFORM) fail(PMB_EINVAL, "bad Parameter mode %d", mode);
     Node n;
-    n.kind = (rows == 0 && cols == 0) ? PMB_KIND_NUM_SCALAR : (cols == 0 ? PMB_KIND_NUM_VECTOR : PMB_KIND_NUM_MATRIX);
+    n.kind = kind_of_ndims(ndims, rows, cols);
     n.rows = rows; n.cols = cols; n.is_const = false; n.nop = NOP_PARAM; n.pmode = mode;
     *out = push_node(ctx, std::move(n));
     API_END(ctx)
@@ -459,12 +466,12 @@ int pmb_param_set_uniform(pmb_ctx* ctx, pmb_node p, uint64_t seed, double scale)
     API_END(ctx)
 }
 
-int pmb_const_numeric(pmb_ctx* ctx, int64_t rows, int64_t cols, const double* host_values, pmb_node* out) {
+int pmb_const_numeric(pmb_ctx* ctx, int ndims, int64_t rows, int64_t cols, const double* host_values, pmb_node* out) {
     API_BEGIN(ctx)
     need_build_phase(ctx, "constant");
     if (rows < 0 || cols < 0 || !out) fail(PMB_EINVAL, "bad constant shape");
-    int kind = (rows == 0 && cols == 0) ? PMB_KIND_NUM_SCALAR : (cols == 0 ? PMB_KIND_NUM_VECTOR : PMB_KIND_NUM_MATRIX);
-    int64_t ne = kind == PMB_KIND_NUM_SCALAR ? 1 : (cols == 0 ? rows : rows * cols);
+    int kind = kind_of_ndims(ndims, rows, cols);
+    int64_t ne = kind == PMB_KIND_NUM_SCALAR ? 1 : (kind == PMB_KIND_NUM_VECTOR ? rows : rows * cols);
     if (ne > 0 && !host_values) fail(PMB_EINVAL, "null constant values");
     *out = make_const(ctx, kind, rows, cols, std::vector<double>(host_values, host_values + ne));
     API_END(ctx)

@@ -192,6 +192,7 @@ struct pmb_ctx {
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraph_t graph = nullptr;
     bool use_graph = false;
+    bool use_tma = true;
     bool timing = false;
     std::vector<cudaEvent_t> ev;         // 2 per step
     bool ev_pending = false;

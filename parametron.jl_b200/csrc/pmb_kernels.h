@@ -37,6 +37,13 @@ struct AffOffTermDev {
     int64_t src_off, row_off, rows;
     AlphaDev alpha;
 };
+struct AffSeg {        // one contiguous piece: dst[dst_off ...] = alpha * src[src_off ...], `bytes` long (multiple of 16)
+    int64_t src_off;   // elements from the source matrix base (within one instance)
+    int64_t dst_off;   // elements from the block's C base (within one instance)
+    int32_t bytes;
+    int32_t stage_off; // byte offset inside the chunk's shared-memory stage
+};
+constexpr int kAffStageBytes = 16384;
 struct AffBlockDev {
     double* C;            // rows x N column-major, ld = rows
     double* d;            // rows
@@ -54,8 +61,16 @@ struct AffBlockDev {
     int32_t simple;           // every touched column has exactly one matrix entry from mats[0] covering all rows
     const int32_t* col_src;   // [ntouched] source column (simple path)
     int32_t vec2;             // 16-byte path legal (even rows/ld/strides, aligned bases)
+    // TMA bulk-copy plan of the simple path (static, built once): the block is a list of contiguous segments
+    // (merged runs of adjacent columns), grouped into chunks of at most one shared-memory stage.
+    int32_t tma;              // plan present (requires vec2)
+    int32_t nchunks;
+    const AffSeg* segs;
+    const int32_t* chunk_first;   // [nchunks + 1] first segment of each chunk
 };
 void launch_affine_assemble(const AffBlockDev& blk, int64_t batch, int sm_count, cudaStream_t stream);
+void launch_affine_assemble_tma(const AffBlockDev& blk, int64_t batch, int sm_count, cudaStream_t stream);  // blk.tma != 0
+void configure_affine_tma_kernels();
 
 // ---------------- K2: fp64 Gram (SYRK-shaped) on the DMMA tensor pipe ---------------------------
 // H[map[i], map[j]] (=|+=) scale * sum_r X[r, i] * X[r, j]   for i, j in [0, n), both triangles written

@@ -231,6 +231,33 @@ static AffBlockDev lower_aff(pmb_ctx* c, const AffForm& f, double* C, int64_t C_
         const AffMatTermDev& m = mats[0];
         b.vec2 = (f.rows % 2 == 0 && m.ld % 2 == 0 && m.src_bstride % 2 == 0 && C_bstride % 2 == 0 && aligned16(m.src) && aligned16(C)) ? 1 : 0;
     }
+    if (b.simple && b.vec2 && c->use_tma) {
+        // bulk-copy plan: merge adjacent columns into contiguous runs, cut runs into <= 16 KB pieces, pack pieces into chunks
+        const AffMatTermDev& m = mats[0];
+        struct Run { int64_t src, dst, len; };
+        std::vector<Run> runs;
+        for (size_t tc = 0; tc < col_out.size(); ++tc) {
+            Run r{(int64_t)col_src[tc] * m.ld, (int64_t)col_out[tc] * f.rows, f.rows};
+            if (!runs.empty() && runs.back().src + runs.back().len == r.src && runs.back().dst + runs.back().len == r.dst) runs.back().len += r.len;
+            else runs.push_back(r);
+        }
+        const int64_t piece = kAffStageBytes / 8;
+        std::vector<AffSeg> segs;
+        std::vector<int32_t> chunk_first{0};
+        int32_t fill = 0;
+        for (auto& r : runs)
+            for (int64_t o = 0; o < r.len; o += piece) {
+                int32_t bytes = (int32_t)(std::min(piece, r.len - o) * 8);
+                if (fill + bytes > kAffStageBytes) { chunk_first.push_back((int32_t)segs.size()); fill = 0; }
+                segs.push_back(AffSeg{r.src + o, r.dst + o, bytes, fill});
+                fill += bytes;
+            }
+        chunk_first.push_back((int32_t)segs.size());
+        b.segs = upload(c, segs);
+        b.chunk_first = upload(c, chunk_first);
+        b.nchunks = (int32_t)chunk_first.size() - 1;
+        b.tma = (m.alpha.ptr == nullptr && m.alpha.c == 1.0) ? 1 : 2;
+    }
     return b;
 }
 
@@ -501,8 +528,11 @@ int pmb_ctx_create(int device, void* stream, int64_t batch, pmb_ctx** out) {
         c->own_stream = true;
     }
     configure_gram_kernels();
+    configure_affine_tma_kernels();
     const char* ng = getenv("PMB_NO_GRAPH");
     c->use_graph = !(ng && ng[0] == '1');
+    const char* nt = getenv("PMB_NO_TMA");
+    c->use_tma = !(nt && nt[0] == '1');
     *out = c;
     return PMB_OK;
 }

@@ -134,7 +134,7 @@ class Parameter(Expr):
         rows = shape[0] if len(shape) >= 1 else 0
         cols = shape[1] if len(shape) == 2 else 0
         out = C.c_int32()
-        model._ck(model._lib.pmb_param_create(model._ctx, rows, cols, mode, out))
+        model._ck(model._lib.pmb_param_create(model._ctx, len(shape), rows, cols, mode, out))
         super().__init__(model, out.value)
         self.mode = mode
         self.numel = int(np.prod(shape)) if shape else 1
@@ -305,7 +305,7 @@ class Model:
         else:
             raise ValueError("constants are scalars, vectors or matrices")
         flat = np.ascontiguousarray(a.T).ravel() if a.ndim == 2 else np.ascontiguousarray(a).ravel()
-        self._ck(self._lib.pmb_const_numeric(self._ctx, rows, cols, C.c_void_p(flat.ctypes.data), out))
+        self._ck(self._lib.pmb_const_numeric(self._ctx, a.ndim, rows, cols, C.c_void_p(flat.ctypes.data), out))
         return out.value
 
     def expr(self, x):
