@@ -12,7 +12,7 @@
 namespace pmb {
 
 constexpr int kTmaStages = 6;
-constexpr int kTmaScaleThreads = 128;
+constexpr int kTmaThreads = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -51,20 +51,23 @@ __device__ __forceinline__ double alpha_at(const AlphaDev& a, int64_t inst) { re
 
 // offsets d = const + sum alpha * v (same as kernels_affine.cu), run by the trailing CTAs of the launch
 __device__ void tma_affine_offsets(const AffBlockDev& blk, int64_t batch, int ob, int nob) {
-    for (int64_t inst = ob; inst < batch; inst += nob)
-        for (int64_t i = threadIdx.x; i < blk.rows; i += blockDim.x) {
-            double acc = blk.d_const ? blk.d_const[i] : 0.0;
-            for (int t = 0; t < blk.noffs; ++t) {
-                const AffOffTermDev& o = blk.offs[t];
-                int64_t r = i - o.row_off;
-                if (r >= 0 && r < o.rows) acc += alpha_at(o.alpha, inst) * o.src[inst * o.src_bstride + o.src_off + r];
-            }
-            blk.d[inst * blk.d_bstride + i] = acc;
+    const int64_t rb = (blk.rows + kTmaThreads - 1) / kTmaThreads;  // work item = (instance, block of kTmaThreads rows)
+    for (int64_t w = ob; w < batch * rb; w += nob) {
+        const int64_t inst = w / rb;
+        const int64_t i = (w - inst * rb) * kTmaThreads + threadIdx.x;
+        if (i >= blk.rows) continue;
+        double acc = blk.d_const ? blk.d_const[i] : 0.0;
+        for (int t = 0; t < blk.noffs; ++t) {
+            const AffOffTermDev o = blk.offs[t];
+            int64_t r = i - o.row_off;
+            if (r >= 0 && r < o.rows) acc += alpha_at(o.alpha, inst) * o.src[inst * o.src_bstride + o.src_off + r];
         }
+        blk.d[inst * blk.d_bstride + i] = acc;
+    }
 }
 
 template <bool SCALE>
-__global__ void __launch_bounds__(SCALE ? kTmaScaleThreads : 32) affine_assemble_tma(AffBlockDev blk, int64_t batch, int copy_blocks) {
+__global__ void __launch_bounds__(kTmaThreads) affine_assemble_tma(AffBlockDev blk, int64_t batch, int copy_blocks) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kTmaStages];
     if ((int)blockIdx.x >= copy_blocks) {
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(SCALE ? kTmaScaleThreads : 32) affine_assemble
         bulk_commit();
     };
 
+    if (!SCALE && warp != 0) return;  // pure DMA: one warp drives the ring
     if (warp == 0)
         for (int64_t i = 0; i < cnt && i < kTmaStages - 1; ++i) issue_load(i);
 
@@ -131,14 +135,14 @@ __global__ void __launch_bounds__(SCALE ? kTmaScaleThreads : 32) affine_assemble
             const int n2 = (last.stage_off + last.bytes) >> 4;
             const double a = alpha_at(m.alpha, inst);
             double2* st = reinterpret_cast<double2*>(smem_raw + (size_t)(i % kTmaStages) * kAffStageBytes);
-            for (int j = threadIdx.x; j < n2; j += kTmaScaleThreads) {
+            for (int j = threadIdx.x; j < n2; j += kTmaThreads) {
                 double2 v = st[j];
                 v.x *= a; v.y *= a;
                 st[j] = v;
             }
             fence_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async proxy) store
             __syncthreads();
-        } else {
+        } else if (warp == 0) {
             mbar_wait(&full[i % kTmaStages], parity);
         }
         if (warp == 0) {
@@ -165,13 +169,14 @@ void launch_affine_assemble_tma(const AffBlockDev& blk, int64_t batch, int sm_co
     if (total > cap)
         for (int64_t t = cap; t >= cap / 2; --t)
             if (total % t == 0) { g = t; break; }
-    const int off_blocks = (int)(batch < 32 ? batch : 32);
+    const int64_t off_items = batch * ((blk.rows + kTmaThreads - 1) / kTmaThreads);
+    const int off_blocks = (int)(off_items < 64 ? off_items : 64);
     // alpha == 1 with no device scalar: pure DMA
     // (the host fills blk.tma = 1 for "pure", 2 for "scaled")
     dim3 grid((unsigned)(g + off_blocks));
     const size_t smem = (size_t)kTmaStages * kAffStageBytes;
-    if (blk.tma == 1) affine_assemble_tma<false><<<grid, 32, smem, stream>>>(blk, batch, (int)g);
-    else affine_assemble_tma<true><<<grid, kTmaScaleThreads, smem, stream>>>(blk, batch, (int)g);
+    if (blk.tma == 1) affine_assemble_tma<false><<<grid, kTmaThreads, smem, stream>>>(blk, batch, (int)g);
+    else affine_assemble_tma<true><<<grid, kTmaThreads, smem, stream>>>(blk, batch, (int)g);
 }
 
 }  // namespace pmb

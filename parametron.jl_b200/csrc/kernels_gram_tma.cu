@@ -1,0 +1,382 @@
+// K2 (TMA, warp-specialised) -- fp64 Gram / SYRK-shaped contraction on the DMMA tensor pipe.
+//
+// Same reference semantics as kernels_gram.cu (vecdot! + muladd!, functions.jl:548-576,702-709, then the symmetric MOI
+// Hessian of moi_interop.jl:45-62:  H = scale * X'X written to both triangles), restructured for Blackwell:
+//   * one producer warp: a single elected thread issues 3-D TMA tile loads (cp.async.bulk.tensor, SASS UTMALDG) of the
+//     K-major operand panels straight from the Parameter buffer into a 6-stage shared-memory ring, completion on mbarriers.
+//     Box = 16 k x 128 columns (one full 128-byte line per column) with the hardware 128-byte swizzle; together with a fixed
+//     permutation of the 8 rows of every MMA fragment (pi = 0,2,4,6,1,3,5,7) every fragment load is bank-conflict-free.
+//     Ragged edges (k, n not multiples of the tile) are zero-filled by the TMA unit;
+//   * eight consumer warps (64x32 each, 4x4 mma.m16n8k4.f64 = SASS DMMA) wait on the "full" mbarrier of a stage and release
+//     it through the "empty" mbarrier: no block-wide barrier and no address arithmetic in the MMA instruction stream, so the
+//     two warps of a scheduler drift out of phase and keep the DMMA pipe fed;
+//   * persistent CTAs walk "units" = (instance, upper-triangular 128x128 tile, k-slice).  Tiles of the last partial wave are
+//     split along k so every SM finishes together: each slice parks its partial tile in a workspace, and the slice that arrives
+//     last (one atomic counter per tile) sums the partials in slice order -- nobody waits, and the summation order is fixed, so
+//     results are bit-identical run to run.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "pmb_kernels.h"
+
+namespace pmb {
+
+constexpr int kTBM = 128;
+constexpr int kTKT = 16;
+constexpr int kTStages = 6;
+constexpr int kTConsumerWarps = 8;
+constexpr int kTThreads = (kTConsumerWarps + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup (setmaxnreg is per warpgroup)
+constexpr int kTPanelBytes = kTBM * kTKT * 8;             // 16 KB
+constexpr int kTSmemBytes = kTStages * 2 * kTPanelBytes + 1024;  // 192 KB + slack to align the ring to the 1 KB swizzle period
+
+struct GramTmaKernelArgs {
+    CUtensorMap tmx, tmy;
+    int64_t k, n, p;
+    double* out; int64_t ldo, o_bstride;
+    const int32_t* map;
+    AlphaDev scale;
+    int32_t accumulate;
+    int32_t tiles_m, tiles_n, kiters;
+    int64_t tiles_per_inst, total_tiles;
+    int64_t full_tiles;   // tiles [0, full_tiles) are one unit each; the rest are cut into nslices k-slices
+    int32_t nslices;
+    int32_t* counters;    // [total_tiles - full_tiles] arrival counters, zero between launches
+    double* workspace;    // [(total_tiles - full_tiles) * nslices][64][256] partial accumulators
+    int64_t total_units;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(s_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(s_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void dmma_16x8x4(double (&c)[4], double a0, double a1, double b0) {
+    asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a0), "d"(a1), "d"(b0));
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTConsumerWarps * 32) : "memory"); }
+
+struct Unit {
+    int64_t inst;
+    int ti, tj;
+    int kt0, kt1;    // k-tile range
+    int slice, nslices;
+    int64_t split_id;  // index of the split tile: counters[split_id], workspace[(split_id * nslices + slice)]
+};
+
+template <bool SYRK>
+__device__ __forceinline__ Unit decode_unit(const GramTmaKernelArgs& a, int64_t u) {
+    Unit w;
+    int64_t tile;
+    if (u < a.full_tiles) {
+        tile = u; w.slice = 0; w.nslices = 1; w.split_id = 0;
+    } else {
+        int64_t v = u - a.full_tiles;
+        w.split_id = v / a.nslices;
+        w.slice = (int)(v - w.split_id * a.nslices);
+        w.nslices = a.nslices;
+        tile = a.full_tiles + w.split_id;
+    }
+    w.inst = tile / a.tiles_per_inst;
+    int64_t tl = tile - w.inst * a.tiles_per_inst;
+    if (SYRK) {  // upper-triangular tile (ti <= tj), row-major enumeration
+        int ti = 0, rowlen = a.tiles_n;
+        while (tl >= rowlen) { tl -= rowlen; --rowlen; ++ti; }
+        w.ti = ti; w.tj = ti + (int)tl;
+    } else {
+        w.ti = (int)(tl / a.tiles_n);
+        w.tj = (int)(tl - (int64_t)w.ti * a.tiles_n);
+    }
+    w.kt0 = (int)((int64_t)a.kiters * w.slice / w.nslices);
+    w.kt1 = (int)((int64_t)a.kiters * (w.slice + 1) / w.nslices);
+    return w;
+}
+
+template <bool SYRK, bool ADD>
+__device__ __forceinline__ void store_tile(const GramTmaKernelArgs& a, double (&acc)[4][4][4], double* out, double sc, int64_t i0, int64_t j0,
+                                           bool diag, int wm, int wn, int pg, int t) {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int cj = 2 * t + (r & 1);  // accumulator column index inside the 8-wide fragment -> panel column pi(cj)
+                const int64_t m = i0 + wm * 64 + mi * 16 + pg + (r >> 1) * 8;
+                const int64_t nn = j0 + wn * 32 + ni * 8 + (((2 * cj) & 7) + (cj >> 2));
+                if (m < a.n && nn < a.p) {
+                    const double v = sc * acc[mi][ni][r];
+                    if (SYRK) {
+                        const int64_t om = a.map ? a.map[m] : m, on = a.map ? a.map[nn] : nn;
+                        double* p1 = out + om + on * a.ldo;
+                        *p1 = ADD ? *p1 + v : v;
+                        if (!diag) {
+                            double* p2 = out + on + om * a.ldo;
+                            *p2 = ADD ? *p2 + v : v;
+                        }
+                    } else {
+                        double* p1 = out + m + nn * a.ldo;
+                        *p1 = ADD ? *p1 + v : v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool SYRK>
+__global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_constant__ GramTmaKernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kTStages];
+    __shared__ __align__(8) uint64_t empty_bar[kTStages];
+    __shared__ int arrival_flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ring = (s_u32(smem_raw) + 1023u) & ~1023u;  // the 128-byte swizzle pattern repeats every 1024 bytes
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kTStages; ++s) { mb_init(&full_bar[s], 1); mb_init(&empty_bar[s], kTConsumerWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= kTConsumerWarps) {
+        // ===== producer warpgroup: gives its registers back; one elected thread drives the TMA ring =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == kTConsumerWarps && lane == 0) {
+            uint32_t it = 0;
+            for (int64_t u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+                const Unit w = decode_unit<SYRK>(a, u);
+                const bool diag = SYRK && w.ti == w.tj;
+                for (int kt = w.kt0; kt < w.kt1; ++kt, ++it) {
+                    const int s = it % kTStages;
+                    mb_wait(&empty_bar[s], ((it / kTStages) & 1) ^ 1);
+                    const uint32_t stage = ring + (uint32_t)s * 2 * kTPanelBytes;
+                    mb_expect_tx(&full_bar[s], diag ? kTPanelBytes : 2 * kTPanelBytes);
+                    tma_load_3d(stage, &a.tmx, kt * kTKT, w.ti * kTBM, (int)w.inst, &full_bar[s]);
+                    if (!diag) tma_load_3d(stage + kTPanelBytes, &a.tmy, kt * kTKT, w.tj * kTBM, (int)w.inst, &full_bar[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: 8 warps (2 warpgroups), warp tile 64 x 32 =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    // MMA fragment row g lives in panel column (8-group base) + pi(g): with the 128-byte swizzle (16-byte chunk index XOR
+    // (column & 7)) the 16 lanes of each half-warp then hit 16 distinct 8-byte bank pairs.
+    const int pg = ((2 * g) & 7) + (g >> 2);
+    uint32_t koff[kTKT / 4];  // byte offset of this thread's k element inside a swizzled 128-byte column line, per k-block
+#pragma unroll
+    for (int kb = 0; kb < kTKT / 4; ++kb) koff[kb] = (uint32_t)((((kb * 2 + (t >> 1)) ^ pg) << 4) + (t & 1) * 8);
+    const uint32_t a_row = (uint32_t)((wm * 64 + pg) * 128);
+    const uint32_t b_row = (uint32_t)((wn * 32 + pg) * 128);
+    uint32_t it = 0;
+    for (int64_t u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+        const Unit w = decode_unit<SYRK>(a, u);
+        const bool diag = SYRK && w.ti == w.tj;
+        double acc[4][4][4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[mi][ni][r] = 0.0;
+
+        for (int kt = w.kt0; kt < w.kt1; ++kt, ++it) {
+            const int s = it % kTStages;
+            mb_wait(&full_bar[s], (it / kTStages) & 1);
+            const uint32_t sA = ring + (uint32_t)s * 2 * kTPanelBytes + a_row;
+            const uint32_t sB = ring + (uint32_t)s * 2 * kTPanelBytes + (diag ? 0u : (uint32_t)kTPanelBytes) + b_row;
+#pragma unroll
+            for (int kb = 0; kb < kTKT / 4; ++kb) {
+                double af[4][2], bf[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    af[mi][0] = lds_f64(sA + mi * 16 * 128 + koff[kb]);
+                    af[mi][1] = lds_f64(sA + (mi * 16 + 8) * 128 + koff[kb]);
+                }
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) bf[ni] = lds_f64(sB + ni * 8 * 128 + koff[kb]);
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma_16x8x4(acc[mi][ni], af[mi][0], af[mi][1], bf[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) mb_arrive(&empty_bar[s]);  // this warp is done reading the stage
+        }
+
+        // ---- k-slices: park the partial, the last arriver sums all partials of the tile in slice order ----
+        if (w.nslices > 1) {
+            double* ws = a.workspace + ((w.split_id * w.nslices + w.slice) * 64) * (int64_t)(kTConsumerWarps * 32) + tid;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) __stcg(ws + ((mi * 4 + ni) * 4 + r) * (kTConsumerWarps * 32), acc[mi][ni][r]);
+            __threadfence();
+            consumer_bar();
+            if (tid == 0) {
+                const int old = atomicAdd(a.counters + w.split_id, 1);
+                const int last = old == w.nslices - 1;
+                if (last) a.counters[w.split_id] = 0;  // ready for the next launch (graph replay)
+                arrival_flag = last;
+            }
+            consumer_bar();
+            if (!arrival_flag) continue;  // uniform across the consumer warps
+            __threadfence();
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[mi][ni][r] = 0.0;
+            const double* wr = a.workspace + (w.split_id * w.nslices * 64) * (int64_t)(kTConsumerWarps * 32) + tid;
+            for (int sl = 0; sl < w.nslices; ++sl, wr += 64 * (kTConsumerWarps * 32)) {
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[mi][ni][r] += __ldcg(wr + ((mi * 4 + ni) * 4 + r) * (kTConsumerWarps * 32));
+            }
+        }
+        // ---- epilogue: scale, (scatter by variable map), both triangles ----
+        const double sc = a.scale.ptr ? a.scale.c * a.scale.ptr[w.inst * a.scale.bstride] : a.scale.c;
+        double* out = a.out + w.inst * a.o_bstride;
+        const int64_t i0 = (int64_t)w.ti * kTBM, j0 = (int64_t)w.tj * kTBM;
+        if (a.accumulate) store_tile<SYRK, true>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t);
+        else store_tile<SYRK, false>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t);
+    }
+}
+
+void configure_gram_tma_kernels() {
+    cudaFuncSetAttribute(gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+}
+
+// ---- host: tensor maps and the unit decomposition ------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// X: k x n column-major (ld), `batch` instances `bstride` elements apart.  Tensor (k, n, batch), box (16, 128, 1), 128-byte swizzle.
+static bool make_panel_map(CUtensorMap* tm, const double* X, int64_t ld, int64_t bstride, int64_t k, int64_t n, int64_t batch) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    if (ld % 2 != 0 || ((uintptr_t)X & 15) != 0 || (batch > 1 && bstride % 2 != 0) || k == 0 || n == 0) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)n, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)(batch > 1 && bstride > 0 ? bstride : ld * n) * 8};
+    cuuint32_t box[3] = {(cuuint32_t)kTKT, (cuuint32_t)kTBM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// unit decomposition: whole waves of tiles run unsplit; the tiles of the last partial wave are cut into k-slices so that
+// (tail tiles x slices) fills whole waves again.  Fewer tiles than SMs: everything is split.
+GramSplitPlan plan_gram_split(bool syrk, int64_t k, int64_t n, int64_t p, int64_t batch, int sm_count) {
+    GramSplitPlan pl{1, 0, 0};
+    const int64_t tm = (n + kTBM - 1) / kTBM, tn = (p + kTBM - 1) / kTBM;
+    const int64_t total = (syrk ? tn * (tn + 1) / 2 : tm * tn) * batch;
+    const int64_t kiters = (k + kTKT - 1) / kTKT;
+    const int64_t G = sm_count;
+    const int64_t tail = total % G;
+    if (tail == 0) return pl;
+    const int64_t max_slices = std::min<int64_t>(8, kiters / 8);  // >= 8 k-tiles (128 k) per slice, workspace <= 8 tiles per SM
+    double best = 1e30;
+    for (int64_t s = 1; s <= max_slices; ++s) {
+        const double waves = (double)((tail * s + G - 1) / G) / (double)s;  // tail time in tile-times
+        const double cost = waves + 0.012 * (double)s;                      // parking + summing the partials is not free
+        if (cost < best - 1e-12) { best = cost; pl.nslices = (int32_t)s; }
+    }
+    if (pl.nslices > 1) {
+        pl.split_tiles = tail;
+        pl.workspace_doubles = tail * pl.nslices * (int64_t)kTBM * kTBM;
+    }
+    return pl;
+}
+
+// Returns false when the TMA path does not apply (alignment / shared constant operand with batch > 1); the caller falls back
+// to the cp.async kernel of kernels_gram.cu.
+static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs, const double* Y, int64_t ldy, int64_t ybs, int64_t k,
+                            int64_t n, int64_t p, double* out, int64_t ldo, int64_t obs, const int32_t* map, AlphaDev scale, int accumulate,
+                            const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+    if (batch > 1 && (xbs == 0 || ybs == 0)) return false;
+    GramTmaKernelArgs a{};
+    if (!make_panel_map(&a.tmx, X, ldx, xbs, k, n, batch)) return false;
+    if (!make_panel_map(&a.tmy, Y, ldy, ybs, k, p, batch)) return false;
+    a.k = k; a.n = n; a.p = p; a.out = out; a.ldo = ldo; a.o_bstride = obs; a.map = map; a.scale = scale; a.accumulate = accumulate;
+    a.tiles_m = (int)((n + kTBM - 1) / kTBM);
+    a.tiles_n = (int)((p + kTBM - 1) / kTBM);
+    a.kiters = (int)((k + kTKT - 1) / kTKT);
+    a.tiles_per_inst = syrk ? (int64_t)a.tiles_n * (a.tiles_n + 1) / 2 : (int64_t)a.tiles_m * a.tiles_n;
+    a.total_tiles = a.tiles_per_inst * batch;
+    if (a.total_tiles == 0) return true;
+    const bool split = sc.plan.nslices > 1 && sc.counters && sc.workspace;
+    a.nslices = split ? sc.plan.nslices : 1;
+    a.full_tiles = split ? a.total_tiles - sc.plan.split_tiles : a.total_tiles;
+    a.counters = sc.counters;
+    a.workspace = sc.workspace;
+    a.total_units = a.full_tiles + (a.total_tiles - a.full_tiles) * a.nslices;
+    const int grid = (int)(a.total_units < sm_count ? a.total_units : sm_count);
+    if (syrk) gram_tma_kernel<true><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+    else gram_tma_kernel<false><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+    return true;
+}
+
+bool launch_gram_syrk_tma(const GramArgs& g, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+    return launch_tma_impl(true, g.X, g.ldx, g.x_bstride, g.X, g.ldx, g.x_bstride, g.k, g.n, g.n, g.H, g.ldh, g.h_bstride, g.map, g.scale,
+                           g.accumulate, sc, batch, sm_count, stream);
+}
+
+bool launch_gemm_tn_tma(const GemmTNArgs& g, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+    return launch_tma_impl(false, g.X, g.ldx, g.x_bstride, g.Y, g.ldy, g.y_bstride, g.k, g.n, g.p, g.M, g.ldm, g.m_bstride, nullptr,
+                           AlphaDev{1.0, nullptr, 0}, 0, sc, batch, sm_count, stream);
+}
+
+}  // namespace pmb

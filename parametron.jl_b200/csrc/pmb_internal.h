@@ -138,6 +138,7 @@ struct Step {
     const double* s0 = nullptr; int64_t s0_bs = 0;
     const double* s1 = nullptr; int64_t s1_bs = 0;
     AffBlockDev aff{};
+    GramScratch gscratch{};  // ST_GRAM / ST_GEMM: k-split plan, arrival counters and partial-tile workspace
     GramArgs gram{};
     GemmTNArgs gemm{};
     GemvArgs gemv{};

@@ -94,6 +94,22 @@ struct GemmTNArgs {
     double* M; int64_t ldm, m_bstride;
 };
 void launch_gemm_tn(const GemmTNArgs& a, int64_t batch, int sm_count, cudaStream_t stream);
+// TMA + warp-specialised variants (kernels_gram_tma.cu).  Return false when the operands do not meet the TMA alignment rules
+// (the caller then uses the cp.async kernels above).
+struct GramSplitPlan {          // k-split of the last partial wave of tiles (computed once by the planner)
+    int32_t nslices;            // 1: no split
+    int64_t split_tiles;        // number of tiles that are split (the tail of the tile enumeration)
+    int64_t workspace_doubles;  // split_tiles * nslices * 128 * 128
+};
+GramSplitPlan plan_gram_split(bool syrk, int64_t k, int64_t n, int64_t p, int64_t batch, int sm_count);
+struct GramScratch {
+    GramSplitPlan plan;
+    int32_t* counters;   // [split_tiles], zero between launches
+    double* workspace;   // [workspace_doubles]
+};
+bool launch_gram_syrk_tma(const GramArgs& a, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
+bool launch_gemm_tn_tma(const GemmTNArgs& a, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
+void configure_gram_tma_kernels();
 
 // ---------------- small kernels ---------------------------------------------------------------
 void launch_tick(unsigned long long* counter, cudaStream_t stream);

@@ -70,6 +70,16 @@ static void mark_quad(pmb_ctx* c, const QuadForm& q) {
     mark_aff(c, q.aff);
 }
 
+static GramScratch make_gram_scratch(pmb_ctx* c, bool syrk, int64_t k, int64_t n, int64_t p, int64_t batch) {
+    GramScratch sc{};
+    sc.plan = plan_gram_split(syrk, k, n, p, batch, c->sm_count);
+    if (sc.plan.nslices > 1) {
+        sc.counters = dalloc<int32_t>(c, sc.plan.split_tiles, true);
+        sc.workspace = dalloc<double>(c, sc.plan.workspace_doubles);
+    }
+    return sc;
+}
+
 // ---- numeric nodes -> buffers + steps -----------------------------------------------------------
 static int64_t src_ld(const Node& n) { return n.kind == PMB_KIND_NUM_MATRIX ? n.rows : 1; }
 
@@ -163,6 +173,7 @@ static void plan_numeric(pmb_ctx* c, int id) {
             g.k = n.gm_k; g.n = n.rows; g.p = n.cols;
             g.M = n.dptr; g.ldm = n.rows; g.m_bstride = n.bstride;
             s.gemm = g;
+            s.gscratch = make_gram_scratch(c, false, g.k, g.n, g.p, nb);
             break;
         }
         default: fail(PMB_EINVAL, "internal: numeric node %d has no plan", id);
@@ -369,6 +380,7 @@ static void plan_objective(pmb_ctx* c) {
             ga.H = c->Q; ga.ldh = N; ga.h_bstride = N * N; ga.map = F.map;
             ga.scale = scaled(a, 2.0 * F.cx * F.cx); ga.accumulate = overwrite ? 0 : 1;
             s.gram = ga;
+            s.gscratch = make_gram_scratch(c, true, ga.k, ga.n, ga.n, nb);
             st.push_back(s);
             c->gram_flops += F.k * F.ncols * (F.ncols + 1) + 2 * F.k * F.ncols + 2 * F.k;
             if (F.g) {
@@ -398,6 +410,7 @@ static void plan_objective(pmb_ctx* c) {
             gm.X = F.X; gm.ldx = F.ldx; gm.x_bstride = F.xbs; gm.Y = Hs.X; gm.ldy = Hs.ldx; gm.y_bstride = Hs.xbs;
             gm.k = F.k; gm.n = F.ncols; gm.p = Hs.ncols; gm.M = M; gm.ldm = F.ncols; gm.m_bstride = F.ncols * Hs.ncols;
             s.gemm = gm;
+            s.gscratch = make_gram_scratch(c, false, gm.k, gm.n, gm.p, nb);
             st.push_back(s);
             Step sc;
             sc.type = ST_SCATTER_SYM; sc.cls = KC_MISC; sc.batch = nb;
@@ -472,8 +485,14 @@ static void run_step(pmb_ctx* c, const Step& s) {
         case ST_DOT: launch_dot(s.dot, s.batch, st); break;
         case ST_SPROD: launch_scalar_prod(s.out, s.out_bstride, s.scale, s.s0, s.s0_bs, s.s1, s.s1_bs, s.batch, st); break;
         case ST_AFFINE: launch_affine_assemble(s.aff, s.batch, c->sm_count, st); break;
-        case ST_GRAM: launch_gram_syrk(s.gram, s.batch, c->sm_count, st); break;
-        case ST_GEMM: launch_gemm_tn(s.gemm, s.batch, c->sm_count, st); break;
+        case ST_GRAM:
+            if (!(c->use_tma && launch_gram_syrk_tma(s.gram, s.gscratch, s.batch, c->sm_count, st)))
+                launch_gram_syrk(s.gram, s.batch, c->sm_count, st);
+            break;
+        case ST_GEMM:
+            if (!(c->use_tma && launch_gemm_tn_tma(s.gemm, s.gscratch, s.batch, c->sm_count, st)))
+                launch_gemm_tn(s.gemm, s.batch, c->sm_count, st);
+            break;
         case ST_SCATTER_VEC: launch_scatter_vec(s.sv, s.batch, st); break;
         case ST_BILINEAR: launch_bilinear_scatter(s.bl, s.batch, st); break;
         case ST_COO: launch_coo_quad(s.coo, s.batch, st); break;
@@ -529,6 +548,7 @@ int pmb_ctx_create(int device, void* stream, int64_t batch, pmb_ctx** out) {
     }
     configure_gram_kernels();
     configure_affine_tma_kernels();
+    configure_gram_tma_kernels();
     const char* ng = getenv("PMB_NO_GRAPH");
     c->use_graph = !(ng && ng[0] == '1');
     const char* nt = getenv("PMB_NO_TMA");
