@@ -67,6 +67,11 @@ struct AffBlockDev {
     int32_t nchunks;
     const AffSeg* segs;
     const int32_t* chunk_first;   // [nchunks + 1] first segment of each chunk
+    // regular plan (one segment per chunk, offsets in arithmetic progression -- e.g. the identity variable map): the kernel
+    // computes the descriptors instead of reading the tables
+    int32_t uniform;
+    int64_t u_src0, u_dst0, u_src_stride, u_dst_stride;
+    int32_t u_bytes, u_last_bytes;
 };
 void launch_affine_assemble(const AffBlockDev& blk, int64_t batch, int sm_count, cudaStream_t stream);
 void launch_affine_assemble_tma(const AffBlockDev& blk, int64_t batch, int sm_count, cudaStream_t stream);  // blk.tma != 0

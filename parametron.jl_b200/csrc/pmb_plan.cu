@@ -268,6 +268,21 @@ static AffBlockDev lower_aff(pmb_ctx* c, const AffForm& f, double* C, int64_t C_
         b.chunk_first = upload(c, chunk_first);
         b.nchunks = (int32_t)chunk_first.size() - 1;
         b.tma = (m.alpha.ptr == nullptr && m.alpha.c == 1.0) ? 1 : 2;
+        // regular plan?
+        bool uni = (size_t)b.nchunks == segs.size() && !segs.empty();
+        if (uni && segs.size() > 1) {
+            const int64_t ds = segs[1].src_off - segs[0].src_off, dd = segs[1].dst_off - segs[0].dst_off;
+            for (size_t i = 1; i < segs.size() && uni; ++i) {
+                uni = segs[i].src_off - segs[i - 1].src_off == ds && segs[i].dst_off - segs[i - 1].dst_off == dd;
+                if (i + 1 < segs.size()) uni = uni && segs[i].bytes == segs[0].bytes;
+            }
+            b.u_src_stride = ds; b.u_dst_stride = dd;
+        }
+        if (uni) {
+            b.uniform = 1;
+            b.u_src0 = segs[0].src_off; b.u_dst0 = segs[0].dst_off;
+            b.u_bytes = segs[0].bytes; b.u_last_bytes = segs.back().bytes;
+        }
     }
     return b;
 }
