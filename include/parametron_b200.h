@@ -94,6 +94,13 @@ int pmb_num_variables(const pmb_ctx* ctx, int64_t* n);
 /* ref: Parameter constructors parameter.jl:48-88.  fp64 value of `ndims` dimensions: 0 = scalar (rows, cols ignored),
  * 1 = vector of length rows (may be 0), 2 = rows x cols column-major matrix. */
 int pmb_param_create(pmb_ctx* ctx, int ndims, int64_t rows, int64_t cols, int mode, pmb_node* out);
+/* Block-sparse Parameter matrix (BSR): rows x cols with `nblocks` stored b x b blocks at 0-based block coordinates
+ * (block_rows[i], block_cols[i]); the value buffer is nblocks * b * b doubles, each block column-major.  The reference has no
+ * sparse path (matvecmul! visits every A[i], functions.jl:790-796); this is its dense matrix with the structural zeros left
+ * out.  Supported use: `A * x` with x::Vector{Variable} as the only coefficient source of a constraint block, which is then
+ * emitted in sparse form (pmb_block_view.is_sparse). */
+int pmb_param_create_bsr(pmb_ctx* ctx, int64_t rows, int64_t cols, int64_t b, int64_t nblocks, const int64_t* block_rows,
+                         const int64_t* block_cols, int mode, pmb_node* out);
 int pmb_param_set_device_ptr(pmb_ctx* ctx, pmb_node p, const double* dptr);           /* PMB_PARAM_DEVICE */
 int pmb_param_set_host_ptr(pmb_ctx* ctx, pmb_node p, double* hptr,
                            pmb_host_callback f, void* user);                          /* PMB_PARAM_HOST */
@@ -161,6 +168,13 @@ typedef struct {
     double* C;           /* device, m_i x N column-major (ld = m_i), batch stride m_i*N; columns are OPTIMIZER indices */
     double* d;           /* device, m_i, batch stride m_i   (the block is  C x + d  in the set) */
     int64_t nterms;      /* number of reference LinearTerms per instance (static sparsity bookkeeping) */
+    /* sparse form (block built from one BSR matrix): C is NULL; coefficient e of an instance is vals[e] at
+     * (sp_rows[e], sp_cols[e]) (0-based row, 0-based OPTIMIZER column), e in value-buffer order; the index tables are static */
+    int32_t is_sparse;
+    int64_t nnz;
+    double* vals;            /* device, batch stride nnz */
+    const int32_t* sp_rows;  /* device, [nnz] */
+    const int32_t* sp_cols;  /* device, [nnz] */
 } pmb_block_view;
 
 int pmb_get_objective(pmb_ctx* ctx, pmb_objective_view* out);

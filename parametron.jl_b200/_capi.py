@@ -28,7 +28,8 @@ class ObjectiveView(C.Structure):
 
 class BlockView(C.Structure):
     _fields_ = [("set_kind", C.c_int32), ("is_scalar", C.c_int32), ("is_constant", C.c_int32), ("bucket", C.c_int32),
-                ("rows", C.c_int64), ("nvars", C.c_int64), ("C", C.c_void_p), ("d", C.c_void_p), ("nterms", C.c_int64)]
+                ("rows", C.c_int64), ("nvars", C.c_int64), ("C", C.c_void_p), ("d", C.c_void_p), ("nterms", C.c_int64),
+                ("is_sparse", C.c_int32), ("nnz", C.c_int64), ("vals", C.c_void_p), ("sp_rows", C.c_void_p), ("sp_cols", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -48,6 +49,7 @@ SIGNATURES = {
     "pmb_add_variables": (C.c_int, [C.c_void_p, C.c_int64, c_i64p]),
     "pmb_num_variables": (C.c_int, [C.c_void_p, c_i64p]),
     "pmb_param_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, c_i32p]),
+    "pmb_param_create_bsr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, c_i32p]),
     "pmb_param_set_device_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "pmb_param_set_host_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmb_param_set_uniform": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_double]),

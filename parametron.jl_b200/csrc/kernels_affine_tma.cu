@@ -53,6 +53,7 @@ __device__ __forceinline__ double alpha_at(const AlphaDev& a, int64_t inst) { re
 
 // offsets d = const + sum alpha * v (same as kernels_affine.cu), run by the trailing CTAs of the launch
 __device__ void tma_affine_offsets(const AffBlockDev& blk, int64_t batch, int ob, int nob) {
+    if (!blk.d) return;
     const int64_t rb = (blk.rows + kTmaThreads - 1) / kTmaThreads;  // work item = (instance, block of kTmaThreads rows)
     for (int64_t w = ob; w < batch * rb; w += nob) {
         const int64_t inst = w / rb;

@@ -40,6 +40,7 @@ void need_build_phase(pmb_ctx* c, const char* what) {
 bool is_numeric(int kind) { return kind == PMB_KIND_NUM_SCALAR || kind == PMB_KIND_NUM_VECTOR || kind == PMB_KIND_NUM_MATRIX; }
 
 int64_t numel_of(const Node& n) {
+    if (n.bsr_b > 0) return n.bsr_nblocks * n.bsr_b * n.bsr_b;
     if (n.kind == PMB_KIND_NUM_SCALAR) return 1;
     if (n.kind == PMB_KIND_NUM_VECTOR) return n.rows;
     return n.rows * n.cols;
@@ -96,6 +97,7 @@ bool aff_is_const(pmb_ctx* c, const AffForm& f) {
     for (auto& t : f.mats) if (!alpha_const(c, t.a) || !node_at(c, t.mat).is_const) return false;
     for (auto& t : f.units) if (!alpha_const(c, t.a)) return false;
     for (auto& t : f.offs) if (!alpha_const(c, t.a) || !node_at(c, t.vec).is_const) return false;
+    for (auto& t : f.sps) if (!alpha_const(c, t.a) || !node_at(c, t.mat).is_const) return false;
     return true;
 }
 
@@ -110,6 +112,7 @@ static void aff_scale(pmb_ctx* c, AffForm& f, Alpha m) {
     for (auto& t : f.mats) t.a = amul(c, t.a, m);
     for (auto& t : f.units) t.a = amul(c, t.a, m);
     for (auto& t : f.offs) t.a = amul(c, t.a, m);
+    for (auto& t : f.sps) t.a = amul(c, t.a, m);
     if (!f.coff.empty()) {
         if (m.node < 0) {
             for (double& v : f.coff) v *= m.c;
@@ -130,6 +133,10 @@ static void aff_append(AffForm& dst, const AffForm& src, double sign, int64_t ro
     for (auto t : src.mats) { t.a.c *= sign; t.row_off += row_shift; dst.mats.push_back(std::move(t)); }
     for (auto t : src.units) { t.a.c *= sign; t.row_off += row_shift; dst.units.push_back(std::move(t)); }
     for (auto t : src.offs) { t.a.c *= sign; t.row_off += row_shift; dst.offs.push_back(t); }
+    for (auto t : src.sps) {
+        if (row_shift != 0) fail(PMB_EUNSUPPORTED, "vcat of a block-sparse product has no device lowering");
+        t.a.c *= sign; dst.sps.push_back(std::move(t)); dst.order_exact = false;
+    }
     if (!src.coff.empty()) {
         if (dst.coff.empty()) dst.coff.assign((size_t)dst.rows, 0.0);
         for (int64_t i = 0; i < src.rows; ++i) dst.coff[(size_t)(row_shift + i)] += sign * src.coff[(size_t)i];
@@ -247,17 +254,35 @@ static int make_transpose(pmb_ctx* c, int A) {
 
 // ---- the rewrite rules ------------------------------------------------------------------------
 // A * x with A::Matrix.  ref: lazyexpression.jl:200-204 -> matvecmul!, functions.jl:775-822
+static void need_dense(pmb_ctx* c, int id, const char* what) {
+    if (node_at(c, id).bsr_b > 0) fail(PMB_EUNSUPPORTED, "%s of a block-sparse Parameter has no device lowering", what);
+}
+static void need_no_sparse(const AffForm& f, const char* what) {
+    if (!f.sps.empty()) fail(PMB_EUNSUPPORTED, "%s over a block-sparse product has no device lowering", what);
+}
+
 static int op_matvec_matrix(pmb_ctx* c, int A, int x) {
     const Node a = node_at(c, A);  // copy: the node vector may grow below
     const Node& xn = node_at(c, x);
     if (xn.kind == PMB_KIND_NUM_VECTOR) {
+        need_dense(c, A, "Matrix * numbers");
         if (a.cols != xn.rows) fail(PMB_EDIM, "DimensionMismatch: A has %lld columns, x has length %lld", (long long)a.cols, (long long)xn.rows);
         return make_gemv(c, A, x, 0, 0, a.cols, 0);
     }
     if (xn.kind != PMB_KIND_VARVEC && xn.kind != PMB_KIND_AFFVEC) fail(PMB_EUNSUPPORTED, "Matrix * (kind %d) has no device lowering", xn.kind);
     if (a.cols != xn.rows)  // functions.jl:780-781
         fail(PMB_EDIM, "DimensionMismatch: A has %lld columns, x has length %lld", (long long)a.cols, (long long)xn.rows);
+    if (a.bsr_b > 0) {
+        if (xn.kind != PMB_KIND_VARVEC) fail(PMB_EUNSUPPORTED, "block-sparse Matrix * x needs x::Vector{Variable}");
+        AffForm y;
+        y.rows = a.rows;
+        y.order_exact = false;  // the reference would also emit the structural zeros as terms
+        SpTerm t; t.mat = A; t.vars = xn.vars;
+        y.sps.push_back(std::move(t));
+        return push_aff(c, PMB_KIND_AFFVEC, std::move(y));
+    }
     AffForm fx = aff_of(c, x);
+    need_no_sparse(fx, "Matrix * x");
     AffForm y;
     y.rows = a.rows;
     // Variables / unit terms of x: column gather of A        (functions.jl:790-796 and :806-818 with single-term rows)
@@ -321,6 +346,7 @@ static int op_dot_impl(pmb_ctx* c, int x, int y) {
         // numbers . (variables | affine functions) -> AffineFunction          functions.jl:665-687
         const int v = kx == PMB_KIND_NUM_VECTOR ? x : y, fn = kx == PMB_KIND_NUM_VECTOR ? y : x;
         AffForm f = aff_of(c, fn);
+        need_no_sparse(f, "dot");
         AffForm out;
         out.rows = 1;
         out.order_exact = f.mats.empty() && f.units.size() == 1 && f.units[0].row_off == 0 && f.units[0].rows == f.rows;
@@ -355,6 +381,8 @@ static int op_dot_impl(pmb_ctx* c, int x, int y) {
     GramTerm g;
     g.f = aff_of(c, x);
     g.h = aff_of(c, y);
+    need_no_sparse(g.f, "dot");
+    need_no_sparse(g.h, "dot");
     g.same = x == y;
     q.grams.push_back(std::move(g));
     return push_quad(c, std::move(q));
@@ -366,6 +394,8 @@ static int op_addsub(pmb_ctx* c, int x, int y, double sign) {
     const int kx = xn.kind, ky = yn.kind;
     if (is_numeric(kx) && is_numeric(ky)) {
         if (kx != ky || xn.rows != yn.rows || xn.cols != yn.cols) fail(PMB_EDIM, "DimensionMismatch in numeric +/-");
+        need_dense(c, x, "+/-");
+        need_dense(c, y, "+/-");
         return make_lincomb(c, kx, xn.rows, xn.cols, {LinTermH{Alpha{1.0, -1}, x, 0}, LinTermH{Alpha{sign, -1}, y, 0}});
     }
     auto is_vec = [](int k) { return k == PMB_KIND_NUM_VECTOR || k == PMB_KIND_VARVEC || k == PMB_KIND_AFFVEC; };
@@ -433,6 +463,27 @@ int pmb_param_create(pmb_ctx* ctx, int ndims, int64_t rows, int64_t cols, int mo
     Node n;
     n.kind = kind_of_ndims(ndims, rows, cols);
     n.rows = rows; n.cols = cols; n.is_const = false; n.nop = NOP_PARAM; n.pmode = mode;
+    *out = push_node(ctx, std::move(n));
+    API_END(ctx)
+}
+
+int pmb_param_create_bsr(pmb_ctx* ctx, int64_t rows, int64_t cols, int64_t b, int64_t nblocks, const int64_t* block_rows,
+                         const int64_t* block_cols, int mode, pmb_node* out) {
+    API_BEGIN(ctx)
+    need_build_phase(ctx, "Parameter(model)");
+    if (rows < 0 || cols < 0 || b < 1 || nblocks < 0 || !out || (nblocks > 0 && (!block_rows || !block_cols)))
+        fail(PMB_EINVAL, "bad block-sparse Parameter shape");
+    if (rows % b != 0 || cols % b != 0) fail(PMB_EINVAL, "block size %lld does not divide %lld x %lld", (long long)b, (long long)rows, (long long)cols);
+    if (mode != PMB_PARAM_DEVICE && mode != PMB_PARAM_HOST && mode != PMB_PARAM_UNIFORM) fail(PMB_EINVAL, "bad Parameter mode %d", mode);
+    Node n;
+    n.kind = PMB_KIND_NUM_MATRIX; n.rows = rows; n.cols = cols; n.is_const = false; n.nop = NOP_PARAM; n.pmode = mode;
+    n.bsr_b = b; n.bsr_nblocks = nblocks;
+    for (int64_t i = 0; i < nblocks; ++i) {
+        if (block_rows[i] < 0 || block_rows[i] >= rows / b || block_cols[i] < 0 || block_cols[i] >= cols / b)
+            fail(PMB_EINVAL, "block %lld at (%lld, %lld) is outside the matrix", (long long)i, (long long)block_rows[i], (long long)block_cols[i]);
+        n.bsr_brow.push_back(block_rows[i]);
+        n.bsr_bcol.push_back(block_cols[i]);
+    }
     *out = push_node(ctx, std::move(n));
     API_END(ctx)
 }
@@ -541,6 +592,7 @@ int pmb_op_adjoint(pmb_ctx* ctx, pmb_node A, pmb_node* out) {
     if (!out) fail(PMB_EINVAL, "null out");
     const Node& a = node_at(ctx, A);
     if (a.kind == PMB_KIND_NUM_MATRIX) {  // lazyexpression.jl:206-217: explicit transposed copy into a buffer
+        need_dense(ctx, A, "adjoint");
         *out = make_transpose(ctx, A);
     } else if (a.kind == PMB_KIND_NUM_VECTOR || a.kind == PMB_KIND_VARVEC || a.kind == PMB_KIND_AFFVEC) {
         Node n;
@@ -587,6 +639,7 @@ int pmb_op_bilinear(pmb_ctx* ctx, pmb_node xT, pmb_node Q, pmb_node y, pmb_node*
     if (xa.kind != PMB_KIND_ADJVEC || node_at(ctx, xa.adj_parent).kind != PMB_KIND_VARVEC || qn.kind != PMB_KIND_NUM_MATRIX ||
         yn.kind != PMB_KIND_VARVEC)
         fail(PMB_EUNSUPPORTED, "x' * Q * y needs Variables' * Matrix * Variables (lazyexpression.jl:219-226)");
+    need_dense(ctx, Q, "x' * Q * y");
     const Node& xn = node_at(ctx, xa.adj_parent);
     if (qn.rows != xn.rows || qn.cols != yn.rows)  // functions.jl:845
         fail(PMB_EDIM, "DimensionMismatch: size(Q) = (%lld, %lld), length(x) = %lld, length(y) = %lld", (long long)qn.rows, (long long)qn.cols,
@@ -647,6 +700,7 @@ int pmb_op_mul(pmb_ctx* ctx, pmb_node x, pmb_node y, pmb_node* out) {
                     *out = id;
                 }
             } else {
+                need_dense(ctx, o, "scalar * Matrix");
                 *out = make_lincomb(ctx, on.kind, on.rows, on.cols, {LinTermH{m, o, 0}});
             }
         } else if (on.kind == PMB_KIND_VARVEC || on.kind == PMB_KIND_AFFVEC || on.kind == PMB_KIND_AFF) {
@@ -711,6 +765,7 @@ int pmb_set_objective(pmb_ctx* ctx, int sense, pmb_node expr) {
     const Node& n = node_at(ctx, expr);
     if (n.kind != PMB_KIND_AFF && n.kind != PMB_KIND_QUAD && n.kind != PMB_KIND_NUM_SCALAR)
         fail(PMB_EUNSUPPORTED, "Unhandled objective type (kind %d)", n.kind);  // model.jl:139
+    if (n.kind != PMB_KIND_QUAD) need_no_sparse(aff_of(ctx, expr), "an objective");
     ctx->obj_node = expr;
     ctx->obj_sense = sense;
     ctx->obj_kind = n.kind == PMB_KIND_QUAD ? PMB_KIND_QUAD : PMB_KIND_AFF;  // canonical_function_type, moi_interop.jl:96-101
@@ -734,6 +789,11 @@ int pmb_add_constraint(pmb_ctx* ctx, pmb_node expr, int set_kind, int32_t* block
     }
     con.form = aff_of(ctx, expr);
     con.rows = con.form.rows;
+    if (!con.form.sps.empty()) {
+        if (con.form.sps.size() != 1 || !con.form.mats.empty() || !con.form.units.empty())
+            fail(PMB_EUNSUPPORTED, "a block-sparse product must be the only coefficient source of its constraint block");
+        con.sparse = true;
+    }
     ctx->cons.push_back(std::move(con));
     if (block_id) *block_id = (int32_t)ctx->cons.size() - 1;
     API_END(ctx)

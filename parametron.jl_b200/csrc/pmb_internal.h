@@ -37,6 +37,13 @@ struct OffTerm {
     int vec = -1;
     int64_t src_off = 0, row_off = 0, rows = 0;
 };
+// block-sparse source (BSR values buffer):  G[row(e), var(vars[col(e)])] += alpha * vals[e]  for every stored coefficient e
+// (the dense meaning of matvecmul! over a matrix whose other entries are structural zeros, functions.jl:775-798)
+struct SpTerm {
+    Alpha a;
+    int mat = -1;               // BSR Parameter node
+    std::vector<int64_t> vars;  // 1-based model variable per matrix column
+};
 struct OrdSeg {
     int is_unit = 0;
     std::vector<int> idx;  // indices into mats (members share row_off/rows/cols) or a single index into units
@@ -47,6 +54,7 @@ struct AffForm {
     std::vector<MatTerm> mats;
     std::vector<UnitTerm> units;
     std::vector<OffTerm> offs;
+    std::vector<SpTerm> sps;                   // block-sparse sources (a block with one of these is emitted in sparse form)
     std::vector<double> coff;                  // folded constant offsets (size rows, or empty == zeros)
     // Reference term-append order, per row: segments are visited in order; a matrix segment with several members emits
     // its members interleaved per source column (matvecmul! over Vector{AffineFunction}, functions.jl:800-822).
@@ -97,6 +105,9 @@ struct Node {
     int64_t dot_xoff = 0, dot_yoff = 0, dot_n = 0;
     int64_t gm_xoff = 0, gm_yoff = 0, gm_k = 0;  // NOP_GEMM_TN: node (rows x cols) = X[xoff.., :]' * Y[:, yoff..] over gm_k rows
     double sprod_c = 1.0;
+    // block-sparse (BSR) matrices: value buffer = nblocks x (b x b column-major); static block coordinates
+    int64_t bsr_b = 0, bsr_nblocks = 0;
+    std::vector<int64_t> bsr_brow, bsr_bcol;   // 0-based block row / block column of each stored block
     // parameters
     int pmode = -1;
     uint64_t seed = 0;
@@ -158,6 +169,12 @@ struct Constraint {
     double* C = nullptr;
     double* d = nullptr;
     int64_t nterms = 0;
+    // sparse form (the block's only coefficient source is one BSR matrix)
+    bool sparse = false;
+    int64_t nnz = 0;
+    double* vals = nullptr;
+    int32_t* sp_rows = nullptr;
+    int32_t* sp_cols = nullptr;
     AffForm form;
 };
 

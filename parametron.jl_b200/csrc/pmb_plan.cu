@@ -62,6 +62,7 @@ static void mark_aff(pmb_ctx* c, const AffForm& f) {
     for (auto& t : f.mats) { mark(c, t.mat); mark(c, t.a.node); }
     for (auto& t : f.units) mark(c, t.a.node);
     for (auto& t : f.offs) { mark(c, t.vec); mark(c, t.a.node); }
+    for (auto& t : f.sps) { mark(c, t.mat); mark(c, t.a.node); }
 }
 static void mark_quad(pmb_ctx* c, const QuadForm& q) {
     for (auto& g : q.grams) { mark(c, g.a.node); mark_aff(c, g.f); mark_aff(c, g.h); }
@@ -298,6 +299,59 @@ static Step affine_step(const AffBlockDev& b, int64_t batch) {
     Step s;
     s.type = ST_AFFINE; s.cls = KC_AFFINE; s.batch = batch; s.aff = b;
     return s;
+}
+
+// ---- sparse constraint block (one BSR source): values-only update over a static (row, optimizer column) index ---------
+static void plan_sparse_block(pmb_ctx* c, Constraint& con) {
+    const SpTerm& sp = con.form.sps[0];
+    const Node& mn = c->nodes[sp.mat];
+    const int64_t b = mn.bsr_b, nb = mn.bsr_nblocks, nnz = nb * b * b;
+    std::vector<int32_t> rows((size_t)nnz), cols((size_t)nnz);
+    for (int64_t blk = 0; blk < nb; ++blk)
+        for (int64_t j = 0; j < b; ++j)
+            for (int64_t i = 0; i < b; ++i) {
+                const size_t e = (size_t)((blk * b + j) * b + i);  // block-major, column-major inside a block
+                rows[e] = (int32_t)(mn.bsr_brow[(size_t)blk] * b + i);
+                cols[e] = optcol(c, sp.vars[(size_t)(mn.bsr_bcol[(size_t)blk] * b + j)]);
+            }
+    con.nnz = nnz;
+    con.vals = dalloc<double>(c, c->batch * nnz, true);
+    con.d = dalloc<double>(c, c->batch * con.rows, true);
+    con.sp_rows = upload(c, rows);
+    con.sp_cols = upload(c, cols);
+    con.nterms = con.rows * (int64_t)sp.vars.size();  // what the reference would emit: every entry, zeros included
+    std::vector<Step>& st = con.is_const ? c->init_steps : c->steps;
+    // coefficients: one contiguous (scaled) copy of the value buffer -> a one-column "simple" block of nnz rows
+    if (nnz > 0) {
+        AffBlockDev v{};
+        v.C = con.vals; v.d = nullptr; v.C_bstride = nnz; v.d_bstride = 0; v.rows = nnz; v.ntouched = 1;
+        v.col_out = upload(c, std::vector<int32_t>{0});
+        v.col_src = upload(c, std::vector<int32_t>{0});
+        v.col_ptr = upload(c, std::vector<int32_t>{0, 1});
+        v.entries = upload(c, std::vector<AffColEntry>{AffColEntry{0, 0}});
+        v.mats = upload(c, std::vector<AffMatTermDev>{AffMatTermDev{mn.dptr, mn.bstride, nnz, 0, nnz, alpha_dev(c, sp.a)}});
+        v.simple = 1;
+        v.vec2 = (nnz % 2 == 0 && mn.bstride % 2 == 0 && aligned16(mn.dptr) && aligned16(con.vals)) ? 1 : 0;
+        if (v.vec2 && c->use_tma) {
+            std::vector<AffSeg> segs;
+            for (int64_t o = 0; o < nnz; o += kAffStageBytes / 8)
+                segs.push_back(AffSeg{o, o, (int32_t)(std::min<int64_t>(kAffStageBytes / 8, nnz - o) * 8), 0});
+            std::vector<int32_t> cf(segs.size() + 1);
+            for (size_t i = 0; i <= segs.size(); ++i) cf[i] = (int32_t)i;
+            v.segs = upload(c, segs); v.chunk_first = upload(c, cf); v.nchunks = (int32_t)segs.size();
+            v.tma = (sp.a.node < 0 && sp.a.c == 1.0) ? 1 : 2;
+            v.uniform = 1; v.u_src0 = 0; v.u_dst0 = 0; v.u_src_stride = v.u_dst_stride = kAffStageBytes / 8;
+            v.u_bytes = segs[0].bytes; v.u_last_bytes = segs.back().bytes;
+        }
+        st.push_back(affine_step(v, c->batch));
+    }
+    // offsets d
+    AffForm only_off;
+    only_off.rows = con.rows; only_off.offs = con.form.offs; only_off.coff = con.form.coff;
+    Step os = affine_step(lower_aff(c, only_off, nullptr, 0, con.d, con.rows, true, nullptr), c->batch);
+    os.cls = KC_MISC;
+    st.push_back(os);
+    if (!con.is_const) c->affine_bytes += 16 * nnz + 16 * con.rows;
 }
 
 // ---- objective ---------------------------------------------------------------------------------
@@ -626,6 +680,7 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
     plan_objective(ctx);
     for (int ci : ctx->update_order) {
         Constraint& con = ctx->cons[(size_t)ci];
+        if (con.sparse) { plan_sparse_block(ctx, con); continue; }
         con.C = dalloc<double>(ctx, ctx->batch * con.rows * N, true);
         con.d = dalloc<double>(ctx, ctx->batch * con.rows, true);
         con.nterms = aff_nterms(con.form);
@@ -741,6 +796,7 @@ int pmb_get_block(pmb_ctx* ctx, int32_t update_pos, pmb_block_view* out) {
     Constraint& con = block_at(ctx, update_pos);
     out->set_kind = con.set_kind; out->is_scalar = con.is_scalar ? 1 : 0; out->is_constant = con.is_const ? 1 : 0;
     out->bucket = con.bucket; out->rows = con.rows; out->nvars = ctx->nvars; out->C = con.C; out->d = con.d; out->nterms = con.nterms;
+    out->is_sparse = con.sparse ? 1 : 0; out->nnz = con.nnz; out->vals = con.vals; out->sp_rows = con.sp_rows; out->sp_cols = con.sp_cols;
     API_END(ctx)
 }
 
@@ -748,6 +804,7 @@ int pmb_block_term_index(pmb_ctx* ctx, int32_t update_pos, int64_t capacity, int
     API_BEGIN(ctx)
     Constraint& con = block_at(ctx, update_pos);
     const AffForm& f = con.form;
+    if (con.sparse) fail(PMB_EUNSUPPORTED, "sparse blocks export their static index through pmb_block_view (sp_rows, sp_cols)");
     if (!f.order_exact) fail(PMB_EUNSUPPORTED, "the reference's term order of this block is not reproducible from the device lowering");
     if (capacity < con.nterms) fail(PMB_EINVAL, "capacity %lld < %lld terms", (long long)capacity, (long long)con.nterms);
     // update!(::VectorAffineFunction): row-outer, term-inner, varmap applied (moi_interop.jl:64-81)

@@ -109,7 +109,14 @@ class Parameter(Expr):
     Matrices are column-major (Julia layout); with batch > 1 every value has a leading instance axis.
     """
 
-    def __init__(self, model, f=None, val=None, shape=None, uniform=None, device=False, device_ptr=None):
+    def __init__(self, model, f=None, val=None, shape=None, uniform=None, device=False, device_ptr=None, bsr=None):
+        """bsr=(rows, cols, b, block_rows, block_cols): block-sparse matrix; the value is an (nblocks, b, b) array of blocks."""
+        self.bsr = None
+        if bsr is not None:
+            rows_, cols_, b_, br, bc = bsr
+            br, bc = np.ascontiguousarray(br, dtype=np.int64), np.ascontiguousarray(bc, dtype=np.int64)
+            self.bsr = (int(rows_), int(cols_), int(b_), br, bc)
+            shape = (len(br), int(b_), int(b_))
         self.f = f
         self.inplace = val is not None
         self.evaluations = 0
@@ -128,13 +135,18 @@ class Parameter(Expr):
             val = np.asarray(val, dtype=np.float64)
             shape = val.shape[1:] if model.batch > 1 else val.shape
         shape = tuple(int(s) for s in (shape if shape is not None else ()))
-        if len(shape) > 2:
+        if len(shape) > 2 and self.bsr is None:
             raise ValueError("Parameters are scalars, vectors or matrices")
         self.shape = shape
         rows = shape[0] if len(shape) >= 1 else 0
         cols = shape[1] if len(shape) == 2 else 0
         out = C.c_int32()
-        model._ck(model._lib.pmb_param_create(model._ctx, len(shape), rows, cols, mode, out))
+        if self.bsr is not None:
+            r_, c_, b_, br, bc = self.bsr
+            model._ck(model._lib.pmb_param_create_bsr(model._ctx, r_, c_, b_, len(br), C.c_void_p(br.ctypes.data), C.c_void_p(bc.ctypes.data),
+                                                      mode, out))
+        else:
+            model._ck(model._lib.pmb_param_create(model._ctx, len(shape), rows, cols, mode, out))
         super().__init__(model, out.value)
         self.mode = mode
         self.numel = int(np.prod(shape)) if shape else 1
@@ -152,7 +164,8 @@ class Parameter(Expr):
             self.val = val
         model.params.append(self)
 
-    def _store(self, val):
+    def _to_device_layout(self, val):
+        """[instance][column-major value] (BSR: [instance][block][column-major block])"""
         val = np.asarray(val, dtype=np.float64)
         b = self.model.batch
         full = ((b,) if b > 1 else ()) + self.shape
@@ -160,8 +173,13 @@ class Parameter(Expr):
             raise K.DimensionMismatch(K.EDIM, f"Parameter value has shape {val.shape}, expected {full}")
         v = val.reshape((b,) + self.shape)
         if len(self.shape) == 2:
-            v = np.transpose(v, (0, 2, 1))  # column-major per instance
-        self.host[...] = v.reshape(b, self.numel)
+            v = np.transpose(v, (0, 2, 1))
+        elif len(self.shape) == 3:
+            v = np.transpose(v, (0, 1, 3, 2))
+        return v.reshape(b, self.numel)
+
+    def _store(self, val):
+        self.host[...] = self._to_device_layout(val)
 
     def _evaluate(self):
         """parameter.jl:93-102 -- called once per update! by Model.update (the dirty flag is the update itself)."""
@@ -178,13 +196,9 @@ class Parameter(Expr):
     # device-resident manual mode
     def upload(self, val):
         m = self.model
-        val = np.asarray(val, dtype=np.float64)
         b = m.batch
-        v = val.reshape((b,) + self.shape)
-        if len(self.shape) == 2:
-            v = np.transpose(v, (0, 2, 1))
         stage = m._pinned((b, self.numel))
-        stage[...] = v.reshape(b, self.numel)
+        stage[...] = self._to_device_layout(val)
         m._ck(m._lib.pmb_param_upload(m._ctx, self.node, C.c_void_p(stage.ctypes.data)))
         m.synchronize()
 
@@ -196,9 +210,13 @@ class Parameter(Expr):
 
     def download(self):
         m = self.model
-        out = m._d2h(self.device_ptr, m.batch * self.numel).reshape((m.batch,) + self.shape[::-1])
-        if len(self.shape) == 2:
-            out = np.transpose(out, (0, 2, 1))
+        flat = m._d2h(self.device_ptr, m.batch * self.numel)
+        if len(self.shape) == 3:
+            out = np.transpose(flat.reshape((m.batch, self.shape[0], self.shape[2], self.shape[1])), (0, 1, 3, 2))
+        else:
+            out = flat.reshape((m.batch,) + self.shape[::-1])
+            if len(self.shape) == 2:
+                out = np.transpose(out, (0, 2, 1))
         return out if m.batch > 1 else out[0]
 
 
@@ -254,10 +272,10 @@ class Model:
         self._pins.append(arr)
         return arr
 
-    def _d2h(self, dptr, count):
-        out = np.empty(count, dtype=np.float64)
+    def _d2h(self, dptr, count, dtype=np.float64):
+        out = np.empty(count, dtype=dtype)
         if count:
-            self._ck(self._lib.pmb_memcpy_d2h(self._ctx, C.c_void_p(out.ctypes.data), C.c_void_p(dptr), count * 8))
+            self._ck(self._lib.pmb_memcpy_d2h(self._ctx, C.c_void_p(out.ctypes.data), C.c_void_p(dptr), out.nbytes))
             self.synchronize()
         return out
 
@@ -384,9 +402,27 @@ class Model:
         """(C, d) of the constraint block at update position `pos` (C x + d in the set), copied to the host."""
         v = self.block_view(pos)
         m, N, b = v.rows, v.nvars, self.batch
-        Cm = np.transpose(self._d2h(v.C, b * m * N).reshape(b, N, m), (0, 2, 1))
         d = self._d2h(v.d, b * m).reshape(b, m)
+        if v.is_sparse:  # densify on the host for inspection: duplicates (a variable used twice) are summed
+            vals, rows, cols, _ = self.block_sparse(pos)
+            Cm = np.zeros((b, m, N))
+            for i in range(b):
+                np.add.at(Cm[i], (rows, cols), vals.reshape(b, -1)[i])
+        else:
+            Cm = np.transpose(self._d2h(v.C, b * m * N).reshape(b, N, m), (0, 2, 1))
         return (Cm[0], d[0]) if b == 1 else (Cm, d)
+
+    def block_sparse(self, pos):
+        """(vals, rows, cols, d) of a sparse block: coefficient e is vals[e] at 0-based (rows[e], cols[e]); the index is static."""
+        v = self.block_view(pos)
+        if not v.is_sparse:
+            raise ValueError("block is dense")
+        b = self.batch
+        vals = self._d2h(v.vals, b * v.nnz).reshape(b, v.nnz)
+        rows = self._d2h(v.sp_rows, v.nnz, np.int32)
+        cols = self._d2h(v.sp_cols, v.nnz, np.int32)
+        d = self._d2h(v.d, b * v.rows).reshape(b, v.rows)
+        return (vals[0], rows, cols, d[0]) if b == 1 else (vals, rows, cols, d)
 
     def block_terms(self, pos):
         """(rows, vars, src) of the reference's VectorAffineTerm list for this block (moi_interop.jl:64-81), int64, 1-based."""

@@ -184,3 +184,76 @@ def test_empty_and_degenerate_shapes():
         Cb, db = model.block_arrays(0)
         assert Cb.shape == (m, n) and np.array_equal(Cb, host["C"]) and np.array_equal(db, -host["d"])
         model.close()
+
+
+def _random_bsr(rng, rows, cols, b, density):
+    nbr, nbc = rows // b, cols // b
+    mask = rng.random((nbr, nbc)) < density
+    mask[0, 0] = True
+    br, bc = np.nonzero(mask)
+    return br.astype(np.int64), bc.astype(np.int64)
+
+
+@pytest.mark.parametrize("rows,cols,b,density,perm", [(64, 128, 16, 0.2, False), (96, 160, 32, 0.3, True), (4096, 16384, 32, 0.01, False)])
+def test_block_sparse_constraint(rows, cols, b, density, perm):
+    """BASELINE.json configs[3]: 1 % block-sparse C, affine-only assembly.  The reference has no sparse path (matvecmul! visits
+    every A[i], functions.jl:790-796), so parity is against the dense meaning: the sparse block densified == (C_dense, -d)."""
+    import parametron_b200 as pm
+    rng = np.random.default_rng(rows + b)
+    br, bc = _random_bsr(rng, rows, cols, b, density)
+    blocks = rng.standard_normal((len(br), b, b))
+    dv = rng.standard_normal(rows)
+    model = pm.Model()
+    x = model.variables(cols)
+    Cp = pm.Parameter(model, val=blocks, bsr=(rows, cols, b, br, bc))
+    dp = pm.Parameter(model, val=dv)
+    pm.constraint(model, Cp * x, "==", dp)
+    vm = (rng.permutation(cols) + 1) if perm else None
+    model.initialize(idxmap=vm)
+    model.update()
+    v = model.block_view(0)
+    assert v.is_sparse == 1 and v.nnz == len(br) * b * b and not v.C
+    vals, rws, cls_, d = model.block_sparse(0)
+    dense = np.zeros((rows, cols))
+    for k_, (i, j) in enumerate(zip(br, bc)):
+        dense[i * b:(i + 1) * b, j * b:(j + 1) * b] = blocks[k_]
+    Co, do = D.affine_block(dense, dv, np.arange(1, cols + 1), cols, varmap=vm)
+    got = np.zeros((rows, cols))
+    got[rws, cls_] = vals
+    assert np.array_equal(got, Co) and np.array_equal(d, do)      # pure copies: bit-exact
+    assert model.stats()["affine_algorithmic_bytes"] == 16 * v.nnz + 16 * rows
+    # values-only update over the static index
+    blocks2 = rng.standard_normal(blocks.shape)
+    Cp.val = blocks2
+    model.update()
+    vals2, rws2, cls2, _ = model.block_sparse(0)
+    assert np.array_equal(rws2, rws) and np.array_equal(cls2, cls_)
+    assert np.array_equal(vals2, np.transpose(blocks2, (0, 2, 1)).ravel())
+    model.close()
+
+
+def test_block_sparse_small_against_literal_oracle():
+    """small enough for the literal term list: the oracle runs the DENSE matrix (zeros included), densified results must agree."""
+    import parametron_b200 as pm
+    from tests.twin import OracleSide, oracle_outputs
+    rows, cols, b = 8, 12, 4
+    rng = np.random.default_rng(8)
+    br, bc = _random_bsr(rng, rows, cols, b, 0.5)
+    blocks = rng.random((len(br), b, b))
+    dv = rng.random(rows)
+    dense = np.zeros((rows, cols))
+    for k_, (i, j) in enumerate(zip(br, bc)):
+        dense[i * b:(i + 1) * b, j * b:(j + 1) * b] = blocks[k_]
+    o = OracleSide()
+    xo = o.variables(cols)
+    o.constraint(o.mul(o.parameter({"v": dense}), xo), ">=", o.parameter({"v": dv}))
+    o.model.initialize()
+    _, oblocks, _ = oracle_outputs(o.model, cols)
+    model = pm.Model()
+    x = model.variables(cols)
+    pm.constraint(model, pm.Parameter(model, val=blocks, bsr=(rows, cols, b, br, bc)) * x, ">=", pm.Parameter(model, val=dv))
+    model.initialize()
+    model.update()
+    Cd, dd = model.block_arrays(0)
+    assert np.array_equal(Cd, oblocks[0][0]) and np.array_equal(dd, oblocks[0][1])
+    assert model.block_view(0).nterms == rows * cols  # what the reference emits: every entry, zeros included
