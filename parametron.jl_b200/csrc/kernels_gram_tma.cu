@@ -22,13 +22,12 @@
 
 namespace pmb {
 
-constexpr int kTBM = 128;
+constexpr int kTBM = 128;  // large-problem tile; small problems (less than one wave of 128-tiles) use 64 x 64 tiles
 constexpr int kTKT = 16;
 constexpr int kTStages = 6;
 constexpr int kTConsumerWarps = 8;
 constexpr int kTThreads = (kTConsumerWarps + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup (setmaxnreg is per warpgroup)
-constexpr int kTPanelBytes = kTBM * kTKT * 8;             // 16 KB
-constexpr int kTSmemBytes = kTStages * 2 * kTPanelBytes + 1024;  // 192 KB + slack to align the ring to the 1 KB swizzle period
+constexpr int kTSmemBytes = kTStages * 2 * kTBM * kTKT * 8 + 1024;  // 192 KB + slack to align the ring to the 1 KB swizzle period
 
 struct GramTmaKernelArgs {
     CUtensorMap tmx, tmy;
@@ -121,18 +120,18 @@ __device__ __forceinline__ Unit decode_unit(const GramTmaKernelArgs& a, int64_t 
     return w;
 }
 
-template <bool SYRK, bool ADD>
-__device__ __forceinline__ void store_tile(const GramTmaKernelArgs& a, double (&acc)[4][4][4], double* out, double sc, int64_t i0, int64_t j0,
-                                           bool diag, int wm, int wn, int pg, int t) {
+template <bool SYRK, bool ADD, int BM>
+__device__ __forceinline__ void store_tile(const GramTmaKernelArgs& a, double (&acc)[BM / 32][BM / 32][4], double* out, double sc, int64_t i0,
+                                           int64_t j0, bool diag, int wm, int wn, int pg, int t) {
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
+    for (int mi = 0; mi < BM / 32; ++mi) {
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
+        for (int ni = 0; ni < BM / 32; ++ni) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int cj = 2 * t + (r & 1);  // accumulator column index inside the 8-wide fragment -> panel column pi(cj)
-                const int64_t m = i0 + wm * 64 + mi * 16 + pg + (r >> 1) * 8;
-                const int64_t nn = j0 + wn * 32 + ni * 8 + (((2 * cj) & 7) + (cj >> 2));
+                const int64_t m = i0 + wm * (BM / 2) + mi * 16 + pg + (r >> 1) * 8;
+                const int64_t nn = j0 + wn * (BM / 4) + ni * 8 + (((2 * cj) & 7) + (cj >> 2));
                 if (m < a.n && nn < a.p) {
                     const double v = sc * acc[mi][ni][r];
                     if (SYRK) {
@@ -153,8 +152,10 @@ __device__ __forceinline__ void store_tile(const GramTmaKernelArgs& a, double (&
     }
 }
 
-template <bool SYRK>
+template <bool SYRK, int BM>
 __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_constant__ GramTmaKernelArgs a) {
+    constexpr int MI = BM / 32, NI = BM / 32;      // warp tile (BM/2) x (BM/4) = MI x NI fragments of 16 x 8
+    constexpr int kPanelBytes = BM * kTKT * 8;     // one operand panel of one stage: BM columns x 128 bytes
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kTStages];
     __shared__ __align__(8) uint64_t empty_bar[kTStages];
@@ -180,10 +181,10 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
                 for (int kt = w.kt0; kt < w.kt1; ++kt, ++it) {
                     const int s = it % kTStages;
                     mb_wait(&empty_bar[s], ((it / kTStages) & 1) ^ 1);
-                    const uint32_t stage = ring + (uint32_t)s * 2 * kTPanelBytes;
-                    mb_expect_tx(&full_bar[s], diag ? kTPanelBytes : 2 * kTPanelBytes);
-                    tma_load_3d(stage, &a.tmx, kt * kTKT, w.ti * kTBM, (int)w.inst, &full_bar[s]);
-                    if (!diag) tma_load_3d(stage + kTPanelBytes, &a.tmy, kt * kTKT, w.tj * kTBM, (int)w.inst, &full_bar[s]);
+                    const uint32_t stage = ring + (uint32_t)s * 2 * kPanelBytes;
+                    mb_expect_tx(&full_bar[s], diag ? kPanelBytes : 2 * kPanelBytes);
+                    tma_load_3d(stage, &a.tmx, kt * kTKT, w.ti * BM, (int)w.inst, &full_bar[s]);
+                    if (!diag) tma_load_3d(stage + kPanelBytes, &a.tmy, kt * kTKT, w.tj * BM, (int)w.inst, &full_bar[s]);
                 }
             }
         }
@@ -200,39 +201,39 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
     uint32_t koff[kTKT / 4];  // byte offset of this thread's k element inside a swizzled 128-byte column line, per k-block
 #pragma unroll
     for (int kb = 0; kb < kTKT / 4; ++kb) koff[kb] = (uint32_t)((((kb * 2 + (t >> 1)) ^ pg) << 4) + (t & 1) * 8);
-    const uint32_t a_row = (uint32_t)((wm * 64 + pg) * 128);
-    const uint32_t b_row = (uint32_t)((wn * 32 + pg) * 128);
+    const uint32_t a_row = (uint32_t)((wm * (BM / 2) + pg) * 128);
+    const uint32_t b_row = (uint32_t)((wn * (BM / 4) + pg) * 128);
     uint32_t it = 0;
     for (int64_t u = blockIdx.x; u < a.total_units; u += gridDim.x) {
         const Unit w = decode_unit<SYRK>(a, u);
         const bool diag = SYRK && w.ti == w.tj;
-        double acc[4][4][4];
+        double acc[MI][NI][4];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
+            for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) acc[mi][ni][r] = 0.0;
 
         for (int kt = w.kt0; kt < w.kt1; ++kt, ++it) {
             const int s = it % kTStages;
             mb_wait(&full_bar[s], (it / kTStages) & 1);
-            const uint32_t sA = ring + (uint32_t)s * 2 * kTPanelBytes + a_row;
-            const uint32_t sB = ring + (uint32_t)s * 2 * kTPanelBytes + (diag ? 0u : (uint32_t)kTPanelBytes) + b_row;
+            const uint32_t sA = ring + (uint32_t)s * 2 * kPanelBytes + a_row;
+            const uint32_t sB = ring + (uint32_t)s * 2 * kPanelBytes + (diag ? 0u : (uint32_t)kPanelBytes) + b_row;
 #pragma unroll
             for (int kb = 0; kb < kTKT / 4; ++kb) {
-                double af[4][2], bf[4];
+                double af[MI][2], bf[NI];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) {
+                for (int mi = 0; mi < MI; ++mi) {
                     af[mi][0] = lds_f64(sA + mi * 16 * 128 + koff[kb]);
                     af[mi][1] = lds_f64(sA + (mi * 16 + 8) * 128 + koff[kb]);
                 }
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) bf[ni] = lds_f64(sB + ni * 8 * 128 + koff[kb]);
+                for (int ni = 0; ni < NI; ++ni) bf[ni] = lds_f64(sB + ni * 8 * 128 + koff[kb]);
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) dmma_16x8x4(acc[mi][ni], af[mi][0], af[mi][1], bf[ni]);
+                    for (int ni = 0; ni < NI; ++ni) dmma_16x8x4(acc[mi][ni], af[mi][0], af[mi][1], bf[ni]);
             }
             __syncwarp();
             if (lane == 0) mb_arrive(&empty_bar[s]);  // this warp is done reading the stage
@@ -240,13 +241,13 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
 
         // ---- k-slices: park the partial, the last arriver sums all partials of the tile in slice order ----
         if (w.nslices > 1) {
-            double* ws = a.workspace + ((w.split_id * w.nslices + w.slice) * 64) * (int64_t)(kTConsumerWarps * 32) + tid;
+            double* ws = a.workspace + ((w.split_id * w.nslices + w.slice) * (MI * NI * 4)) * (int64_t)(kTConsumerWarps * 32) + tid;
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+            for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
+                for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) __stcg(ws + ((mi * 4 + ni) * 4 + r) * (kTConsumerWarps * 32), acc[mi][ni][r]);
+                    for (int r = 0; r < 4; ++r) __stcg(ws + ((mi * NI + ni) * 4 + r) * (kTConsumerWarps * 32), acc[mi][ni][r]);
             __threadfence();
             consumer_bar();
             if (tid == 0) {
@@ -259,33 +260,35 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
             if (!arrival_flag) continue;  // uniform across the consumer warps
             __threadfence();
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+            for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
+                for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
                     for (int r = 0; r < 4; ++r) acc[mi][ni][r] = 0.0;
-            const double* wr = a.workspace + (w.split_id * w.nslices * 64) * (int64_t)(kTConsumerWarps * 32) + tid;
-            for (int sl = 0; sl < w.nslices; ++sl, wr += 64 * (kTConsumerWarps * 32)) {
+            const double* wr = a.workspace + (w.split_id * w.nslices * (MI * NI * 4)) * (int64_t)(kTConsumerWarps * 32) + tid;
+            for (int sl = 0; sl < w.nslices; ++sl, wr += (MI * NI * 4) * (kTConsumerWarps * 32)) {
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni)
+                    for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) acc[mi][ni][r] += __ldcg(wr + ((mi * 4 + ni) * 4 + r) * (kTConsumerWarps * 32));
+                        for (int r = 0; r < 4; ++r) acc[mi][ni][r] += __ldcg(wr + ((mi * NI + ni) * 4 + r) * (kTConsumerWarps * 32));
             }
         }
         // ---- epilogue: scale, (scatter by variable map), both triangles ----
         const double sc = a.scale.ptr ? a.scale.c * a.scale.ptr[w.inst * a.scale.bstride] : a.scale.c;
         double* out = a.out + w.inst * a.o_bstride;
-        const int64_t i0 = (int64_t)w.ti * kTBM, j0 = (int64_t)w.tj * kTBM;
-        if (a.accumulate) store_tile<SYRK, true>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t);
-        else store_tile<SYRK, false>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t);
+        const int64_t i0 = (int64_t)w.ti * BM, j0 = (int64_t)w.tj * BM;
+        if (a.accumulate) store_tile<SYRK, true, BM>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t);
+        else store_tile<SYRK, false, BM>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t);
     }
 }
 
 void configure_gram_tma_kernels() {
-    cudaFuncSetAttribute(gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
-    cudaFuncSetAttribute(gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
 }
 
 // ---- host: tensor maps and the unit decomposition ------------------------------------------------
@@ -304,13 +307,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 // X: k x n column-major (ld), `batch` instances `bstride` elements apart.  Tensor (k, n, batch), box (16, 128, 1), 128-byte swizzle.
-static bool make_panel_map(CUtensorMap* tm, const double* X, int64_t ld, int64_t bstride, int64_t k, int64_t n, int64_t batch) {
+static bool make_panel_map(CUtensorMap* tm, const double* X, int64_t ld, int64_t bstride, int64_t k, int64_t n, int64_t batch, int bm) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
     if (ld % 2 != 0 || ((uintptr_t)X & 15) != 0 || (batch > 1 && bstride % 2 != 0) || k == 0 || n == 0) return false;
     cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)n, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)(batch > 1 && bstride > 0 ? bstride : ld * n) * 8};
-    cuuint32_t box[3] = {(cuuint32_t)kTKT, (cuuint32_t)kTBM, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kTKT, (cuuint32_t)bm, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -320,9 +323,14 @@ static bool make_panel_map(CUtensorMap* tm, const double* X, int64_t ld, int64_t
 // unit decomposition: whole waves of tiles run unsplit; the tiles of the last partial wave are cut into k-slices so that
 // (tail tiles x slices) fills whole waves again.  Fewer tiles than SMs: everything is split.
 GramSplitPlan plan_gram_split(bool syrk, int64_t k, int64_t n, int64_t p, int64_t batch, int sm_count) {
-    GramSplitPlan pl{1, 0, 0};
-    const int64_t tm = (n + kTBM - 1) / kTBM, tn = (p + kTBM - 1) / kTBM;
-    const int64_t total = (syrk ? tn * (tn + 1) / 2 : tm * tn) * batch;
+    GramSplitPlan pl{1, 0, 0, kTBM};
+    auto tiles = [&](int bm) {
+        const int64_t tm = (n + bm - 1) / bm, tn = (p + bm - 1) / bm;
+        return (syrk ? tn * (tn + 1) / 2 : tm * tn) * batch;
+    };
+    // less than one wave of 128 x 128 tiles: the problem is latency-bound, spread it over more SMs with 64 x 64 tiles
+    if (tiles(kTBM) < sm_count) pl.bm = 64;
+    const int64_t total = tiles(pl.bm);
     const int64_t kiters = (k + kTKT - 1) / kTKT;
     const int64_t G = sm_count;
     const int64_t tail = total % G;
@@ -336,7 +344,7 @@ GramSplitPlan plan_gram_split(bool syrk, int64_t k, int64_t n, int64_t p, int64_
     }
     if (pl.nslices > 1) {
         pl.split_tiles = tail;
-        pl.workspace_doubles = tail * pl.nslices * (int64_t)kTBM * kTBM;
+        pl.workspace_doubles = tail * pl.nslices * (int64_t)pl.bm * pl.bm;
     }
     return pl;
 }
@@ -348,11 +356,12 @@ static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs
                             const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
     if (batch > 1 && (xbs == 0 || ybs == 0)) return false;
     GramTmaKernelArgs a{};
-    if (!make_panel_map(&a.tmx, X, ldx, xbs, k, n, batch)) return false;
-    if (!make_panel_map(&a.tmy, Y, ldy, ybs, k, p, batch)) return false;
+    const int bm = sc.plan.bm == 64 ? 64 : kTBM;
+    if (!make_panel_map(&a.tmx, X, ldx, xbs, k, n, batch, bm)) return false;
+    if (!make_panel_map(&a.tmy, Y, ldy, ybs, k, p, batch, bm)) return false;
     a.k = k; a.n = n; a.p = p; a.out = out; a.ldo = ldo; a.o_bstride = obs; a.map = map; a.scale = scale; a.accumulate = accumulate;
-    a.tiles_m = (int)((n + kTBM - 1) / kTBM);
-    a.tiles_n = (int)((p + kTBM - 1) / kTBM);
+    a.tiles_m = (int)((n + bm - 1) / bm);
+    a.tiles_n = (int)((p + bm - 1) / bm);
     a.kiters = (int)((k + kTKT - 1) / kTKT);
     a.tiles_per_inst = syrk ? (int64_t)a.tiles_n * (a.tiles_n + 1) / 2 : (int64_t)a.tiles_m * a.tiles_n;
     a.total_tiles = a.tiles_per_inst * batch;
@@ -364,8 +373,13 @@ static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs
     a.workspace = sc.workspace;
     a.total_units = a.full_tiles + (a.total_tiles - a.full_tiles) * a.nslices;
     const int grid = (int)(a.total_units < sm_count ? a.total_units : sm_count);
-    if (syrk) gram_tma_kernel<true><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
-    else gram_tma_kernel<false><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+    if (bm == 64) {
+        if (syrk) gram_tma_kernel<true, 64><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+        else gram_tma_kernel<false, 64><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+    } else {
+        if (syrk) gram_tma_kernel<true, 128><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+        else gram_tma_kernel<false, 128><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+    }
     return true;
 }
 

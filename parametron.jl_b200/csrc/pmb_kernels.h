@@ -104,7 +104,8 @@ void launch_gemm_tn(const GemmTNArgs& a, int64_t batch, int sm_count, cudaStream
 struct GramSplitPlan {          // k-split of the last partial wave of tiles (computed once by the planner)
     int32_t nslices;            // 1: no split
     int64_t split_tiles;        // number of tiles that are split (the tail of the tile enumeration)
-    int64_t workspace_doubles;  // split_tiles * nslices * 128 * 128
+    int64_t workspace_doubles;  // split_tiles * nslices * bm * bm
+    int32_t bm;                 // tile edge: 128, or 64 for problems smaller than one wave of 128-tiles
 };
 GramSplitPlan plan_gram_split(bool syrk, int64_t k, int64_t n, int64_t p, int64_t batch, int sm_count);
 struct GramScratch {
