@@ -32,7 +32,7 @@ constexpr int kAffUnroll = 4;  // independent 16-byte loads in flight per thread
 // offsets: d[i] = d_const[i] + sum_t alpha_t * v_t[...]; handled by the CTAs after the coefficient CTAs
 __device__ void affine_offsets(const AffBlockDev& blk, int64_t inst, int tid, int nthreads) {
     if (!blk.d) return;
-    for (int64_t i = tid; i < blk.rows; i += nthreads) {
+    for (int64_t i = tid; i < blk.d_rows; i += nthreads) {
         double acc = blk.d_const ? blk.d_const[i] : 0.0;
         for (int t = 0; t < blk.noffs; ++t) {
             const AffOffTermDev& o = blk.offs[t];

@@ -54,11 +54,11 @@ __device__ __forceinline__ double alpha_at(const AlphaDev& a, int64_t inst) { re
 // offsets d = const + sum alpha * v (same as kernels_affine.cu), run by the trailing CTAs of the launch
 __device__ void tma_affine_offsets(const AffBlockDev& blk, int64_t batch, int ob, int nob) {
     if (!blk.d) return;
-    const int64_t rb = (blk.rows + kTmaThreads - 1) / kTmaThreads;  // work item = (instance, block of kTmaThreads rows)
+    const int64_t rb = (blk.d_rows + kTmaThreads - 1) / kTmaThreads;  // work item = (instance, block of kTmaThreads rows)
     for (int64_t w = ob; w < batch * rb; w += nob) {
         const int64_t inst = w / rb;
         const int64_t i = (w - inst * rb) * kTmaThreads + threadIdx.x;
-        if (i >= blk.rows) continue;
+        if (i >= blk.d_rows) continue;
         double acc = blk.d_const ? blk.d_const[i] : 0.0;
         for (int t = 0; t < blk.noffs; ++t) {
             const AffOffTermDev o = blk.offs[t];
@@ -222,7 +222,7 @@ void launch_affine_assemble_tma(const AffBlockDev& blk, int64_t batch, int sm_co
     if (total > cap)
         for (int64_t t = cap; t >= cap - cap / 8; --t)
             if (total % t == 0) { g = t; break; }
-    const int64_t off_items = batch * ((blk.rows + kTmaThreads - 1) / kTmaThreads);
+    const int64_t off_items = blk.d ? batch * ((blk.d_rows + kTmaThreads - 1) / kTmaThreads) : 0;
     const int off_blocks = (int)(off_items < 64 ? off_items : 64);
     dim3 grid((unsigned)(g + off_blocks));
     const size_t smem = (size_t)nstages * kAffStageBytes;

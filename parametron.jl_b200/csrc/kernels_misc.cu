@@ -78,6 +78,56 @@ void launch_philox_uniform(double* out, int64_t numel, int64_t batch, uint64_t s
     philox_uniform_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(out, numel, batch, seed, scale, update_counter);
 }
 
+// ---------------- fused prologue: every built-in Parameter generator + the zeroing of (q, c0) + the update tick -------------
+// One launch replaces  tick + one Philox launch per Parameter + a memset node  (launch latency dominates the small configs).
+// All blocks read the update counter, use counter + 1 as this update's id, and the block that finishes LAST (atomic ticket)
+// publishes the incremented counter -- every other block has read it by then.
+__global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int njobs, int total_blocks, int64_t batch,
+                                                       unsigned long long* counter, unsigned int* ticket) {
+    const uint32_t upd = (uint32_t)(*counter + 1ULL);
+    // which job does this block belong to?
+    int j = 0;
+    int b = blockIdx.x;
+    while (j + 1 < njobs && b >= jobs[j].nblocks) { b -= jobs[j].nblocks; ++j; }
+    const FillJob job = jobs[j];
+    if (job.kind == 0) {
+        const int64_t pairs = (job.numel + 1) / 2;
+        const bool vec_ok = (job.numel % 2 == 0) && (((uintptr_t)job.out & 15) == 0);
+        for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+            double* o = job.out + inst * job.numel;
+            for (int64_t p = (int64_t)b * 256 + threadIdx.x; p < pairs; p += (int64_t)job.nblocks * 256) {
+                uint32_t c[4] = {(uint32_t)p, (uint32_t)((uint64_t)p >> 32), (uint32_t)inst, upd};
+                philox4x32_10(c, (uint32_t)job.seed, (uint32_t)(job.seed >> 32));
+                double d0 = (double)((((uint64_t)c[1] << 32) | c[0]) >> 11) * (1.0 / 9007199254740992.0) * job.scale;
+                double d1 = (double)((((uint64_t)c[3] << 32) | c[2]) >> 11) * (1.0 / 9007199254740992.0) * job.scale;
+                if (vec_ok) {
+                    *reinterpret_cast<double2*>(o + 2 * p) = make_double2(d0, d1);
+                } else {
+                    o[2 * p] = d0;
+                    if (2 * p + 1 < job.numel) o[2 * p + 1] = d1;
+                }
+            }
+        }
+    } else if (blockIdx.y == 0) {  // zero job: numel covers all instances
+        for (int64_t i = (int64_t)b * 256 + threadIdx.x; i < job.numel; i += (int64_t)job.nblocks * 256) job.out[i] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int done = atomicAdd(ticket, 1u);
+        if (done == (unsigned int)(total_blocks * gridDim.y) - 1u) {
+            *counter = (unsigned long long)upd;
+            *ticket = 0u;
+        }
+    }
+}
+void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, unsigned long long* counter, unsigned int* ticket,
+                     cudaStream_t stream) {
+    if (njobs == 0 || total_blocks == 0) return;
+    int64_t by = batch < 65535 ? batch : 65535;
+    prologue_kernel<<<dim3((unsigned)total_blocks, (unsigned)by), 256, 0, stream>>>(jobs_dev, njobs, total_blocks, batch, counter, ticket);
+}
+
 // ---------------- numeric prologue ---------------------------------------------------------------
 __global__ void lincomb_kernel(double* out, int64_t out_bstride, int64_t n, const LinCombTermDev* terms, int nterms, const double* cst,
                                int64_t batch) {
@@ -123,12 +173,20 @@ void launch_transpose(double* out, int64_t out_bstride, const double* in, int64_
 }
 
 // y = A'v : one warp per column, rows contiguous -> coalesced, warp-shuffle reduction
-__global__ void __launch_bounds__(256) gemv_t_kernel(GemvArgs a, int64_t batch) {
+__device__ void dot_body(const DotArgs& a, int64_t inst);
+
+// y = A'v (one warp per column) with an optional fused  out (+)= scale * x.y  done by the last block of the launch
+__global__ void __launch_bounds__(256) gemv_t_kernel(GemvArgs a, int64_t batch, DotArgs dt, int has_dot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (has_dot && blockIdx.x == gridDim.x - 1) {
+        for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) dot_body(dt, inst);
+        return;
+    }
+    const int gx = gridDim.x - (has_dot ? 1 : 0);
     for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
         const double* A = a.A + inst * a.a_bstride;
         const double* v = a.v + inst * a.v_bstride + a.v_off;
-        for (int64_t col = (int64_t)blockIdx.x * 8 + warp; col < a.cols; col += (int64_t)gridDim.x * 8) {
+        for (int64_t col = (int64_t)blockIdx.x * 8 + warp; col < a.cols; col += (int64_t)gx * 8) {
             const double* ac = A + col * a.lda;
             double acc = 0.0;
             for (int64_t r = lane; r < a.rows; r += 32) acc += ac[r] * v[r];
@@ -167,32 +225,39 @@ __global__ void __launch_bounds__(256) gemv_n_kernel(GemvArgs a, int64_t batch) 
         }
     }
 }
+void launch_gemv_t_dot(const GemvArgs& a, const DotArgs& d, int64_t batch, cudaStream_t stream) {
+    int64_t by = batch < 65535 ? batch : 65535;
+    int64_t bx = (a.cols + 7) / 8; if (bx > 4096) bx = 4096;
+    if (bx < 1) bx = 1;
+    gemv_t_kernel<<<dim3((unsigned)(bx + 1), (unsigned)by), 256, 0, stream>>>(a, batch, d, 1);
+}
 void launch_gemv(const GemvArgs& a, int64_t batch, cudaStream_t stream) {
     int64_t outlen = a.trans ? a.cols : a.rows;
     if (outlen == 0) return;
     int64_t by = batch < 65535 ? batch : 65535;
     if (a.trans) {
         int64_t bx = (a.cols + 7) / 8; if (bx > 4096) bx = 4096;
-        gemv_t_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(a, batch);
+        gemv_t_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(a, batch, DotArgs{}, 0);
     } else {
         int64_t bx = (a.rows + 31) / 32; if (bx > 4096) bx = 4096;
         gemv_n_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(a, batch);
     }
 }
 
-__global__ void __launch_bounds__(256) dot_kernel(DotArgs a, int64_t batch) {
-    for (int64_t inst = blockIdx.x; inst < batch; inst += gridDim.x) {
-        const double* x = a.x + inst * a.x_bstride + a.x_off;
-        const double* y = a.y + inst * a.y_bstride + a.y_off;
-        double acc = 0.0;
-        for (int64_t i = threadIdx.x; i < a.n; i += 256) acc += x[i] * y[i];
-        acc = block_sum_256(acc);
-        if (threadIdx.x == 0) {
-            double val = alpha_val(a.scale, inst) * acc;
-            double* dst = a.out + inst * a.out_bstride;
-            if (a.accumulate) *dst += val; else *dst = val;
-        }
+__device__ void dot_body(const DotArgs& a, int64_t inst) {
+    const double* x = a.x + inst * a.x_bstride + a.x_off;
+    const double* y = a.y + inst * a.y_bstride + a.y_off;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < a.n; i += 256) acc += x[i] * y[i];
+    acc = block_sum_256(acc);
+    if (threadIdx.x == 0) {
+        double val = alpha_val(a.scale, inst) * acc;
+        double* dst = a.out + inst * a.out_bstride;
+        if (a.accumulate) *dst += val; else *dst = val;
     }
+}
+__global__ void __launch_bounds__(256) dot_kernel(DotArgs a, int64_t batch) {
+    for (int64_t inst = blockIdx.x; inst < batch; inst += gridDim.x) dot_body(a, inst);
 }
 void launch_dot(const DotArgs& a, int64_t batch, cudaStream_t stream) {
     int64_t bx = batch < 65535 ? batch : 65535;

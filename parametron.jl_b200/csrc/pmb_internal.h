@@ -131,7 +131,7 @@ enum KernelClass { KC_AFFINE = 0, KC_GRAM, KC_GEMM, KC_PHILOX, KC_H2D, KC_REDUCE
 
 enum StepType {
     ST_TICK, ST_PHILOX, ST_H2D, ST_MEMSET, ST_LINCOMB, ST_TRANSPOSE, ST_GEMV, ST_DOT, ST_SPROD, ST_AFFINE, ST_GRAM, ST_GEMM,
-    ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM
+    ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM, ST_PROLOGUE, ST_GEMV_DOT
 };
 
 struct Step {
@@ -149,7 +149,8 @@ struct Step {
     const double* s0 = nullptr; int64_t s0_bs = 0;
     const double* s1 = nullptr; int64_t s1_bs = 0;
     AffBlockDev aff{};
-    GramScratch gscratch{};  // ST_GRAM / ST_GEMM: k-split plan, arrival counters and partial-tile workspace
+    GramScratch gscratch{};
+    const FillJob* jobs = nullptr; int njobs = 0, job_blocks = 0;  // ST_PROLOGUE  // ST_GRAM / ST_GEMM: k-split plan, arrival counters and partial-tile workspace
     GramArgs gram{};
     GemmTNArgs gemm{};
     GemvArgs gemv{};
@@ -206,6 +207,8 @@ struct pmb_ctx {
     std::vector<void*> allocs;
     int64_t bytes_alloc = 0;
     unsigned long long* d_counter = nullptr;
+    unsigned int* d_ticket = nullptr;
+    std::vector<pmb::FillJob> fill_jobs;  // collected while planning, lowered to one ST_PROLOGUE step
     int64_t updates = 0;
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraph_t graph = nullptr;

@@ -49,6 +49,7 @@ struct AffBlockDev {
     double* d;            // rows
     int64_t C_bstride, d_bstride;
     int64_t rows;
+    int64_t d_rows;       // length of d (== rows except for sparse blocks, whose "rows" is the number of stored values)
     int32_t ntouched;     // number of output columns with at least one contribution (the others stay 0 forever)
     const int32_t* col_out;   // [ntouched] output column (0-based optimizer variable index)
     const int32_t* col_ptr;   // [ntouched + 1] CSR pointer into entries
@@ -119,6 +120,18 @@ void configure_gram_tma_kernels();
 
 // ---------------- small kernels ---------------------------------------------------------------
 void launch_tick(unsigned long long* counter, cudaStream_t stream);
+// fused prologue of one update: all built-in Parameter generators (kind 0: Philox uniform fill, per instance) + zero fills
+// (kind 1: numel doubles in total) + the update-counter tick (published by the last block to finish)
+struct FillJob {
+    double* out;
+    int64_t numel;
+    uint64_t seed;
+    double scale;
+    int32_t kind;
+    int32_t nblocks;   // blocks of 256 threads assigned to this job
+};
+void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, unsigned long long* counter, unsigned int* ticket,
+                     cudaStream_t stream);
 // Philox4x32-10 uniform fill: out[b*numel + e] = scale * U[0,1), counter = (pair index, instance, update counter), key = seed
 void launch_philox_uniform(double* out, int64_t numel, int64_t batch, uint64_t seed, double scale,
                            const unsigned long long* update_counter, int sm_count, cudaStream_t stream);
@@ -144,6 +157,7 @@ struct DotArgs {
     int64_t n; double* out; int64_t out_bstride; AlphaDev scale; int32_t accumulate;
 };
 void launch_dot(const DotArgs& a, int64_t batch, cudaStream_t stream);
+void launch_gemv_t_dot(const GemvArgs& a, const DotArgs& d, int64_t batch, cudaStream_t stream);  // y = A'v and out (+)= s * x.y in one launch
 // scalar chain: out = c * prod_i s_i
 void launch_scalar_prod(double* out, int64_t out_bstride, double c, const double* s0, int64_t s0_bstride,
                         const double* s1, int64_t s1_bstride, int64_t batch, cudaStream_t stream);

@@ -102,12 +102,7 @@ static void plan_numeric(pmb_ctx* c, int id) {
             n.dptr = dalloc<double>(c, c->batch * n.numel, true);
             n.owned = true;
         }
-        if (n.pmode == PMB_PARAM_UNIFORM) {
-            Step s;
-            s.type = ST_PHILOX; s.cls = KC_PHILOX; s.batch = c->batch;
-            s.out = n.dptr; s.n = n.numel; s.seed = n.seed; s.scale = n.scale;
-            c->steps.push_back(s);
-        }
+        if (n.pmode == PMB_PARAM_UNIFORM && n.numel > 0) c->fill_jobs.push_back(FillJob{n.dptr, n.numel, n.seed, n.scale, 0, 0});
         return;
     }
     n.dptr = dalloc<double>(c, nb * n.numel);
@@ -224,7 +219,7 @@ static AffBlockDev lower_aff(pmb_ctx* c, const AffForm& f, double* C, int64_t C_
         offs.push_back(AffOffTermDev{sn.dptr, sn.bstride, o.src_off, o.row_off, o.rows, alpha_dev(c, o.a)});
     }
     AffBlockDev b{};
-    b.C = C; b.d = d; b.C_bstride = C_bstride; b.d_bstride = d_bstride; b.rows = f.rows;
+    b.C = C; b.d = d; b.C_bstride = C_bstride; b.d_bstride = d_bstride; b.rows = f.rows; b.d_rows = f.rows;
     b.ntouched = (int32_t)col_out.size();
     b.col_out = upload(c, col_out);
     b.col_ptr = upload(c, col_ptr);
@@ -321,10 +316,13 @@ static void plan_sparse_block(pmb_ctx* c, Constraint& con) {
     con.sp_cols = upload(c, cols);
     con.nterms = con.rows * (int64_t)sp.vars.size();  // what the reference would emit: every entry, zeros included
     std::vector<Step>& st = con.is_const ? c->init_steps : c->steps;
-    // coefficients: one contiguous (scaled) copy of the value buffer -> a one-column "simple" block of nnz rows
+    // one launch: the offsets d (rows of the block) + one contiguous (scaled) copy of the value buffer, expressed as a
+    // one-column "simple" block of nnz rows
+    AffForm only_off;
+    only_off.rows = con.rows; only_off.offs = con.form.offs; only_off.coff = con.form.coff;
+    AffBlockDev v = lower_aff(c, only_off, nullptr, 0, con.d, con.rows, true, nullptr);
     if (nnz > 0) {
-        AffBlockDev v{};
-        v.C = con.vals; v.d = nullptr; v.C_bstride = nnz; v.d_bstride = 0; v.rows = nnz; v.ntouched = 1;
+        v.C = con.vals; v.C_bstride = nnz; v.rows = nnz; v.ntouched = 1;
         v.col_out = upload(c, std::vector<int32_t>{0});
         v.col_src = upload(c, std::vector<int32_t>{0});
         v.col_ptr = upload(c, std::vector<int32_t>{0, 1});
@@ -337,20 +335,14 @@ static void plan_sparse_block(pmb_ctx* c, Constraint& con) {
             for (int64_t o = 0; o < nnz; o += kAffStageBytes / 8)
                 segs.push_back(AffSeg{o, o, (int32_t)(std::min<int64_t>(kAffStageBytes / 8, nnz - o) * 8), 0});
             std::vector<int32_t> cf(segs.size() + 1);
-            for (size_t i = 0; i <= segs.size(); ++i) cf[i] = (int32_t)i;
+            for (size_t q = 0; q <= segs.size(); ++q) cf[q] = (int32_t)q;
             v.segs = upload(c, segs); v.chunk_first = upload(c, cf); v.nchunks = (int32_t)segs.size();
             v.tma = (sp.a.node < 0 && sp.a.c == 1.0) ? 1 : 2;
             v.uniform = 1; v.u_src0 = 0; v.u_dst0 = 0; v.u_src_stride = v.u_dst_stride = kAffStageBytes / 8;
             v.u_bytes = segs[0].bytes; v.u_last_bytes = segs.back().bytes;
         }
-        st.push_back(affine_step(v, c->batch));
     }
-    // offsets d
-    AffForm only_off;
-    only_off.rows = con.rows; only_off.offs = con.form.offs; only_off.coff = con.form.coff;
-    Step os = affine_step(lower_aff(c, only_off, nullptr, 0, con.d, con.rows, true, nullptr), c->batch);
-    os.cls = KC_MISC;
-    st.push_back(os);
+    st.push_back(affine_step(v, c->batch));
     if (!con.is_const) c->affine_bytes += 16 * nnz + 16 * con.rows;
 }
 
@@ -362,6 +354,7 @@ struct DenseSide {
     const double* g = nullptr;  // offsets (k), null when identically zero
     int64_t gbs = 0;
     double cx = 1.0;
+    double cg = 1.0;            // the offsets are cg * g[...]
 };
 
 static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps, int64_t nb) {
@@ -377,12 +370,20 @@ static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps,
         std::sort(sorted.begin(), sorted.end());
         direct = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
     }
-    double* g = has_off ? dalloc<double>(c, nb * f.rows) : nullptr;
+    // offsets that are one scaled numeric vector are used in place (no launch): g = cg * v
+    const bool g_direct = has_off && f.offs.size() == 1 && f.offs[0].a.node < 0 && f.offs[0].row_off == 0 && f.offs[0].rows == f.rows &&
+                          std::all_of(f.coff.begin(), f.coff.end(), [](double v) { return v == 0.0; });
+    double* g = (has_off && !(direct && g_direct)) ? dalloc<double>(c, nb * f.rows) : nullptr;
     if (direct) {
         const MatTerm& m = f.mats[0];
         const Node& sn = c->nodes[m.mat];
         s.X = sn.dptr + m.src_col_off * sn.rows; s.ldx = sn.rows; s.xbs = sn.bstride; s.ncols = m.cols; s.cx = m.a.c;
         s.map = upload(c, map);
+        if (has_off && g_direct) {
+            const Node& gn = c->nodes[f.offs[0].vec];
+            s.g = gn.dptr + f.offs[0].src_off; s.gbs = gn.bstride; s.cg = f.offs[0].a.c;
+            return s;
+        }
         if (has_off) {
             AffForm only_off;
             only_off.rows = f.rows; only_off.offs = f.offs; only_off.coff = f.coff;
@@ -423,9 +424,13 @@ static void plan_objective(pmb_ctx* c) {
     const bool has_quad = !qf.grams.empty() || !qf.bilins.empty() || !qf.coos.empty();
     if (c->obj_kind == PMB_KIND_QUAD) c->Q = dalloc<double>(c, nb * N * N, true);
     // (q, c0) <- 0, then the affine part overwrites its touched columns, then the quadratic terms accumulate
-    Step z;
-    z.type = ST_MEMSET; z.cls = KC_MISC; z.out = qc; z.n = nb * (N + 1);
-    st.push_back(z);
+    if (c->obj_const) {
+        Step z;
+        z.type = ST_MEMSET; z.cls = KC_MISC; z.out = qc; z.n = nb * (N + 1);
+        st.push_back(z);
+    } else {
+        c->fill_jobs.push_back(FillJob{qc, nb * (N + 1), 0, 0.0, 1, 0});  // zeroed by the fused prologue launch
+    }
     if (qf.aff.rows == 0) qf.aff.rows = 1;
     if (!qf.aff.mats.empty() || !qf.aff.units.empty() || !qf.aff.offs.empty() || !qf.aff.coff.empty())
         st.push_back(affine_step(lower_aff(c, qf.aff, c->q, N, c->c0, 1, false, nullptr), nb));
@@ -458,16 +463,14 @@ static void plan_objective(pmb_ctx* c) {
                 GemvArgs g{};
                 g.A = F.X; g.lda = F.ldx; g.a_bstride = F.xbs; g.rows = F.k; g.cols = F.ncols; g.trans = 1;
                 g.v = F.g; g.v_bstride = F.gbs; g.v_off = 0; g.y = c->q; g.y_bstride = N; g.map = F.map;
-                g.scale = scaled(a, 2.0 * F.cx); g.accumulate = 1;
+                g.scale = scaled(a, 2.0 * F.cx * F.cg); g.accumulate = 1;
                 v.gemv = g;
-                st.push_back(v);
-                Step dd;
-                dd.type = ST_DOT; dd.cls = KC_REDUCE; dd.batch = nb;
                 DotArgs d{};
                 d.x = F.g; d.x_bstride = F.gbs; d.y = F.g; d.y_bstride = F.gbs; d.n = F.k; d.out = c->c0; d.out_bstride = 1;
-                d.scale = a; d.accumulate = 1;
-                dd.dot = d;
-                st.push_back(dd);
+                d.scale = scaled(a, F.cg * F.cg); d.accumulate = 1;
+                v.dot = d;
+                v.type = ST_GEMV_DOT;  // q += 2 a cx X'g and c0 += a g.g in one launch
+                st.push_back(v);
             }
         } else {
             // M = Xf' Xh (scratch);  H[mf[i], mh[j]] += a M ; H[mh[j], mf[i]] += a M ;  q[mf] += a Xf' gh ; q[mh] += a Xh' gf ; c0 += a gf.gh
@@ -496,7 +499,7 @@ static void plan_objective(pmb_ctx* c) {
                 GemvArgs g{};
                 g.A = X.X; g.lda = X.ldx; g.a_bstride = X.xbs; g.rows = X.k; g.cols = X.ncols; g.trans = 1;
                 g.v = G.g; g.v_bstride = G.gbs; g.v_off = 0; g.y = c->q; g.y_bstride = N; g.map = X.map;
-                g.scale = scaled(a, X.cx); g.accumulate = 1;
+                g.scale = scaled(a, X.cx * G.cg); g.accumulate = 1;
                 v.gemv = g;
                 st.push_back(v);
             };
@@ -507,7 +510,7 @@ static void plan_objective(pmb_ctx* c) {
                 dd.type = ST_DOT; dd.cls = KC_REDUCE; dd.batch = nb;
                 DotArgs d{};
                 d.x = F.g; d.x_bstride = F.gbs; d.y = Hs.g; d.y_bstride = Hs.gbs; d.n = F.k; d.out = c->c0; d.out_bstride = 1;
-                d.scale = a; d.accumulate = 1;
+                d.scale = scaled(a, F.cg * Hs.cg); d.accumulate = 1;
                 dd.dot = d;
                 st.push_back(dd);
             }
@@ -546,6 +549,8 @@ static void run_step(pmb_ctx* c, const Step& s) {
     cudaStream_t st = c->stream;
     switch (s.type) {
         case ST_TICK: launch_tick(c->d_counter, st); break;
+        case ST_PROLOGUE: launch_prologue(s.jobs, s.njobs, s.job_blocks, s.batch, c->d_counter, c->d_ticket, st); break;
+        case ST_GEMV_DOT: launch_gemv_t_dot(s.gemv, s.dot, s.batch, st); break;
         case ST_PHILOX: launch_philox_uniform(s.out, s.n, s.batch, s.seed, s.scale, c->d_counter, c->sm_count, st); break;
         case ST_MEMSET: CK(cudaMemsetAsync(s.out, 0, (size_t)s.n * sizeof(double), st)); break;
         case ST_LINCOMB: launch_lincomb(s.out, s.out_bstride, s.n, s.lterms, s.nl, s.cst, s.batch, st); break;
@@ -669,11 +674,8 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
     bool any_uniform = false;
     for (auto& n : ctx->nodes) any_uniform = any_uniform || (n.needed && n.nop == NOP_PARAM && n.pmode == PMB_PARAM_UNIFORM);
     ctx->d_counter = (unsigned long long*)dalloc<unsigned long long>(ctx, 1, true);
-    if (any_uniform) {
-        Step s;
-        s.type = ST_TICK; s.cls = KC_MISC;
-        ctx->steps.push_back(s);
-    }
+    (void)any_uniform;
+    ctx->d_ticket = (unsigned int*)dalloc<unsigned int>(ctx, 1, true);
     const size_t nn = ctx->nodes.size();
     for (size_t i = 0; i < nn; ++i)
         if (ctx->nodes[i].needed && is_numeric(ctx->nodes[i].kind)) plan_numeric(ctx, (int)i);
@@ -687,6 +689,22 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
         AffBlockDev b = lower_aff(ctx, con.form, con.C, con.rows * N, con.d, con.rows, false, nullptr);
         (con.is_const ? ctx->init_steps : ctx->steps).push_back(affine_step(b, ctx->batch));
         if (!con.is_const) ctx->affine_bytes += 16 * (int64_t)b.ntouched * con.rows + 16 * con.rows;
+    }
+    if (!ctx->fill_jobs.empty()) {
+        // one fused prologue launch: Philox fills of every built-in generator, zeroing of (q, c0), update tick
+        int total = 0;
+        const int64_t cap = (int64_t)ctx->sm_count * 16;
+        for (auto& j : ctx->fill_jobs) {
+            const int64_t items = j.kind == 0 ? (j.numel + 1) / 2 : j.numel;
+            int64_t nbk = (items + 255) / 256;
+            const int64_t lim = j.kind == 0 ? std::max<int64_t>(1, cap / std::max<int64_t>(1, std::min<int64_t>(ctx->batch, 64))) : 64;
+            j.nblocks = (int32_t)std::max<int64_t>(1, std::min(nbk, lim));
+            total += j.nblocks;
+        }
+        Step s;
+        s.type = ST_PROLOGUE; s.cls = KC_PHILOX; s.batch = ctx->batch;
+        s.jobs = upload(ctx, ctx->fill_jobs); s.njobs = (int)ctx->fill_jobs.size(); s.job_blocks = total;
+        ctx->steps.insert(ctx->steps.begin(), s);
     }
     ctx->launches_per_update = 0;
     ctx->memcpy_per_update = 0;
