@@ -310,15 +310,16 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(st["kernel_launches_per_update"]) * args.steps,
             "launches_per_update": int(st["kernel_launches_per_update"]), "cuda_graph": bool(st["uses_cuda_graph"]),
-            "roofline": {"bound": "tensor", "kernel": "gram_dmma_kernel (Q = 2A'A, fp64 DMMA pipe)", "achieved": gram_tflops,
+            "roofline": {"bound": "tensor", "kernel": "gram_tma_kernel<SYRK,128> (Q = 2A'A: TMA ring + warp-specialised fp64 DMMA)", "achieved": gram_tflops,
                          "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gram_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
                          "algorithmic_flops": int(st["gram_algorithmic_flops"]), "avg_launch_ms": gram_ms,
                          "peak_source": "fp64 mma.sync (DMMA) peak measured on this pool's B200, profiles/r01_probe_dmma.txt; "
                                         "MEASURED_PEAKS.json has no fp64 entry and tcgen05 has no f64 kind"},
-            "roofline_affine": {"bound": "hbm", "kernel": "affine_assemble_simple (C, -d)", "achieved": aff_gbs, "peak": peaks["hbm_gbs"],
+            "roofline_affine": {"bound": "hbm", "kernel": "affine_assemble_tma (C, -d): bulk-copy ring", "achieved": aff_gbs, "peak": peaks["hbm_gbs"],
                                 "unit": "GB/s", "frac": (aff_gbs / peaks["hbm_gbs"]) if aff_gbs else None, "traffic": None,
                                 "algorithmic_bytes": int(st["affine_algorithmic_bytes"]), "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
-                                "note": "avg over the affine-class launches of one update"},
+                                "note": "CUDA-event time of the single launch inside an eager replay of the step (includes ~3 us of event/launch overhead; "
+                                        "ncu gpu__time_duration of the same launch: profiles/r01_e_affine_tma_ncu_full.txt)"},
             "kernel_ms_per_update": {k: v[0] / max(ksteps, 1) for k, v in kt.items()},
             "kernel_share": kernel_share,
             "cpu_baseline": cpu,
