@@ -319,3 +319,110 @@ def test_parameters_evaluated_once_per_update():
         assert np.array_equal(Cb, np.full((4, 4), float(k)))
         Q, _, _ = m.objective_arrays()
         assert np.array_equal(Q, np.full((4, 4), 2.0 * 4 * k * k))
+
+
+def test_nested_matrix_products():
+    """A * (B * x) - c : matvecmul! over Vector{AffineFunction} whose rows are matrix rows (functions.jl:800-822) -> dense A*B."""
+    rng = np.random.default_rng(29)
+    Ah, Bh, ch = {"v": rng.random((3, 4))}, {"v": rng.random((4, 5))}, {"v": rng.random(3)}
+
+    def build(s):
+        x = s.variables(5)
+        A, B, c = s.parameter(Ah), s.parameter(Bh), s.parameter(ch)
+        s.constraint(s.mul(A, s.sub(s.mul(B, x), np.ones(4))), "<=", c)
+        return 5
+
+    def mutate(step):
+        Ah["v"] = rng.random((3, 4)); Bh["v"] = rng.random((4, 5)); ch["v"] = rng.random(3)
+
+    run_twin(build, None, mutate, check_terms=False)  # the reference emits 4 terms per variable here; the dense block sums them
+
+
+def test_numbers_dot_affine_vector_objective():
+    """dot(p, A*x + q) with numeric p (functions.jl:665-674): affine objective, Maximize sense; plus a Variable-sum constraint."""
+    n, k = 6, 4
+    rng = np.random.default_rng(31)
+    Ah, ph, qh, wh = {"v": rng.random((k, n))}, {"v": rng.random(k)}, {"v": rng.random(k)}, {"v": 2.0}
+
+    def build(s):
+        x = s.variables(n)
+        A, p, q, w = (s.parameter(h) for h in (Ah, ph, qh, wh))
+        e = s.dot(p, s.add(s.mul(A, x), q))
+        s.objective("max", s.mul(w, e))
+        s.constraint(s.dot(p, s.mul(A, x)), "<=", 1.0)      # scalar affine constraint (bucket ScalarAffine/LessThan)
+        return n
+
+    def mutate(step):
+        Ah["v"] = rng.random((k, n)); ph["v"] = rng.random(k); qh["v"] = rng.random(k); wh["v"] = float(rng.random()) + 0.5
+
+    o, d = run_twin(build, None, mutate, check_terms=False)
+    assert d.model.objective_view().sense == 1 and d.model.objective_view().kind == 5  # Maximize, AffineFunction
+
+
+def test_weighted_sum_of_quadratics_with_two_dynamic_scalars():
+    """w1 * (x.x) + w2 * w1 * ||Ax - b||^2 : mul!(::QuadraticFunction, scalar) twice -> a product of two device scalars."""
+    n, k = 5, 3
+    rng = np.random.default_rng(37)
+    Ah, bh, w1h, w2h = {"v": rng.random((k, n))}, {"v": rng.random(k)}, {"v": 0.7}, {"v": 1.3}
+
+    def build(s):
+        x = s.variables(n)
+        A, b, w1, w2 = (s.parameter(h) for h in (Ah, bh, w1h, w2h))
+        r = s.sub(s.mul(A, x), b)
+        s.objective("min", s.add(s.mul(w1, s.dot(x, x)), s.mul(w2, s.mul(w1, s.dot(r, r)))))
+        return n
+
+    def mutate(step):
+        Ah["v"] = rng.random((k, n)); bh["v"] = rng.random(k); w1h["v"] = float(rng.random()) + 0.1; w2h["v"] = float(rng.random()) + 0.1
+
+    run_twin(build, None, mutate)
+
+
+def test_repeated_variables_are_summed_in_the_dense_block():
+    """x appears twice in the variable vector: the reference keeps two terms per row, MOI sums duplicates; the Gram operand
+    must be materialised (non-unique scatter map) and the dense C column holds the sum."""
+    import parametron_b200 as pm
+    from oracle import dense as D
+    rng = np.random.default_rng(41)
+    A = rng.random((4, 3))
+    b = rng.random(4)
+    m = pm.Model()
+    x = m.variables(2)
+    xx = [x[0], x[1], x[0]]
+    pA, pb = pm.Parameter(m, val=A), pm.Parameter(m, val=b)
+    r = pA * xx - pb
+    pm.objective(m, pm.Minimize, pm.dot(r, r))
+    pm.constraint(m, pA * xx, ">=", pb)
+    m.initialize()
+    m.update()
+    Aeff = np.stack([A[:, 0] + A[:, 2], A[:, 1]], axis=1)
+    Qo, qo, c0o = D.least_squares_objective(Aeff, b, [1, 2], 2)
+    Q, q, c0 = m.objective_arrays()
+    assert_close(Q, Qo, 1e-10, "Q"); assert_close(q, qo, 1e-10, "q"); assert_close([c0], [c0o], 1e-10, "c0")
+    Cb, db = m.block_arrays(0)
+    assert_close(Cb, Aeff, 1e-15, "C"); assert np.array_equal(db, -b)
+    rows, vars_, _ = m.block_terms(0)
+    assert list(vars_) == [1, 2, 1] * 4 and list(rows) == [r_ for r_ in range(1, 5) for _ in range(3)]  # reference term list keeps both
+
+
+def test_constant_quadratic_terms_and_linear_objective():
+    """test/model.jl:281-321 shapes: constant QuadraticFunction objective terms (COO path) + x'Px with a Parameter scale."""
+    import ctypes as C
+    import parametron_b200 as pm
+    m = pm.Model()
+    x = m.variables(3)
+    # 2 x1^2 + x1 x2 + 0.5 x3^2 + 3 x2 + 1  as a constant QuadraticFunction
+    qc = np.array([2.0, 1.0, 0.5]); rv = np.array([1, 1, 3], dtype=np.int64); cv = np.array([1, 2, 3], dtype=np.int64)
+    lc = np.array([3.0]); lv = np.array([2], dtype=np.int64)
+    out = C.c_int32()
+    m._ck(m._lib.pmb_const_quadratic(m._ctx, 3, C.c_void_p(qc.ctypes.data), C.c_void_p(rv.ctypes.data), C.c_void_p(cv.ctypes.data),
+                                     1, C.c_void_p(lc.ctypes.data), C.c_void_p(lv.ctypes.data), 1.0, out))
+    base = pm.Expr(m, out.value)
+    w = pm.Parameter(m, f=lambda: np.float64(2.0))
+    pm.objective(m, pm.Minimize, w * base + pm.dot(x, np.array([1.0, 1.0, 1.0]), model=m))
+    m.initialize()
+    m.update()
+    Q, q, c0 = m.objective_arrays()
+    # MOI Hessian: diagonal terms doubled (moi_interop.jl:58), off-diagonal term counted in both triangles
+    assert np.array_equal(Q, 2.0 * np.array([[4.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]]))
+    assert np.array_equal(q, [1.0, 7.0, 1.0]) and c0 == 2.0
