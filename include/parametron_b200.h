@@ -186,6 +186,43 @@ int pmb_get_block(pmb_ctx* ctx, int32_t update_pos, pmb_block_view* out);
  * (column-major, within one instance) of the dense C entry its coefficient is summed into. */
 int pmb_block_term_index(pmb_ctx* ctx, int32_t update_pos, int64_t capacity, int64_t* rows, int64_t* vars, int64_t* src);
 
+/* ---- MOI-compatible term-list export -------------------------------------------------------
+ * One record per reference term of a vector (or scalar) affine constraint block, in EXACTLY the order and layout of
+ * update!(::MOI.VectorAffineFunction, ...) (moi_interop.jl:64-81): row-outer / term-inner, 1-based output index, variable =
+ * optimizer index (varmap applied), duplicates NOT combined (a variable used twice yields two records, as in the reference). */
+typedef struct {
+    int64_t output_index;  /* MOI.VectorAffineTerm.output_index (1-based row) */
+    double coefficient;    /* MOI.ScalarAffineTerm.coefficient */
+    int64_t variable;      /* MOI.ScalarAffineTerm.variable_index.value (1-based) */
+} pmb_vector_affine_term;
+/* Writes batch * nterms records to the DEVICE buffer `terms_dev` and (if non-NULL) batch * rows constants to `constants_dev`,
+ * asynchronously on the context stream, from the Parameter values of the most recent pmb_update.  PMB_EUNSUPPORTED for sparse
+ * blocks and for blocks whose rows do not all have the same term layout (vcat of different shapes). */
+int pmb_block_export_terms(pmb_ctx* ctx, int32_t update_pos, pmb_vector_affine_term* terms_dev, double* constants_dev);
+
+/* ---- solver-side ingest: the QP in the form an OSQP-style solver consumes ---------------------------
+ *     minimize 1/2 x'Px + q'x + c0   subject to   l <= A x <= u
+ * P_x: values of the UPPER triangle of the MOI Hessian in CSC order (column j holds rows 0..j); A: all constraint blocks stacked
+ * in update order, CSC; bounds from the set kinds (block  Cx + d in set):  Zeros l = u = -d;  Nonnegatives l = -d, u = +inf;
+ * Nonpositives l = -inf, u = -d.  The patterns are static (written once by pmb_initialize); every pmb_update refreshes the
+ * VALUES only (value-only updates into a fixed pattern, replacing MOI.set at moi_interop.jl:134,171). */
+typedef struct {
+    int64_t n, m;            /* variables, total constraint rows */
+    int64_t nnzP, nnzA;
+    double* P_x;             /* device, batch stride nnzP (NULL for affine objectives) */
+    double* q;               /* device, batch stride n  (same buffer as pmb_objective_view.q) */
+    double* c0;              /* device, batch stride 1 */
+    double* A_x;             /* device, batch stride nnzA */
+    double* l;               /* device, batch stride m */
+    double* u;               /* device, batch stride m */
+    const int64_t* P_p;      /* device [n + 1] */
+    const int64_t* P_i;      /* device [nnzP] */
+    const int64_t* A_p;      /* device [n + 1] */
+    const int64_t* A_i;      /* device [nnzA] */
+} pmb_qp_view;
+int pmb_enable_qp_pack(pmb_ctx* ctx);             /* build phase: adds the pack launches to every update */
+int pmb_get_qp(pmb_ctx* ctx, pmb_qp_view* out);   /* after pmb_initialize */
+
 /* ---- host staging helpers (pinned memory + stream-ordered copies; the e2e path of bench.py and the ctypes tests) -- */
 int pmb_host_alloc(pmb_ctx* ctx, size_t bytes, void** out);   /* cudaHostAlloc; freed by pmb_host_free or pmb_ctx_destroy */
 int pmb_host_free(pmb_ctx* ctx, void* p);

@@ -32,6 +32,12 @@ class BlockView(C.Structure):
                 ("is_sparse", C.c_int32), ("nnz", C.c_int64), ("vals", C.c_void_p), ("sp_rows", C.c_void_p), ("sp_cols", C.c_void_p)]
 
 
+class QpView(C.Structure):
+    _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("nnzP", C.c_int64), ("nnzA", C.c_int64), ("P_x", C.c_void_p), ("q", C.c_void_p),
+                ("c0", C.c_void_p), ("A_x", C.c_void_p), ("l", C.c_void_p), ("u", C.c_void_p), ("P_p", C.c_void_p), ("P_i", C.c_void_p),
+                ("A_p", C.c_void_p), ("A_i", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches_per_update", C.c_int64), ("memcpy_nodes_per_update", C.c_int64),
                 ("device_bytes_allocated", C.c_int64), ("uses_cuda_graph", C.c_int64),
@@ -80,6 +86,9 @@ SIGNATURES = {
     "pmb_num_blocks": (C.c_int, [C.c_void_p, c_i32p]),
     "pmb_get_block": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(BlockView)]),
     "pmb_block_term_index": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pmb_block_export_terms": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pmb_enable_qp_pack": (C.c_int, [C.c_void_p]),
+    "pmb_get_qp": (C.c_int, [C.c_void_p, C.POINTER(QpView)]),
     "pmb_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "pmb_enable_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "pmb_kernel_class_count": (C.c_int, []),

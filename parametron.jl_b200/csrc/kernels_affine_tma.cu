@@ -213,8 +213,11 @@ void launch_affine_assemble_tma(const AffBlockDev& blk, int64_t batch, int sm_co
     }
     // measured at cfg2 (profiles/r01_c_affine_sweep.txt): the single issuing thread of a CTA is the limiter, so more CTAs per SM
     // with shallower rings beat one deep ring: 3 CTAs x 4 stages x 16 KB.
-    int cps = env_cps > 0 ? env_cps : 3;
-    int nstages = env_stages > 0 ? env_stages : 4;
+    // Long streams (cfg3: thousands of chunks per SM) are bandwidth- rather than issue-latency-bound: 2 CTAs x 6 stages measured
+    // 6.0 TB/s there against 5.5 TB/s for 3 x 4.
+    const bool long_stream = total > (int64_t)sm_count * 64;
+    int cps = env_cps > 0 ? env_cps : (long_stream ? 2 : 3);
+    int nstages = env_stages > 0 ? env_stages : (long_stream ? 6 : 4);
     if (nstages > kTmaMaxStages) nstages = kTmaMaxStages;
     if (nstages < 2) nstages = 2;
     int64_t cap = (int64_t)sm_count * cps;

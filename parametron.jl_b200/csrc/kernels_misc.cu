@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int 
 void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, unsigned long long* counter, unsigned int* ticket,
                      cudaStream_t stream) {
     if (njobs == 0 || total_blocks == 0) return;
-    int64_t by = batch < 65535 ? batch : 65535;
+    // at most 64 instance rows: the per-job block counts were sized for min(batch, 64) rows, and the end-of-kernel ticket is one
+    // atomic per block (hundreds of thousands of blocks would serialise on it)
+    int64_t by = batch < 64 ? batch : 64;
     prologue_kernel<<<dim3((unsigned)total_blocks, (unsigned)by), 256, 0, stream>>>(jobs_dev, njobs, total_blocks, batch, counter, ticket);
 }
 
@@ -183,13 +185,37 @@ __global__ void __launch_bounds__(256) gemv_t_kernel(GemvArgs a, int64_t batch, 
         return;
     }
     const int gx = gridDim.x - (has_dot ? 1 : 0);
+    const bool vec2 = (a.rows % 2 == 0) && (a.lda % 2 == 0) && (a.a_bstride % 2 == 0) && (a.v_bstride % 2 == 0) && (a.v_off % 2 == 0) &&
+                      (((uintptr_t)a.A | (uintptr_t)a.v) & 15) == 0;
     for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
         const double* A = a.A + inst * a.a_bstride;
         const double* v = a.v + inst * a.v_bstride + a.v_off;
         for (int64_t col = (int64_t)blockIdx.x * 8 + warp; col < a.cols; col += (int64_t)gx * 8) {
             const double* ac = A + col * a.lda;
             double acc = 0.0;
-            for (int64_t r = lane; r < a.rows; r += 32) acc += ac[r] * v[r];
+            if (vec2) {
+                // 16-byte loads, four independent loads in flight per lane
+                const double2* ac2 = reinterpret_cast<const double2*>(ac);
+                const double2* v2 = reinterpret_cast<const double2*>(v);
+                const int64_t n2 = a.rows >> 1;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int64_t r = lane;
+                for (; r + 96 < n2; r += 128) {
+                    const double2 x0 = ac2[r], x1 = ac2[r + 32], x2 = ac2[r + 64], x3 = ac2[r + 96];
+                    const double2 y0 = v2[r], y1 = v2[r + 32], y2 = v2[r + 64], y3 = v2[r + 96];
+                    s0 += x0.x * y0.x + x0.y * y0.y;
+                    s1 += x1.x * y1.x + x1.y * y1.y;
+                    s2 += x2.x * y2.x + x2.y * y2.y;
+                    s3 += x3.x * y3.x + x3.y * y3.y;
+                }
+                for (; r < n2; r += 32) {
+                    const double2 x0 = ac2[r], y0 = v2[r];
+                    s0 += x0.x * y0.x + x0.y * y0.y;
+                }
+                acc = (s0 + s1) + (s2 + s3);
+            } else {
+                for (int64_t r = lane; r < a.rows; r += 32) acc += ac[r] * v[r];
+            }
             acc = warp_sum(acc);
             if (lane == 0) {
                 double val = alpha_val(a.scale, inst) * acc;

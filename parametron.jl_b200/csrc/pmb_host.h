@@ -26,6 +26,46 @@ bool quad_is_const(pmb_ctx* c, const QuadForm& q);
 AffForm aff_of(pmb_ctx* c, int id);
 QuadForm quad_of(pmb_ctx* c, int id);
 
+#define CK(x)                                                                                  \
+    do {                                                                                       \
+        cudaError_t e_ = (x);                                                                  \
+        if (e_ != cudaSuccess) pmb::fail(PMB_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---- device memory ---------------------------------------------------------------------------
+template <class T>
+inline T* dalloc(pmb_ctx* c, int64_t count, bool zero = false) {
+    if (count <= 0) return nullptr;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)count * sizeof(T));
+    if (e != cudaSuccess) fail(PMB_ENOMEM, "cudaMalloc of %lld bytes failed: %s", (long long)(count * sizeof(T)), cudaGetErrorString(e));
+    c->allocs.push_back(p);
+    c->bytes_alloc += count * (int64_t)sizeof(T);
+    if (zero) CK(cudaMemsetAsync(p, 0, (size_t)count * sizeof(T), c->stream));
+    return (T*)p;
+}
+
+template <class T>
+inline T* upload(pmb_ctx* c, const std::vector<T>& v) {
+    if (v.empty()) return nullptr;
+    T* d = dalloc<T>(c, (int64_t)v.size());
+    // synchronous copy: `v` is usually a temporary
+    CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+inline AlphaDev alpha_dev(pmb_ctx* c, const Alpha& a) {
+    AlphaDev d;
+    d.c = a.c; d.ptr = nullptr; d.bstride = 0;
+    if (a.node >= 0) {
+        const Node& n = c->nodes[a.node];
+        d.ptr = n.dptr; d.bstride = n.bstride;
+    }
+    return d;
+}
+
+inline int32_t optcol(pmb_ctx* c, int64_t var) { return (int32_t)(c->varmap[(size_t)(var - 1)] - 1); }
+
 }  // namespace pmb
 
 #define API_BEGIN(ctx)                 \
@@ -43,8 +83,3 @@ QuadForm quad_of(pmb_ctx* c, int id);
     }                                                        \
     return PMB_OK;
 
-#define CK(x)                                                                                  \
-    do {                                                                                       \
-        cudaError_t e_ = (x);                                                                  \
-        if (e_ != cudaSuccess) pmb::fail(PMB_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
-    } while (0)

@@ -127,11 +127,11 @@ struct Node {
     std::shared_ptr<QuadForm> quad;
 };
 
-enum KernelClass { KC_AFFINE = 0, KC_GRAM, KC_GEMM, KC_PHILOX, KC_H2D, KC_REDUCE, KC_MISC, KC_COUNT };
+enum KernelClass { KC_AFFINE = 0, KC_GRAM, KC_GEMM, KC_PHILOX, KC_H2D, KC_REDUCE, KC_MISC, KC_PACK, KC_COUNT };
 
 enum StepType {
     ST_TICK, ST_PHILOX, ST_H2D, ST_MEMSET, ST_LINCOMB, ST_TRANSPOSE, ST_GEMV, ST_DOT, ST_SPROD, ST_AFFINE, ST_GRAM, ST_GEMM,
-    ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM, ST_PROLOGUE, ST_GEMV_DOT
+    ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM, ST_PROLOGUE, ST_GEMV_DOT, ST_PACK_P, ST_PACK_A
 };
 
 struct Step {
@@ -176,6 +176,9 @@ struct Constraint {
     double* vals = nullptr;
     int32_t* sp_rows = nullptr;
     int32_t* sp_cols = nullptr;
+    // term-list export (built lazily by pmb_block_export_terms)
+    bool export_ready = false;
+    ExportArgs ex{};
     AffForm form;
 };
 
@@ -208,7 +211,13 @@ struct pmb_ctx {
     int64_t bytes_alloc = 0;
     unsigned long long* d_counter = nullptr;
     unsigned int* d_ticket = nullptr;
-    std::vector<pmb::FillJob> fill_jobs;  // collected while planning, lowered to one ST_PROLOGUE step
+    std::vector<pmb::FillJob> fill_jobs;
+    // solver-side ingest (pmb_enable_qp_pack): packed upper-triangular P, stacked CSC A, row bounds
+    bool qp_pack = false;
+    int64_t qp_m = 0, qp_nnzP = 0, qp_nnzA = 0;
+    double *qp_Px = nullptr, *qp_Ax = nullptr, *qp_l = nullptr, *qp_u = nullptr;
+    int64_t *qp_Pp = nullptr, *qp_Pi = nullptr, *qp_Ap = nullptr, *qp_Ai = nullptr;
+    pmb::PackBlockDev* qp_blocks_dev = nullptr;  // collected while planning, lowered to one ST_PROLOGUE step
     int64_t updates = 0;
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraph_t graph = nullptr;

@@ -189,4 +189,34 @@ struct ScatterSymArgs {
 void launch_scatter_sym(const ScatterSymArgs& a, int64_t batch, cudaStream_t stream);
 void launch_fill(double* p, int64_t n, double v, cudaStream_t stream);
 
+// ---------------- term-list export + QP pack (kernels_export.cu) ---------------------------------------------------------
+struct TermEntryDev {      // one term of the per-row template
+    int32_t kind;          // 0: matrix term (coefficient = alpha * src[row + srccol * ld]),  1: unit term (coefficient = alpha)
+    int32_t term;          // index into mats / units
+    int64_t srccol;        // matrix: source column;  unit: offset into unit_vars of this unit's per-row variable table
+    int64_t var;           // matrix: 1-based optimizer variable;  unit: unused
+};
+struct ExportArgs {
+    const TermEntryDev* tmpl; int32_t T;          // terms per row
+    const AffMatTermDev* mats; const AffUnitTermDev* units;
+    const int64_t* unit_vars;                     // per-row 1-based optimizer variable of unit terms
+    int64_t rows;
+    void* out;                                    // batch * rows * T records of 24 bytes
+};
+void launch_export_terms(const ExportArgs& a, int64_t batch, cudaStream_t stream);
+// P_x[j(j+1)/2 + i] = Q[i + j*N]  (i <= j)
+void launch_pack_upper(const double* Q, int64_t N, int64_t q_bstride, double* Px, int64_t px_bstride, int64_t batch, cudaStream_t stream);
+struct PackBlockDev {      // one constraint block inside the stacked CSC matrix
+    const double* C;       // dense: rows x N column-major;  sparse: value buffer
+    const double* d;
+    int64_t c_bstride, d_bstride;
+    int64_t rows, row_off; // rows of the block, first row in the stacked matrix
+    int32_t set_kind, sparse;
+    int64_t nnz;                 // sparse: stored values
+    const int64_t* colbase;      // dense: [N] position of this block's first entry in column j of A_x
+    const int64_t* pos;          // sparse: [nnz] position of each stored value in A_x
+};
+void launch_pack_constraints(const PackBlockDev* blocks_dev, int nblocks, int64_t N, double* Ax, int64_t ax_bstride, double* l, double* u,
+                             int64_t m_total, int64_t batch, int sm_count, cudaStream_t stream);
+
 }  // namespace pmb

@@ -14,40 +14,7 @@
 namespace pmb {
 
 void configure_gram_kernels();  // kernels_gram.cu
-
-// ---- device memory ---------------------------------------------------------------------------
-template <class T>
-static T* dalloc(pmb_ctx* c, int64_t count, bool zero = false) {
-    if (count <= 0) return nullptr;
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (size_t)count * sizeof(T));
-    if (e != cudaSuccess) fail(PMB_ENOMEM, "cudaMalloc of %lld bytes failed: %s", (long long)(count * sizeof(T)), cudaGetErrorString(e));
-    c->allocs.push_back(p);
-    c->bytes_alloc += count * (int64_t)sizeof(T);
-    if (zero) CK(cudaMemsetAsync(p, 0, (size_t)count * sizeof(T), c->stream));
-    return (T*)p;
-}
-
-template <class T>
-static T* upload(pmb_ctx* c, const std::vector<T>& v) {
-    if (v.empty()) return nullptr;
-    T* d = dalloc<T>(c, (int64_t)v.size());
-    // synchronous copy: `v` is usually a temporary
-    CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return d;
-}
-
-static AlphaDev alpha_dev(pmb_ctx* c, const Alpha& a) {
-    AlphaDev d;
-    d.c = a.c; d.ptr = nullptr; d.bstride = 0;
-    if (a.node >= 0) {
-        const Node& n = c->nodes[a.node];
-        d.ptr = n.dptr; d.bstride = n.bstride;
-    }
-    return d;
-}
-
-static int32_t optcol(pmb_ctx* c, int64_t var) { return (int32_t)(c->varmap[(size_t)(var - 1)] - 1); }
+void plan_qp_pack(pmb_ctx* c);   // pmb_export.cu
 
 // ---- reachability ----------------------------------------------------------------------------
 static void mark(pmb_ctx* c, int id) {
@@ -551,6 +518,11 @@ static void run_step(pmb_ctx* c, const Step& s) {
         case ST_TICK: launch_tick(c->d_counter, st); break;
         case ST_PROLOGUE: launch_prologue(s.jobs, s.njobs, s.job_blocks, s.batch, c->d_counter, c->d_ticket, st); break;
         case ST_GEMV_DOT: launch_gemv_t_dot(s.gemv, s.dot, s.batch, st); break;
+        case ST_PACK_P: launch_pack_upper(s.src, s.n, s.src_bstride, s.out, s.out_bstride, s.batch, st); break;
+        case ST_PACK_A:
+            launch_pack_constraints(c->qp_blocks_dev, (int)c->cons.size(), c->nvars, c->qp_Ax, c->qp_nnzA, c->qp_l, c->qp_u, c->qp_m, s.batch,
+                                    c->sm_count, st);
+            break;
         case ST_PHILOX: launch_philox_uniform(s.out, s.n, s.batch, s.seed, s.scale, c->d_counter, c->sm_count, st); break;
         case ST_MEMSET: CK(cudaMemsetAsync(s.out, 0, (size_t)s.n * sizeof(double), st)); break;
         case ST_LINCOMB: launch_lincomb(s.out, s.out_bstride, s.n, s.lterms, s.nl, s.cst, s.batch, st); break;
@@ -592,7 +564,7 @@ static void collect_timing(pmb_ctx* c) {
 
 using namespace pmb;
 
-static const char* kClassNames[KC_COUNT] = {"affine_assemble", "gram_dmma", "gemm_tn_dmma", "philox_uniform", "h2d_stage", "reduce", "misc"};
+static const char* kClassNames[KC_COUNT] = {"affine_assemble", "gram_dmma", "gemm_tn_dmma", "philox_uniform", "h2d_stage", "reduce", "misc", "pack"};
 
 extern "C" {
 
@@ -690,6 +662,7 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
         (con.is_const ? ctx->init_steps : ctx->steps).push_back(affine_step(b, ctx->batch));
         if (!con.is_const) ctx->affine_bytes += 16 * (int64_t)b.ntouched * con.rows + 16 * con.rows;
     }
+    if (ctx->qp_pack) plan_qp_pack(ctx);
     if (!ctx->fill_jobs.empty()) {
         // one fused prologue launch: Philox fills of every built-in generator, zeroing of (q, c0), update tick
         int total = 0;

@@ -220,6 +220,27 @@ class Parameter(Expr):
         return out if m.batch > 1 else out[0]
 
 
+_rt = None
+
+
+def _cudart():
+    """libcudart (already loaded by libpmb200.so) for the two scratch allocations of export_block_terms"""
+    global _rt
+    if _rt is None:
+        import ctypes.util
+        for name in ("libcudart.so.12", "libcudart.so", ctypes.util.find_library("cudart")):
+            try:
+                _rt = C.CDLL(name)
+                break
+            except (OSError, TypeError):
+                continue
+        if _rt is None:
+            raise OSError("libcudart not found")
+        _rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        _rt.cudaFree.argtypes = [C.c_void_p]
+    return _rt
+
+
 def _flatten_vars(x):
     if isinstance(x, np.ndarray) and x.dtype == object:
         x = list(x.ravel())
@@ -432,6 +453,48 @@ class Model:
         self._ck(self._lib.pmb_block_term_index(self._ctx, pos, n, C.c_void_p(rows.ctypes.data), C.c_void_p(vars_.ctypes.data),
                                                 C.c_void_p(src.ctypes.data)))
         return rows, vars_, src
+
+    # -- "next" rows of the scope table: MOI-compatible term list, solver-side QP ingest
+    TERM_DTYPE = np.dtype([("output_index", np.int64), ("coefficient", np.float64), ("variable", np.int64)])
+
+    def export_block_terms(self, pos):
+        """The reference's MOI.VectorAffineTerm list of block `pos` after update! (moi_interop.jl:64-81), produced on the device:
+        (records[batch?, nterms] of TERM_DTYPE, constants[batch?, rows])."""
+        v = self.block_view(pos)
+        b, nt, m = self.batch, v.nterms, v.rows
+        rt = _cudart()  # two scratch device buffers owned by the caller, as a Julia/MOI consumer would
+        dterms, dconst = C.c_void_p(), C.c_void_p()
+        assert rt.cudaMalloc(C.byref(dterms), max(b * nt * 24, 8)) == 0 and rt.cudaMalloc(C.byref(dconst), max(b * m * 8, 8)) == 0
+        try:
+            self._ck(self._lib.pmb_block_export_terms(self._ctx, pos, dterms, dconst))
+            recs = self._d2h(dterms.value, b * nt, self.TERM_DTYPE).reshape(b, nt)
+            consts = self._d2h(dconst.value, b * m).reshape(b, m)
+        finally:
+            rt.cudaFree(dterms)
+            rt.cudaFree(dconst)
+        return (recs[0], consts[0]) if b == 1 else (recs, consts)
+
+    def enable_qp_pack(self):
+        self._ck(self._lib.pmb_enable_qp_pack(self._ctx))
+
+    def qp_view(self):
+        v = K.QpView()
+        self._ck(self._lib.pmb_get_qp(self._ctx, C.byref(v)))
+        return v
+
+    def qp_arrays(self):
+        """Host copies of the OSQP-style QP (P upper-triangular CSC, q, c0, A CSC, l, u) -- values refreshed by every update()."""
+        v, b = self.qp_view(), self.batch
+        out = {"n": v.n, "m": v.m,
+               "P_p": self._d2h(v.P_p, v.n + 1, np.int64), "P_i": self._d2h(v.P_i, v.nnzP, np.int64),
+               "A_p": self._d2h(v.A_p, v.n + 1, np.int64), "A_i": self._d2h(v.A_i, v.nnzA, np.int64),
+               "P_x": self._d2h(v.P_x, b * v.nnzP).reshape(b, v.nnzP), "q": self._d2h(v.q, b * v.n).reshape(b, v.n),
+               "c0": self._d2h(v.c0, b), "A_x": self._d2h(v.A_x, b * v.nnzA).reshape(b, v.nnzA),
+               "l": self._d2h(v.l, b * v.m).reshape(b, v.m), "u": self._d2h(v.u, b * v.m).reshape(b, v.m)}
+        if b == 1:
+            for k_ in ("P_x", "q", "c0", "A_x", "l", "u"):
+                out[k_] = out[k_][0]
+        return out
 
     def stats(self):
         s = K.Stats()

@@ -1,0 +1,138 @@
+"""GPU parity of the two "next" rows: the MOI-compatible term-list export (bit-exact order, indices AND
+coefficients against the literal oracle's VectorAffineFunction) and the OSQP-style QP pack (patterns == and values 1e-10)."""
+import numpy as np
+import pytest
+
+from oracle import dense as D
+from tests.twin import DeviceSide, OracleSide, assert_close, oracle_outputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _moi_vector_terms(om):
+    return [e[2] for e in om.optimizer.log if e[0] == "constraint"]
+
+
+@pytest.mark.parametrize("shape", ["dense", "mpc", "box"])
+def test_term_list_export_matches_reference_order_and_values(shape):
+    rng = np.random.default_rng(hash(shape) % 1000)
+    n, m = 6, 4
+    hs = {"C": {"v": rng.random((m, n))}, "d": {"v": rng.random(m)}, "H": {"v": rng.random((n, n))}, "v0": {"v": rng.random(n)},
+          "dt": {"v": 0.25}, "c": {"v": rng.random(n)}, "lb": {"v": rng.random(n)}}
+    perm = [int(i) + 1 for i in rng.permutation(2 * n)]
+
+    def build(s):
+        x = s.variables(n)
+        u = s.variables(n)
+        P = {k_: s.parameter(h) for k_, h in hs.items()}
+        if shape == "dense":
+            s.constraint(s.mul(P["C"], x), "==", P["d"])
+        elif shape == "mpc":  # test/lazyexpression.jl:330-347
+            s.constraint(s.sub(s.mul(P["H"], s.sub(x, P["v0"])), s.mul(P["dt"], s.sub(u, P["c"]))), "==", np.zeros(n))
+        else:                 # test/model.jl:162-163
+            s.constraint(x, ">=", P["lb"])
+        return 2 * n
+
+    o, d = OracleSide(), DeviceSide()
+    build(o); build(d)
+    o.model.initialize(idxmap={i + 1: perm[i] for i in range(2 * n)})
+    d.model.initialize(idxmap=perm)
+    for step in range(2):
+        for h in hs.values():
+            h["v"] = rng.random(np.shape(h["v"])) if np.ndim(h["v"]) else float(rng.random())
+        oracle_outputs(o.model, 2 * n)
+        d.model.update()
+        f = _moi_vector_terms(o.model)[0]
+        recs, consts = d.model.export_block_terms(0)
+        assert [(int(r["output_index"]), float(r["coefficient"]), int(r["variable"])) for r in recs] == \
+               [(int(a), float(b), int(c)) for a, b, c in f.terms]          # order, indices and coefficients: bit-exact
+        assert_close(consts, [float(z) for z in f.constants], 1e-10, "constants")  # H*v0 is a reduction: 1e-10, not bit-exact
+
+
+def test_term_list_export_full_size_properties():
+    """cfg2's constraint block (m=1024, n=4096: 4.19 M records, 100 MB): row-outer / term-inner, coefficients == C row-major."""
+    import parametron_b200 as pm
+    n, m = 4096, 1024
+    rng = np.random.default_rng(0)
+    Cv, dv = rng.random((m, n)), rng.random(m)
+    model = pm.Model()
+    x = model.variables(n)
+    pm.constraint(model, pm.Parameter(model, val=Cv) * x, "==", pm.Parameter(model, val=dv))
+    model.initialize()
+    model.update()
+    recs, consts = model.export_block_terms(0)
+    assert recs.shape == (m * n,)
+    assert np.array_equal(recs["output_index"], np.repeat(np.arange(1, m + 1), n))
+    assert np.array_equal(recs["variable"], np.tile(np.arange(1, n + 1), m))
+    assert np.array_equal(recs["coefficient"], Cv.ravel()) and np.array_equal(consts, -dv)
+
+
+def test_qp_pack_matches_dense_oracle():
+    """README Example 1 shape + box constraints: P upper CSC, stacked A CSC (update order: Nonnegatives, Nonpositives, Zeros),
+    bounds from the set kinds."""
+    import parametron_b200 as pm
+    n, k, m = 12, 9, 5
+    rng = np.random.default_rng(3)
+    A, b, Cm, dv, lo, hi = rng.random((k, n)), rng.random(k), rng.random((m, n)), rng.random(m), -rng.random(n), rng.random(n)
+    model = pm.Model()
+    x = model.variables(n)
+    r = pm.Parameter(model, val=A) * x - pm.Parameter(model, val=b)
+    pm.objective(model, pm.Minimize, pm.dot(r, r))
+    pm.constraint(model, pm.Parameter(model, val=Cm) * x, "==", pm.Parameter(model, val=dv))   # Zeros        (bucket 5)
+    pm.constraint(model, x, "<=", pm.Parameter(model, val=hi))                                # Nonpositives (bucket 4)
+    pm.constraint(model, x, ">=", pm.Parameter(model, val=lo))                                # Nonnegatives (bucket 3)
+    model.enable_qp_pack()
+    perm = rng.permutation(n) + 1
+    model.initialize(idxmap=perm)
+    model.update()
+    qp = model.qp_arrays()
+    Qo, qo, c0o = D.least_squares_objective(A, b, np.arange(1, n + 1), n, varmap=perm)
+    # P: upper triangle, CSC
+    assert np.array_equal(qp["P_p"], np.array([j * (j + 1) // 2 for j in range(n + 1)]))
+    assert np.array_equal(qp["P_i"], np.concatenate([np.arange(j + 1) for j in range(n)]))
+    assert_close(qp["P_x"], np.concatenate([Qo[:j + 1, j] for j in range(n)]), 1e-10, "P_x")
+    assert_close(qp["q"], qo, 1e-10, "q"); assert_close([qp["c0"]], [c0o], 1e-10, "c0")
+    # A: stacked in update order  [x - lo >= 0 ; x - hi <= 0 ; Cx - d == 0]
+    I = np.zeros((n, n)); I[np.arange(n), perm - 1] = 1.0
+    Co, _ = D.affine_block(Cm, dv, np.arange(1, n + 1), n, varmap=perm)
+    Astack = np.vstack([I, I, Co])
+    M = 2 * n + m
+    assert qp["m"] == M and np.array_equal(qp["A_p"], np.arange(n + 1) * M) and np.array_equal(qp["A_i"], np.tile(np.arange(M), n))
+    assert np.array_equal(qp["A_x"], Astack.T.ravel())
+    assert np.array_equal(qp["l"], np.concatenate([lo, np.full(n, -np.inf), dv]))
+    assert np.array_equal(qp["u"], np.concatenate([np.full(n, np.inf), hi, dv]))
+    # KKT sanity with the packed data: the equality-constrained least-squares solution satisfies A_eq x = d
+    Pfull = np.zeros((n, n))
+    for j in range(n):
+        Pfull[:j + 1, j] = qp["P_x"][qp["P_p"][j]:qp["P_p"][j + 1]]
+    Pfull = Pfull + Pfull.T - np.diag(np.diag(Pfull))
+    assert_close(Pfull, Qo, 1e-10, "P symmetric completion")
+
+
+def test_qp_pack_with_sparse_block():
+    import parametron_b200 as pm
+    rows, cols, b = 8, 16, 4
+    rng = np.random.default_rng(5)
+    br, bc = np.array([0, 1, 1], dtype=np.int64), np.array([2, 0, 3], dtype=np.int64)
+    blocks = rng.random((3, b, b))
+    dv, lo = rng.random(rows), rng.random(cols)
+    model = pm.Model()
+    x = model.variables(cols)
+    pm.constraint(model, pm.Parameter(model, val=blocks, bsr=(rows, cols, b, br, bc)) * x, "==", pm.Parameter(model, val=dv))
+    pm.constraint(model, x, ">=", pm.Parameter(model, val=lo))
+    model.enable_qp_pack()
+    model.initialize()
+    model.update()
+    qp = model.qp_arrays()
+    dense = np.zeros((rows, cols))
+    for k_, (i, j) in enumerate(zip(br, bc)):
+        dense[i * b:(i + 1) * b, j * b:(j + 1) * b] = blocks[k_]
+    Astack = np.vstack([np.eye(cols), dense])       # update order: Nonnegatives (bucket 3) before Zeros (bucket 5)
+    got = np.zeros_like(Astack)
+    for j in range(cols):
+        sl = slice(qp["A_p"][j], qp["A_p"][j + 1])
+        assert np.all(np.diff(qp["A_i"][sl]) > 0)   # rows ascending inside a column
+        got[qp["A_i"][sl], j] = qp["A_x"][sl]
+    assert np.array_equal(got, Astack)
+    assert qp["A_p"][-1] == cols * cols + 3 * b * b and qp["P_x"].size == 0  # the Variable block is dense (identity incl. zeros)
+    assert np.array_equal(qp["l"], np.concatenate([lo, dv])) and np.array_equal(qp["u"], np.concatenate([np.full(cols, np.inf), dv]))
