@@ -9,7 +9,8 @@ One "step" = one `update!`: every Parameter (A 4096x4096, b, C 1024x4096, d) re-
   python bench.py --impl reference ...                          the reference's CPU path (literal term-list port, 1 thread)
 
 Prints ONE JSON line (rank 0).  `value` = updates/s with inputs resident in HBM; `e2e` = the same through the C ABI with
-pinned HOST Parameter buffers copied H2D every step and (Q, q, c0, C, d) copied D2H every step.
+pinned HOST Parameter buffers copied H2D every step and the assembled QP in solver-ingest form (P upper-triangular CSC values,
+q, c0, stacked A CSC values, l, u -- what replaces MOI.set) copied D2H every step.
 """
 import argparse
 import json
@@ -251,17 +252,17 @@ def main():
     # one affine-class launch per update here: the constraint block (16 B per stored coefficient + 16 B per row)
     aff_gbs = st["affine_algorithmic_bytes"] / (aff_ms * 1e-3) / 1e9 if aff_ms > 0 else None
 
-    # ---- e2e arm: HOST Parameter buffers (pinned) -> H2D every step -> update -> D2H of (Q, q, c0, C, d) every step ----
+    # ---- e2e arm: HOST Parameter buffers (pinned) -> H2D every step -> update (+ QP pack) -> D2H of (P_x, q, c0, A_x, l, u) every step ----
     e2e = None
     if not args.no_e2e:
-        from oracle import philox  # noqa: F401  (NOT used to compute anything measured: only fills the synthetic host inputs)
         em = pm.Model(device=local_rank, batch=1, stream=stream)
         rng = np.random.default_rng(SEED + rank)
         host = {"A": rng.random((K_ROWS, N_VARS)), "b": rng.random(K_ROWS), "C": rng.random((M_ROWS, N_VARS)), "d": 2 * rng.random(M_ROWS)}
         EP = declare_model(pm, em, "host", host)
+        em.enable_qp_pack()   # results leave the device in the form the solver ingests: P upper-triangular CSC, q, c0, A CSC, l, u
         em.initialize()
-        ov, bv = em.objective_view(), em.block_view(0)
-        outs = [(ov.Q, N_VARS * N_VARS), (ov.q, N_VARS), (ov.c0, 1), (bv.C, M_ROWS * N_VARS), (bv.d, M_ROWS)]
+        qv = em.qp_view()
+        outs = [(qv.P_x, qv.nnzP), (qv.q, N_VARS), (qv.c0, 1), (qv.A_x, qv.nnzA), (qv.l, qv.m), (qv.u, qv.m)]
         pinned = [em._pinned((n,)) for _, n in outs]
         import ctypes as C
 
@@ -280,11 +281,12 @@ def main():
         d2h = 8 * sum(n for _, n in outs)
         e2e = {"value": world * 1e3 / ems, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems,
                "steps": esteps}
-        # sanity: the e2e result is the dense meaning of the host inputs (spot check on a few entries, fp64)
-        Qh = pinned[0].reshape(N_VARS, N_VARS)
+        # sanity: the e2e result is the dense meaning of the host inputs (spot checks, fp64)
         i, j = 17, 2049
         ref = 2.0 * float(host["A"][:, i] @ host["A"][:, j])
-        assert abs(Qh[j, i] - ref) <= 1e-10 * abs(ref), (Qh[j, i], ref)
+        got = pinned[0][j * (j + 1) // 2 + i]                       # P_x: column j holds rows 0..j
+        assert abs(got - ref) <= 1e-10 * abs(ref), (got, ref)
+        assert pinned[3][j * M_ROWS + 5] == host["C"][5, j] and pinned[4][7] == host["d"][7] == pinned[5][7]
         em.close()
 
     cpu = None

@@ -64,7 +64,8 @@ def test_readme_example_1():
     assert_close(Q, 2 * A["v"].T @ A["v"], 1e-10, "Q=2A'A")
     assert_close(q, -2 * A["v"].T @ b["v"], 1e-10, "q=-2A'b")
     st = d.model.stats()
-    assert st["uses_cuda_graph"] == 1 and st["kernel_launches_per_update"] > 0
+    import os
+    assert st["uses_cuda_graph"] == (0 if os.environ.get("PMB_NO_GRAPH") == "1" else 1) and st["kernel_launches_per_update"] > 0
 
 
 def test_readme_example_1_with_index_map():
