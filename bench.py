@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 N_VARS, K_ROWS, M_ROWS = 4096, 4096, 1024
 SEED = 1234
 METRIC = "QP re-parameterizations/sec (update!+coeff-assemble) at n=4096,m=1024"
+GRAM_DRAM_TRAFFIC_BYTES = 410174464 + 167363328    # ncu --set full, one launch of gram_tma_kernel<1,128> at cfg2
+AFFINE_DRAM_TRAFFIC_BYTES = 33626880 + 689664       # ncu --set full, one launch of affine_assemble_tma<0> at cfg2
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200: profiles/r01_probe_dmma.txt (mma.sync f64, all SMs)
 
 
@@ -313,12 +315,15 @@ def main():
             "gpu_launches": int(st["kernel_launches_per_update"]) * args.steps,
             "launches_per_update": int(st["kernel_launches_per_update"]), "cuda_graph": bool(st["uses_cuda_graph"]),
             "roofline": {"bound": "tensor", "kernel": "gram_tma_kernel<SYRK,128> (Q = 2A'A: TMA ring + warp-specialised fp64 DMMA)", "achieved": gram_tflops,
-                         "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gram_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                         "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gram_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": GRAM_DRAM_TRAFFIC_BYTES,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_e_gram_tma_ncu_full.txt "
+                                           "(algorithmic: 134 MB read of A + 134 MB write of Q)",
                          "algorithmic_flops": int(st["gram_algorithmic_flops"]), "avg_launch_ms": gram_ms,
                          "peak_source": "fp64 mma.sync (DMMA) peak measured on this pool's B200, profiles/r01_probe_dmma.txt; "
                                         "MEASURED_PEAKS.json has no fp64 entry and tcgen05 has no f64 kind"},
             "roofline_affine": {"bound": "hbm", "kernel": "affine_assemble_tma (C, -d): bulk-copy ring", "achieved": aff_gbs, "peak": peaks["hbm_gbs"],
-                                "unit": "GB/s", "frac": (aff_gbs / peaks["hbm_gbs"]) if aff_gbs else None, "traffic": None,
+                                "unit": "GB/s", "frac": (aff_gbs / peaks["hbm_gbs"]) if aff_gbs else None, "traffic": AFFINE_DRAM_TRAFFIC_BYTES,
+                                "traffic_source": "profiles/r01_e_affine_tma_ncu_full.txt: 33.6 MB read; the 33.5 MB written stay in the 126 MB L2",
                                 "algorithmic_bytes": int(st["affine_algorithmic_bytes"]), "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                                 "note": "CUDA-event time of the single launch inside an eager replay of the step (includes ~3 us of event/launch overhead; "
                                         "ncu gpu__time_duration of the same launch: profiles/r01_e_affine_tma_ncu_full.txt)"},

@@ -427,3 +427,49 @@ def test_constant_quadratic_terms_and_linear_objective():
     # MOI Hessian: diagonal terms doubled (moi_interop.jl:58), off-diagonal term counted in both triangles
     assert np.array_equal(Q, 2.0 * np.array([[4.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]]))
     assert np.array_equal(q, [1.0, 7.0, 1.0]) and c0 == 2.0
+
+
+def test_c_abi_host_callback_and_external_device_pointer():
+    """The two Parameter plumbing modes only the raw C ABI exposes: a C host callback run exactly once per pmb_update
+    (parameter.jl:93-102 through @cfunction) and a caller-owned device buffer (manual mode, parameter.jl:88)."""
+    import ctypes as C
+    import parametron_b200 as pm
+    from parametron_b200 import _capi as K
+    from parametron_b200.model import _cudart
+    n, k = 4, 3
+    m = pm.Model()
+    lib, ctx = m._lib, m._ctx
+    x = m.variables(n)
+    # host Parameter A with a C callback that fills it with (call count)
+    A = C.c_int32()
+    m._ck(lib.pmb_param_create(ctx, 2, k, n, K.PARAM_HOST, A))
+    hostA = m._pinned((k * n,))
+    calls = []
+
+    @K.HOST_CALLBACK
+    def cb(val, rows, cols, batch, user):
+        calls.append((rows, cols, batch))
+        for i in range(rows * cols):
+            val[i] = float(len(calls))
+    m._ck(lib.pmb_param_set_host_ptr(ctx, A.value, C.c_void_p(hostA.ctypes.data), C.cast(cb, C.c_void_p), None))
+    # device Parameter d living in a buffer this test owns
+    rt = _cudart()
+    dbuf = C.c_void_p()
+    assert rt.cudaMalloc(C.byref(dbuf), k * 8) == 0
+    d = C.c_int32()
+    m._ck(lib.pmb_param_create(ctx, 1, k, 0, K.PARAM_DEVICE, d))
+    m._ck(lib.pmb_param_set_device_ptr(ctx, d.value, dbuf))
+    pm.constraint(m, pm.Expr(m, A.value) * x, "==", pm.Expr(m, d.value))
+    m.initialize()
+    p = C.c_void_p()
+    m._ck(lib.pmb_param_device_ptr(ctx, d.value, p))
+    assert p.value == dbuf.value                       # the library reads the caller's buffer in place
+    for step in (1, 2, 3):
+        dv = np.arange(k, dtype=np.float64) * step
+        m._ck(lib.pmb_memcpy_h2d(ctx, dbuf, C.c_void_p(dv.ctypes.data), k * 8))
+        m.update()
+        Cb, db = m.block_arrays(0)
+        assert len(calls) == step and calls[-1] == (k, n, 1)
+        assert np.array_equal(Cb, np.full((k, n), float(step))) and np.array_equal(db, -dv)
+    m.close()
+    rt.cudaFree(dbuf)
