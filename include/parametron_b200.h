@@ -175,6 +175,9 @@ typedef struct {
     double* vals;            /* device, batch stride nnz */
     const int32_t* sp_rows;  /* device, [nnz] */
     const int32_t* sp_cols;  /* device, [nnz] */
+    /* scalar quadratic constraint (bucket 6-8: 1/2 x'Qx + C x + d in GreaterThan/LessThan/EqualTo(0)): Q is the symmetric MOI
+     * Hessian (N x N column-major, batch stride N*N), C the 1 x N linear part, d the constant; NULL for affine blocks */
+    double* Q;
 } pmb_block_view;
 
 int pmb_get_objective(pmb_ctx* ctx, pmb_objective_view* out);

@@ -29,7 +29,8 @@ class ObjectiveView(C.Structure):
 class BlockView(C.Structure):
     _fields_ = [("set_kind", C.c_int32), ("is_scalar", C.c_int32), ("is_constant", C.c_int32), ("bucket", C.c_int32),
                 ("rows", C.c_int64), ("nvars", C.c_int64), ("C", C.c_void_p), ("d", C.c_void_p), ("nterms", C.c_int64),
-                ("is_sparse", C.c_int32), ("nnz", C.c_int64), ("vals", C.c_void_p), ("sp_rows", C.c_void_p), ("sp_cols", C.c_void_p)]
+                ("is_sparse", C.c_int32), ("nnz", C.c_int64), ("vals", C.c_void_p), ("sp_rows", C.c_void_p), ("sp_cols", C.c_void_p),
+                ("Q", C.c_void_p)]
 
 
 class QpView(C.Structure):

@@ -784,6 +784,13 @@ int pmb_add_constraint(pmb_ctx* ctx, pmb_node expr, int set_kind, int32_t* block
         con.is_scalar = false; con.bucket = 3 + set_kind;
     } else if (n.kind == PMB_KIND_AFF) {  // model.jl:79-86 scalar sets
         con.is_scalar = true; con.bucket = 0 + set_kind;
+    } else if (n.kind == PMB_KIND_QUAD) {  // model.jl:79-86 with a QuadraticFunction value: ScalarQuadraticFunction-in-set
+        con.is_scalar = true; con.bucket = 6 + set_kind; con.is_quad = true;
+        con.quad = std::make_shared<QuadForm>(quad_of(ctx, expr));
+        con.rows = 1;
+        ctx->cons.push_back(std::move(con));
+        if (block_id) *block_id = (int32_t)ctx->cons.size() - 1;
+        return PMB_OK;
     } else {
         fail(PMB_EUNSUPPORTED, "constraint on a value of kind %d has no device lowering", n.kind);
     }

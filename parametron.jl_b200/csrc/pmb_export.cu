@@ -12,6 +12,8 @@ namespace pmb {
 // ---- QP pack plan (called from pmb_initialize when enabled) -------------------------------------------------------------------
 void plan_qp_pack(pmb_ctx* c) {
     const int64_t N = c->nvars, nb = c->batch;
+    for (auto& con : c->cons)
+        if (con.is_quad) fail(PMB_EUNSUPPORTED, "the OSQP-style QP form has no quadratic constraints");
     // P: upper triangle of the dense Hessian, column j holds rows 0..j
     if (c->obj_kind == PMB_KIND_QUAD && c->Q) {
         c->qp_nnzP = N * (N + 1) / 2;
@@ -134,6 +136,7 @@ int pmb_block_export_terms(pmb_ctx* ctx, int32_t update_pos, pmb_vector_affine_t
     Constraint& con = ctx->cons[(size_t)ctx->update_order[(size_t)update_pos]];
     const AffForm& f = con.form;
     if (con.sparse) fail(PMB_EUNSUPPORTED, "sparse blocks have no reference term list (the reference would emit the structural zeros)");
+    if (con.is_quad) fail(PMB_EUNSUPPORTED, "quadratic constraints have no affine term list");
     if (!f.order_exact) fail(PMB_EUNSUPPORTED, "the reference's term order of this block is not reproducible from the device lowering");
     if (!con.export_ready) {
         // per-row template: every segment must cover all rows so that every row has the same layout

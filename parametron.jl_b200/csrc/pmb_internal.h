@@ -170,6 +170,10 @@ struct Constraint {
     double* C = nullptr;
     double* d = nullptr;
     int64_t nterms = 0;
+    // scalar quadratic constraint: (Qc, C = q as a 1 x N row, d = c0)
+    bool is_quad = false;
+    std::shared_ptr<pmb::QuadForm> quad;
+    double* Qc = nullptr;
     // sparse form (the block's only coefficient source is one BSR matrix)
     bool sparse = false;
     int64_t nnz = 0;

@@ -380,18 +380,24 @@ static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps,
 
 static AlphaDev scaled(AlphaDev a, double k) { a.c *= k; return a; }
 
-static void plan_objective(pmb_ctx* c) {
+// One scalar quadratic function (the objective, or a ScalarQuadraticFunction-in-set constraint) -> (Q, q, c0) buffers + launches.
+// The device restatement of update!(::MOI.ScalarQuadraticFunction, f, varmap), moi_interop.jl:45-62.
+struct QuadTarget {
+    double* Q = nullptr;
+    double* q = nullptr;
+    double* c0 = nullptr;
+};
+static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool want_Q) {
     const int64_t N = c->nvars, nb = c->batch;
+    QuadTarget T;
     double* qc = dalloc<double>(c, nb * (N + 1), true);
-    c->q = qc;
-    c->c0 = qc + nb * N;
-    if (c->obj_node < 0) { c->obj_const = true; c->obj_kind = PMB_KIND_AFF; return; }  // default objective: zero AffineFunction (model.jl:18)
-    QuadForm qf = quad_of(c, c->obj_node);
-    std::vector<Step>& st = c->obj_const ? c->init_steps : c->steps;
+    T.q = qc;
+    T.c0 = qc + nb * N;
+    std::vector<Step>& st = is_const ? c->init_steps : c->steps;
     const bool has_quad = !qf.grams.empty() || !qf.bilins.empty() || !qf.coos.empty();
-    if (c->obj_kind == PMB_KIND_QUAD) c->Q = dalloc<double>(c, nb * N * N, true);
+    if (want_Q) T.Q = dalloc<double>(c, nb * N * N, true);
     // (q, c0) <- 0, then the affine part overwrites its touched columns, then the quadratic terms accumulate
-    if (c->obj_const) {
+    if (is_const) {
         Step z;
         z.type = ST_MEMSET; z.cls = KC_MISC; z.out = qc; z.n = nb * (N + 1);
         st.push_back(z);
@@ -400,12 +406,12 @@ static void plan_objective(pmb_ctx* c) {
     }
     if (qf.aff.rows == 0) qf.aff.rows = 1;
     if (!qf.aff.mats.empty() || !qf.aff.units.empty() || !qf.aff.offs.empty() || !qf.aff.coff.empty())
-        st.push_back(affine_step(lower_aff(c, qf.aff, c->q, N, c->c0, 1, false, nullptr), nb));
-    if (!has_quad) return;
+        st.push_back(affine_step(lower_aff(c, qf.aff, T.q, N, T.c0, 1, false, nullptr), nb));
+    if (!has_quad) return T;
     const bool overwrite = qf.grams.size() == 1 && qf.grams[0].same && qf.bilins.empty() && qf.coos.empty();
     if (!overwrite) {
         Step zq;
-        zq.type = ST_MEMSET; zq.cls = KC_MISC; zq.out = c->Q; zq.n = nb * N * N;
+        zq.type = ST_MEMSET; zq.cls = KC_MISC; zq.out = T.Q; zq.n = nb * N * N;
         st.push_back(zq);
     }
     for (auto& gt : qf.grams) {
@@ -418,7 +424,7 @@ static void plan_objective(pmb_ctx* c) {
             s.type = ST_GRAM; s.cls = KC_GRAM; s.batch = nb;
             GramArgs ga{};
             ga.X = F.X; ga.ldx = F.ldx; ga.x_bstride = F.xbs; ga.k = F.k; ga.n = F.ncols;
-            ga.H = c->Q; ga.ldh = N; ga.h_bstride = N * N; ga.map = F.map;
+            ga.H = T.Q; ga.ldh = N; ga.h_bstride = N * N; ga.map = F.map;
             ga.scale = scaled(a, 2.0 * F.cx * F.cx); ga.accumulate = overwrite ? 0 : 1;
             s.gram = ga;
             s.gscratch = make_gram_scratch(c, true, ga.k, ga.n, ga.n, nb);
@@ -429,11 +435,11 @@ static void plan_objective(pmb_ctx* c) {
                 v.type = ST_GEMV; v.cls = KC_REDUCE; v.batch = nb;
                 GemvArgs g{};
                 g.A = F.X; g.lda = F.ldx; g.a_bstride = F.xbs; g.rows = F.k; g.cols = F.ncols; g.trans = 1;
-                g.v = F.g; g.v_bstride = F.gbs; g.v_off = 0; g.y = c->q; g.y_bstride = N; g.map = F.map;
+                g.v = F.g; g.v_bstride = F.gbs; g.v_off = 0; g.y = T.q; g.y_bstride = N; g.map = F.map;
                 g.scale = scaled(a, 2.0 * F.cx * F.cg); g.accumulate = 1;
                 v.gemv = g;
                 DotArgs d{};
-                d.x = F.g; d.x_bstride = F.gbs; d.y = F.g; d.y_bstride = F.gbs; d.n = F.k; d.out = c->c0; d.out_bstride = 1;
+                d.x = F.g; d.x_bstride = F.gbs; d.y = F.g; d.y_bstride = F.gbs; d.n = F.k; d.out = T.c0; d.out_bstride = 1;
                 d.scale = scaled(a, F.cg * F.cg); d.accumulate = 1;
                 v.dot = d;
                 v.type = ST_GEMV_DOT;  // q += 2 a cx X'g and c0 += a g.g in one launch
@@ -455,7 +461,7 @@ static void plan_objective(pmb_ctx* c) {
             sc.type = ST_SCATTER_SYM; sc.cls = KC_MISC; sc.batch = nb;
             ScatterSymArgs ss{};
             ss.M = M; ss.ldm = F.ncols; ss.m_bstride = F.ncols * Hs.ncols; ss.n = F.ncols; ss.p = Hs.ncols; ss.xmap = F.map; ss.ymap = Hs.map;
-            ss.H = c->Q; ss.ldh = N; ss.h_bstride = N * N; ss.alpha = scaled(a, F.cx * Hs.cx);
+            ss.H = T.Q; ss.ldh = N; ss.h_bstride = N * N; ss.alpha = scaled(a, F.cx * Hs.cx);
             sc.ss = ss;
             st.push_back(sc);
             c->gram_flops += 2 * F.k * F.ncols * Hs.ncols + 2 * F.k * (F.ncols + Hs.ncols) + 2 * F.k;
@@ -465,7 +471,7 @@ static void plan_objective(pmb_ctx* c) {
                 v.type = ST_GEMV; v.cls = KC_REDUCE; v.batch = nb;
                 GemvArgs g{};
                 g.A = X.X; g.lda = X.ldx; g.a_bstride = X.xbs; g.rows = X.k; g.cols = X.ncols; g.trans = 1;
-                g.v = G.g; g.v_bstride = G.gbs; g.v_off = 0; g.y = c->q; g.y_bstride = N; g.map = X.map;
+                g.v = G.g; g.v_bstride = G.gbs; g.v_off = 0; g.y = T.q; g.y_bstride = N; g.map = X.map;
                 g.scale = scaled(a, X.cx * G.cg); g.accumulate = 1;
                 v.gemv = g;
                 st.push_back(v);
@@ -476,7 +482,7 @@ static void plan_objective(pmb_ctx* c) {
                 Step dd;
                 dd.type = ST_DOT; dd.cls = KC_REDUCE; dd.batch = nb;
                 DotArgs d{};
-                d.x = F.g; d.x_bstride = F.gbs; d.y = Hs.g; d.y_bstride = Hs.gbs; d.n = F.k; d.out = c->c0; d.out_bstride = 1;
+                d.x = F.g; d.x_bstride = F.gbs; d.y = Hs.g; d.y_bstride = Hs.gbs; d.n = F.k; d.out = T.c0; d.out_bstride = 1;
                 d.scale = scaled(a, F.cg * Hs.cg); d.accumulate = 1;
                 dd.dot = d;
                 st.push_back(dd);
@@ -493,7 +499,7 @@ static void plan_objective(pmb_ctx* c) {
         BilinearArgs b{};
         b.Q = qn.dptr; b.ldq = qn.rows; b.q_bstride = qn.bstride; b.nx = (int64_t)xm.size(); b.ny = (int64_t)ym.size();
         b.xmap = upload(c, xm); b.ymap = upload(c, ym);
-        b.H = c->Q; b.ldh = N; b.h_bstride = N * N; b.alpha = alpha_dev(c, bt.a);
+        b.H = T.Q; b.ldh = N; b.h_bstride = N * N; b.alpha = alpha_dev(c, bt.a);
         s.bl = b;
         st.push_back(s);
     }
@@ -505,10 +511,22 @@ static void plan_objective(pmb_ctx* c) {
         s.type = ST_COO; s.cls = KC_MISC; s.batch = nb;
         CooQuadArgs q{};
         q.i = upload(c, ii); q.j = upload(c, jj); q.c = upload(c, ct.c); q.nnz = (int64_t)ii.size();
-        q.H = c->Q; q.ldh = N; q.h_bstride = N * N; q.alpha = alpha_dev(c, ct.a);
+        q.H = T.Q; q.ldh = N; q.h_bstride = N * N; q.alpha = alpha_dev(c, ct.a);
         s.coo = q;
         st.push_back(s);
     }
+    return T;
+}
+
+static void plan_objective(pmb_ctx* c) {
+    if (c->obj_node < 0) {  // default objective: zero AffineFunction (model.jl:18)
+        c->obj_const = true; c->obj_kind = PMB_KIND_AFF;
+        double* qc = dalloc<double>(c, c->batch * (c->nvars + 1), true);
+        c->q = qc; c->c0 = qc + c->batch * c->nvars;
+        return;
+    }
+    QuadTarget T = plan_quadratic(c, quad_of(c, c->obj_node), c->obj_const, c->obj_kind == PMB_KIND_QUAD);
+    c->Q = T.Q; c->q = T.q; c->c0 = T.c0;
 }
 
 // ---- run ---------------------------------------------------------------------------------------
@@ -642,7 +660,10 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
             if (ctx->cons[i].bucket == b) ctx->update_order.push_back((int)i);
     // which numeric nodes are live
     if (ctx->obj_node >= 0) mark_quad(ctx, quad_of(ctx, ctx->obj_node));
-    for (auto& con : ctx->cons) mark_aff(ctx, con.form);
+    for (auto& con : ctx->cons) {
+        if (con.is_quad) mark_quad(ctx, *con.quad);
+        else mark_aff(ctx, con.form);
+    }
     bool any_uniform = false;
     for (auto& n : ctx->nodes) any_uniform = any_uniform || (n.needed && n.nop == NOP_PARAM && n.pmode == PMB_PARAM_UNIFORM);
     ctx->d_counter = (unsigned long long*)dalloc<unsigned long long>(ctx, 1, true);
@@ -655,6 +676,11 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
     for (int ci : ctx->update_order) {
         Constraint& con = ctx->cons[(size_t)ci];
         if (con.sparse) { plan_sparse_block(ctx, con); continue; }
+        if (con.is_quad) {  // ScalarQuadraticFunction-in-set (buckets 6-8, moi_interop.jl:186-188)
+            QuadTarget T = plan_quadratic(ctx, *con.quad, con.is_const, true);
+            con.Qc = T.Q; con.C = T.q; con.d = T.c0; con.nterms = 0;
+            continue;
+        }
         con.C = dalloc<double>(ctx, ctx->batch * con.rows * N, true);
         con.d = dalloc<double>(ctx, ctx->batch * con.rows, true);
         con.nterms = aff_nterms(con.form);
@@ -787,6 +813,7 @@ int pmb_get_block(pmb_ctx* ctx, int32_t update_pos, pmb_block_view* out) {
     Constraint& con = block_at(ctx, update_pos);
     out->set_kind = con.set_kind; out->is_scalar = con.is_scalar ? 1 : 0; out->is_constant = con.is_const ? 1 : 0;
     out->bucket = con.bucket; out->rows = con.rows; out->nvars = ctx->nvars; out->C = con.C; out->d = con.d; out->nterms = con.nterms;
+    out->Q = con.Qc;
     out->is_sparse = con.sparse ? 1 : 0; out->nnz = con.nnz; out->vals = con.vals; out->sp_rows = con.sp_rows; out->sp_cols = con.sp_cols;
     API_END(ctx)
 }
@@ -796,6 +823,7 @@ int pmb_block_term_index(pmb_ctx* ctx, int32_t update_pos, int64_t capacity, int
     Constraint& con = block_at(ctx, update_pos);
     const AffForm& f = con.form;
     if (con.sparse) fail(PMB_EUNSUPPORTED, "sparse blocks export their static index through pmb_block_view (sp_rows, sp_cols)");
+    if (con.is_quad) fail(PMB_EUNSUPPORTED, "quadratic constraints have no affine term index");
     if (!f.order_exact) fail(PMB_EUNSUPPORTED, "the reference's term order of this block is not reproducible from the device lowering");
     if (capacity < con.nterms) fail(PMB_EINVAL, "capacity %lld < %lld terms", (long long)capacity, (long long)con.nterms);
     // update!(::VectorAffineFunction): row-outer, term-inner, varmap applied (moi_interop.jl:64-81)

@@ -433,6 +433,17 @@ class Model:
             Cm = np.transpose(self._d2h(v.C, b * m * N).reshape(b, N, m), (0, 2, 1))
         return (Cm[0], d[0]) if b == 1 else (Cm, d)
 
+    def block_quadratic(self, pos):
+        """(Q, q, c0) of a scalar quadratic constraint block (1/2 x'Qx + q'x + c0 in the set)."""
+        v = self.block_view(pos)
+        if not v.Q:
+            raise ValueError("block is not a quadratic constraint")
+        N, b = v.nvars, self.batch
+        Q = np.transpose(self._d2h(v.Q, b * N * N).reshape(b, N, N), (0, 2, 1))
+        q = self._d2h(v.C, b * N).reshape(b, N)
+        c0 = self._d2h(v.d, b)
+        return (Q[0], q[0], float(c0[0])) if b == 1 else (Q, q, c0)
+
     def block_sparse(self, pos):
         """(vals, rows, cols, d) of a sparse block: coefficient e is vals[e] at 0-based (rows[e], cols[e]); the index is static."""
         v = self.block_view(pos)

@@ -473,3 +473,36 @@ def test_c_abi_host_callback_and_external_device_pointer():
         assert np.array_equal(Cb, np.full((k, n), float(step))) and np.array_equal(db, -dv)
     m.close()
     rt.cudaFree(dbuf)
+
+
+def test_quadratic_constraint_blocks():
+    """test/model.jl:364-394 (the Gurobi QCQP case, skipped on the reference's CI): a QuadraticFunction-valued constraint goes
+    to the ScalarQuadraticFunction buckets (moi_interop.jl:186-188), after every affine bucket; same (Q, q, c0) translation
+    (diagonal x2, moi_interop.jl:45-62) as the objective."""
+    from oracle import dense as D
+    from oracle import model as OM
+    n, k = 5, 4
+    rng = np.random.default_rng(43)
+    Ah, bh, rh = {"v": rng.random((k, n))}, {"v": rng.random(k)}, {"v": 3.0}
+    sides = []
+    for side in (OracleSide(), DeviceSide()):
+        x = side.variables(n)
+        A, b, r = (side.parameter(h) for h in (Ah, bh, rh))
+        res = side.sub(side.mul(A, x), b)
+        side.constraint(side.dot(res, res), "<=", r)            # ||Ax - b||^2 <= r       (ScalarQuadratic / LessThan: bucket 7)
+        side.constraint(side.mul(A, x), ">=", b)                # vector Nonnegatives      (bucket 3)
+        side.objective("min", side.dot(x, x))
+        side.model.initialize()
+        sides.append(side)
+    o, d = sides
+    assert [d.model.block_view(i).bucket for i in range(2)] == [3, 7]
+    for step in range(3):
+        Ah["v"] = rng.random((k, n)); bh["v"] = rng.random(k); rh["v"] = float(rng.random()) + 1.0
+        o.model.optimizer.log.clear()
+        o.model.update()
+        d.model.update()
+        fq = [e[2] for e in o.model.optimizer.log if e[0] == "constraint" and isinstance(e[2], OM.ScalarQuadraticFunctionMOI)][0]
+        Qo, qo, c0o = D.moi_quadratic_to_dense(fq, n)
+        Q, q, c0 = d.model.block_quadratic(1)
+        assert_close(Q, Qo, 1e-10, "Qc"); assert_close(q, qo, 1e-10, "qc"); assert_close([c0], [c0o], 1e-10, "c0c")
+        assert d.model.block_view(1).set_kind == 1 and d.model.block_view(1).is_scalar == 1
