@@ -264,31 +264,27 @@ def main():
         em.enable_qp_pack()   # results leave the device in the form the solver ingests: P upper-triangular CSC, q, c0, A CSC, l, u
         em.initialize()
         qv = em.qp_view()
-        outs = [(qv.P_x, qv.nnzP), (qv.q, N_VARS), (qv.c0, 1), (qv.A_x, qv.nnzA), (qv.l, qv.m), (qv.u, qv.m)]
-        pinned = [em._pinned((n,)) for _, n in outs]
-        import ctypes as C
+        sink = em.qp_host_sink()   # pinned host destinations filled by memcpy nodes of the update graph
+        d2h = 8 * sum(a.size for a in sink.values())
 
         def e2e_step():
-            # the user-facing call: Parameters already written into their pinned host buffers by the caller; pmb_update copies
-            # them H2D and assembles; then the results are read back
+            # the user-facing call: Parameters already written into their pinned host buffers by the caller; ONE pmb_update uploads
+            # them, assembles, packs and downloads the QP (all inside the update graph); the host then waits for the results
             em._ck(em._lib.pmb_update(em._ctx))
-            for (dptr, n), hb in zip(outs, pinned):
-                em._ck(em._lib.pmb_memcpy_d2h(em._ctx, C.c_void_p(hb.ctypes.data), C.c_void_p(dptr), n * 8))
             em.synchronize()
         for _ in range(args.warmup):
             e2e_step()
         esteps = max(3, min(args.steps, 20))
         ems = timed(e2e_step, esteps) / esteps
         h2d = 8 * (K_ROWS * N_VARS + K_ROWS + M_ROWS * N_VARS + M_ROWS)
-        d2h = 8 * sum(n for _, n in outs)
         e2e = {"value": world * 1e3 / ems, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems,
                "steps": esteps}
         # sanity: the e2e result is the dense meaning of the host inputs (spot checks, fp64)
         i, j = 17, 2049
         ref = 2.0 * float(host["A"][:, i] @ host["A"][:, j])
-        got = pinned[0][j * (j + 1) // 2 + i]                       # P_x: column j holds rows 0..j
+        got = sink["P_x"][0, j * (j + 1) // 2 + i]                  # P_x: column j holds rows 0..j
         assert abs(got - ref) <= 1e-10 * abs(ref), (got, ref)
-        assert pinned[3][j * M_ROWS + 5] == host["C"][5, j] and pinned[4][7] == host["d"][7] == pinned[5][7]
+        assert sink["A_x"][0, j * M_ROWS + 5] == host["C"][5, j] and sink["l"][0, 7] == host["d"][7] == sink["u"][0, 7]
         em.close()
 
     cpu = None

@@ -225,6 +225,10 @@ typedef struct {
 } pmb_qp_view;
 int pmb_enable_qp_pack(pmb_ctx* ctx);             /* build phase: adds the pack launches to every update */
 int pmb_get_qp(pmb_ctx* ctx, pmb_qp_view* out);   /* after pmb_initialize */
+/* After pmb_enable_qp_pack (before or after pmb_initialize -- the sizes come from pmb_get_qp): pinned HOST buffers (pmb_host_alloc; sizes batch * nnzP / n / 1 / nnzA / m / m doubles, any
+ * may be NULL) that every pmb_update fills as part of the update graph: the constraint pieces (A_x, l, u) leave the device as soon
+ * as the constraint chain is done, concurrently with the objective chain; (P_x, q, c0) follow it.  Valid after pmb_synchronize. */
+int pmb_qp_set_host_sink(pmb_ctx* ctx, double* P_x, double* q, double* c0, double* A_x, double* l, double* u);
 
 /* ---- host staging helpers (pinned memory + stream-ordered copies; the e2e path of bench.py and the ctypes tests) -- */
 int pmb_host_alloc(pmb_ctx* ctx, size_t bytes, void** out);   /* cudaHostAlloc; freed by pmb_host_free or pmb_ctx_destroy */

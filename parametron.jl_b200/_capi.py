@@ -90,6 +90,7 @@ SIGNATURES = {
     "pmb_block_export_terms": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "pmb_enable_qp_pack": (C.c_int, [C.c_void_p]),
     "pmb_get_qp": (C.c_int, [C.c_void_p, C.POINTER(QpView)]),
+    "pmb_qp_set_host_sink": (C.c_int, [C.c_void_p] * 7),
     "pmb_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "pmb_enable_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "pmb_kernel_class_count": (C.c_int, []),

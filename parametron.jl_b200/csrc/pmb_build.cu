@@ -504,7 +504,10 @@ int pmb_param_set_device_ptr(pmb_ctx* ctx, pmb_node p, const double* dptr) {
 
 int pmb_param_set_host_ptr(pmb_ctx* ctx, pmb_node p, double* hptr, pmb_host_callback f, void* user) {
     API_BEGIN(ctx)
-    Node& n = param_at(ctx, p, PMB_PARAM_HOST);  // the host buffer may be re-pointed between updates (it is read in pmb_update)
+    Node& n = param_at(ctx, p, PMB_PARAM_HOST);
+    // the host buffer may be re-pointed between updates unless it was baked into the update graph as a memcpy node
+    if (ctx->initialized && ctx->h2d_in_graph && hptr != n.hptr)
+        fail(PMB_EINITIALIZED, "Model has already been initialized. The pinned host buffer of a Parameter is fixed by pmb_initialize.");
     n.hptr = hptr; n.cb = f; n.user = user;
     API_END(ctx)
 }

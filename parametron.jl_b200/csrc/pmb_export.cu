@@ -117,6 +117,17 @@ int pmb_enable_qp_pack(pmb_ctx* ctx) {
     API_END(ctx)
 }
 
+int pmb_qp_set_host_sink(pmb_ctx* ctx, double* P_x, double* q, double* c0, double* A_x, double* l, double* u) {
+    API_BEGIN(ctx)
+    if (!ctx->qp_pack) fail(PMB_EINVAL, "pmb_enable_qp_pack was not called");
+    ctx->sink_Px = P_x; ctx->sink_q = q; ctx->sink_c0 = c0; ctx->sink_Ax = A_x; ctx->sink_l = l; ctx->sink_u = u;
+    if (ctx->initialized) {  // the sizes are only known after pmb_initialize: re-capture the update graph with the new memcpy nodes
+        CK(cudaStreamSynchronize(ctx->stream));
+        build_update_graph(ctx);
+    }
+    API_END(ctx)
+}
+
 int pmb_get_qp(pmb_ctx* ctx, pmb_qp_view* out) {
     API_BEGIN(ctx)
     if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_get_qp before pmb_initialize");

@@ -25,6 +25,7 @@ bool aff_is_const(pmb_ctx* c, const AffForm& f);
 bool quad_is_const(pmb_ctx* c, const QuadForm& q);
 AffForm aff_of(pmb_ctx* c, int id);
 QuadForm quad_of(pmb_ctx* c, int id);
+void build_update_graph(pmb_ctx* c);  // pmb_plan.cu
 
 #define CK(x)                                                                                  \
     do {                                                                                       \

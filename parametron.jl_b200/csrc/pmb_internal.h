@@ -120,6 +120,7 @@ struct Node {
     double* dptr = nullptr;
     int64_t numel = 0, bstride = 0;
     bool owned = false, needed = false;
+    bool used_main = false;   // read by a numeric node or the objective chain (else: constraint chain only)
     // symbolic nodes
     std::vector<int64_t> vars;
     int adj_parent = -1;
@@ -136,6 +137,7 @@ enum StepType {
 
 struct Step {
     int type = 0, cls = KC_MISC;
+    int phase = 1;  // 0: prologue, 1: numeric nodes, 2: objective chain (main branch), 3: constraint chain (aux branch)
     int64_t batch = 1;
     // generic pointer/size slots
     double* out = nullptr;
@@ -216,6 +218,12 @@ struct pmb_ctx {
     unsigned long long* d_counter = nullptr;
     unsigned int* d_ticket = nullptr;
     std::vector<pmb::FillJob> fill_jobs;
+    // two-branch update graph: objective chain on the context stream, constraint chain on an auxiliary stream
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork0 = nullptr, ev_fork1 = nullptr, ev_join = nullptr;
+    bool h2d_in_graph = false;           // HOST Parameters are copied by memcpy nodes of the graph (pinned, pointer fixed at initialize)
+    // host sinks of the packed QP (pmb_qp_set_host_sink): D2H memcpy nodes at the end of each branch
+    double *sink_Px = nullptr, *sink_q = nullptr, *sink_c0 = nullptr, *sink_Ax = nullptr, *sink_l = nullptr, *sink_u = nullptr;
     // solver-side ingest (pmb_enable_qp_pack): packed upper-triangular P, stacked CSC A, row bounds
     bool qp_pack = false;
     int64_t qp_m = 0, qp_nnzP = 0, qp_nnzA = 0;

@@ -578,6 +578,75 @@ static void collect_timing(pmb_ctx* c) {
     c->ev_pending = false;
 }
 
+// (Re)build the CUDA graph of one update: two branches -- objective chain on the context stream, constraint chain on an
+// auxiliary stream -- with the HOST-Parameter uploads and the host sinks of the packed QP as memcpy nodes.
+void build_update_graph(pmb_ctx* ctx) {
+    const int64_t N = ctx->nvars;
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+    if (ctx->graph) { cudaGraphDestroy(ctx->graph); ctx->graph = nullptr; }
+    // HOST Parameters can live inside the graph (memcpy nodes) when their buffers are pinned and fixed from here on
+    ctx->h2d_in_graph = ctx->use_graph;
+    for (auto& n : ctx->nodes) {
+        if (!n.needed || n.nop != NOP_PARAM || n.pmode != PMB_PARAM_HOST) continue;
+        unsigned int flags = 0;
+        if (!n.hptr || cudaHostGetFlags(&flags, n.hptr) != cudaSuccess) { ctx->h2d_in_graph = false; (void)cudaGetLastError(); }
+    }
+    if (ctx->use_graph && !ctx->steps.empty()) {
+        if (!ctx->aux_stream) {
+            CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->ev_fork0, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_fork1, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        cudaStream_t main_s = ctx->stream, aux_s = ctx->aux_stream;
+        CK(cudaStreamBeginCapture(main_s, cudaStreamCaptureModeThreadLocal));
+        try {
+            auto run_phase = [&](int ph, cudaStream_t on) {
+                ctx->stream = on;
+                for (auto& s : ctx->steps) if (s.phase == ph) run_step(ctx, s);
+                ctx->stream = main_s;
+            };
+            auto h2d = [&](bool main_branch, cudaStream_t on) {
+                if (!ctx->h2d_in_graph) return;
+                for (auto& n : ctx->nodes) {
+                    if (!n.needed || n.nop != NOP_PARAM || n.pmode != PMB_PARAM_HOST || n.used_main != main_branch) continue;
+                    CK(cudaMemcpyAsync(n.dptr, n.hptr, (size_t)(ctx->batch * n.numel) * sizeof(double), cudaMemcpyHostToDevice, on));
+                }
+            };
+            auto sink = [&](double* host, const double* dev, int64_t count, cudaStream_t on) {
+                if (host && dev && count > 0) CK(cudaMemcpyAsync(host, dev, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, on));
+            };
+            const int64_t nb = ctx->batch;
+            run_phase(0, main_s);                                        // prologue: generators, zeroing, tick
+            CK(cudaEventRecord(ctx->ev_fork0, main_s));
+            CK(cudaStreamWaitEvent(aux_s, ctx->ev_fork0, 0));
+            h2d(false, aux_s);                                           // constraint-only Parameters travel on the aux branch
+            h2d(true, main_s);
+            run_phase(1, main_s);                                        // derived numeric nodes (shared by both chains)
+            CK(cudaEventRecord(ctx->ev_fork1, main_s));
+            CK(cudaStreamWaitEvent(aux_s, ctx->ev_fork1, 0));
+            run_phase(3, aux_s);                                         // constraint blocks (+ stacked-A pack)
+            sink(ctx->sink_Ax, ctx->qp_Ax, nb * ctx->qp_nnzA, aux_s);
+            sink(ctx->sink_l, ctx->qp_l, nb * ctx->qp_m, aux_s);
+            sink(ctx->sink_u, ctx->qp_u, nb * ctx->qp_m, aux_s);
+            CK(cudaEventRecord(ctx->ev_join, aux_s));
+            run_phase(2, main_s);                                        // objective chain (+ upper-triangular P pack)
+            sink(ctx->sink_Px, ctx->qp_Px, nb * ctx->qp_nnzP, main_s);
+            sink(ctx->sink_q, ctx->q, nb * N, main_s);
+            sink(ctx->sink_c0, ctx->c0, nb, main_s);
+            CK(cudaStreamWaitEvent(main_s, ctx->ev_join, 0));
+        } catch (...) {
+            ctx->stream = main_s;
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(main_s, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        CK(cudaStreamEndCapture(main_s, &ctx->graph));
+        CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
+    }
+}
+
 }  // namespace pmb
 
 using namespace pmb;
@@ -628,6 +697,10 @@ int pmb_ctx_destroy(pmb_ctx* c) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->graph) cudaGraphDestroy(c->graph);
     for (auto e : c->ev) cudaEventDestroy(e);
+    if (c->ev_fork0) cudaEventDestroy(c->ev_fork0);
+    if (c->ev_fork1) cudaEventDestroy(c->ev_fork1);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     for (void* p : c->allocs) cudaFree(p);
     for (void* p : c->pinned) cudaFreeHost(p);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -670,9 +743,15 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
     (void)any_uniform;
     ctx->d_ticket = (unsigned int*)dalloc<unsigned int>(ctx, 1, true);
     const size_t nn = ctx->nodes.size();
+    size_t tagged = 0;
+    auto tag_phase = [&](int ph) {
+        for (; tagged < ctx->steps.size(); ++tagged) ctx->steps[tagged].phase = ph;
+    };
     for (size_t i = 0; i < nn; ++i)
         if (ctx->nodes[i].needed && is_numeric(ctx->nodes[i].kind)) plan_numeric(ctx, (int)i);
+    tag_phase(1);
     plan_objective(ctx);
+    tag_phase(2);
     for (int ci : ctx->update_order) {
         Constraint& con = ctx->cons[(size_t)ci];
         if (con.sparse) { plan_sparse_block(ctx, con); continue; }
@@ -688,7 +767,24 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
         (con.is_const ? ctx->init_steps : ctx->steps).push_back(affine_step(b, ctx->batch));
         if (!con.is_const) ctx->affine_bytes += 16 * (int64_t)b.ntouched * con.rows + 16 * con.rows;
     }
+    tag_phase(3);
     if (ctx->qp_pack) plan_qp_pack(ctx);
+    for (; tagged < ctx->steps.size(); ++tagged) ctx->steps[tagged].phase = ctx->steps[tagged].type == ST_PACK_P ? 2 : 3;
+    // which Parameters does the main branch (numeric nodes + objective) read?  The rest belong to the constraint chain only.
+    {
+        std::vector<char> saved(ctx->nodes.size());
+        for (size_t i = 0; i < ctx->nodes.size(); ++i) { saved[i] = ctx->nodes[i].needed; ctx->nodes[i].needed = false; }
+        if (ctx->obj_node >= 0) mark_quad(ctx, quad_of(ctx, ctx->obj_node));
+        for (size_t i = 0; i < ctx->nodes.size(); ++i) ctx->nodes[i].used_main = ctx->nodes[i].needed;
+        // anything feeding a derived numeric node is produced on the main branch too
+        for (size_t i = 0; i < ctx->nodes.size(); ++i) {
+            const Node& n = ctx->nodes[i];
+            if (!saved[i] || !is_numeric(n.kind) || n.nop == NOP_PARAM || n.nop == NOP_CONST) continue;
+            for (int in : n.in) ctx->nodes[(size_t)in].used_main = true;
+            for (auto& t : n.lin) { ctx->nodes[(size_t)t.src].used_main = true; if (t.a.node >= 0) ctx->nodes[(size_t)t.a.node].used_main = true; }
+        }
+        for (size_t i = 0; i < ctx->nodes.size(); ++i) ctx->nodes[i].needed = saved[i];
+    }
     if (!ctx->fill_jobs.empty()) {
         // one fused prologue launch: Philox fills of every built-in generator, zeroing of (q, c0), update tick
         int total = 0;
@@ -703,6 +799,7 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
         Step s;
         s.type = ST_PROLOGUE; s.cls = KC_PHILOX; s.batch = ctx->batch;
         s.jobs = upload(ctx, ctx->fill_jobs); s.njobs = (int)ctx->fill_jobs.size(); s.job_blocks = total;
+        s.phase = 0;
         ctx->steps.insert(ctx->steps.begin(), s);
     }
     ctx->launches_per_update = 0;
@@ -712,19 +809,7 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
     // constants: evaluated exactly once (constant folding lazyexpression.jl:189-192; isconstant moi_interop.jl:123,153)
     for (auto& s : ctx->init_steps) run_step(ctx, s);
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->use_graph && !ctx->steps.empty()) {
-        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        try {
-            for (auto& s : ctx->steps) run_step(ctx, s);
-        } catch (...) {
-            cudaGraph_t g = nullptr;
-            cudaStreamEndCapture(ctx->stream, &g);
-            if (g) cudaGraphDestroy(g);
-            throw;
-        }
-        CK(cudaStreamEndCapture(ctx->stream, &ctx->graph));
-        CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
-    }
+    build_update_graph(ctx);
     ctx->initialized = true;
     API_END(ctx)
 }
@@ -733,11 +818,13 @@ int pmb_update(pmb_ctx* ctx) {
     API_BEGIN(ctx)
     if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_update before pmb_initialize");
     // setdirty! + evaluate every Parameter exactly once (model.jl:133, parameter.jl:93-104)
+    const bool graph_path = !ctx->timing && ctx->graph_exec;
     for (auto& n : ctx->nodes) {
         if (!n.needed || n.nop != NOP_PARAM || n.pmode != PMB_PARAM_HOST) continue;
         if (!n.hptr) fail(PMB_EINVAL, "host Parameter has no buffer (pmb_param_set_host_ptr)");
         if (n.cb) n.cb(n.hptr, n.rows, n.cols, ctx->batch, n.user);
-        CK(cudaMemcpyAsync(n.dptr, n.hptr, (size_t)(ctx->batch * n.numel) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (!(graph_path && ctx->h2d_in_graph))
+            CK(cudaMemcpyAsync(n.dptr, n.hptr, (size_t)(ctx->batch * n.numel) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (ctx->timing) {
         collect_timing(ctx);
@@ -751,6 +838,14 @@ int pmb_update(pmb_ctx* ctx) {
         CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
     } else {
         for (auto& s : ctx->steps) run_step(ctx, s);
+    }
+    if (!graph_path) {  // eager paths: the host sinks are plain stream-ordered copies
+        const int64_t nb = ctx->batch;
+        auto sink = [&](double* host, const double* dev, int64_t count) {
+            if (host && dev && count > 0) CK(cudaMemcpyAsync(host, dev, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        };
+        sink(ctx->sink_Ax, ctx->qp_Ax, nb * ctx->qp_nnzA); sink(ctx->sink_l, ctx->qp_l, nb * ctx->qp_m); sink(ctx->sink_u, ctx->qp_u, nb * ctx->qp_m);
+        sink(ctx->sink_Px, ctx->qp_Px, nb * ctx->qp_nnzP); sink(ctx->sink_q, ctx->q, nb * ctx->nvars); sink(ctx->sink_c0, ctx->c0, nb);
     }
     ctx->updates += 1;
     API_END(ctx)

@@ -493,6 +493,17 @@ class Model:
         self._ck(self._lib.pmb_get_qp(self._ctx, C.byref(v)))
         return v
 
+    def qp_host_sink(self):
+        """Register pinned host buffers that every update() fills with the packed QP as part of the update graph (call after
+        initialize()).  Returns the dict of numpy views; valid after synchronize()."""
+        v, b = self.qp_view(), self.batch
+        bufs = {"P_x": self._pinned((b, v.nnzP)), "q": self._pinned((b, v.n)), "c0": self._pinned((b,)),
+                "A_x": self._pinned((b, v.nnzA)), "l": self._pinned((b, v.m)), "u": self._pinned((b, v.m))}
+        ptr = lambda a: C.c_void_p(a.ctypes.data) if a.size else None
+        self._ck(self._lib.pmb_qp_set_host_sink(self._ctx, ptr(bufs["P_x"]), ptr(bufs["q"]), ptr(bufs["c0"]), ptr(bufs["A_x"]),
+                                                ptr(bufs["l"]), ptr(bufs["u"])))
+        return bufs
+
     def qp_arrays(self):
         """Host copies of the OSQP-style QP (P upper-triangular CSC, q, c0, A CSC, l, u) -- values refreshed by every update()."""
         v, b = self.qp_view(), self.batch

@@ -136,3 +136,35 @@ def test_qp_pack_with_sparse_block():
     assert np.array_equal(got, Astack)
     assert qp["A_p"][-1] == cols * cols + 3 * b * b and qp["P_x"].size == 0  # the Variable block is dense (identity incl. zeros)
     assert np.array_equal(qp["l"], np.concatenate([lo, dv])) and np.array_equal(qp["u"], np.concatenate([np.full(cols, np.inf), dv]))
+
+
+def test_qp_host_sink_filled_by_the_update_graph():
+    """pmb_qp_set_host_sink: the packed QP lands in pinned host buffers as part of pmb_update (two-branch graph with in-graph
+    H2D of the pinned HOST Parameters); values equal the explicit device reads, across several re-parameterisations."""
+    import parametron_b200 as pm
+    n, k, m = 40, 33, 12
+    rng = np.random.default_rng(9)
+    vals = {"A": rng.random((k, n)), "b": rng.random(k), "C": rng.random((m, n)), "d": rng.random(m)}
+    model = pm.Model()
+    x = model.variables(n)
+    P = {key: pm.Parameter(model, val=v) for key, v in vals.items()}
+    r = P["A"] * x - P["b"]
+    pm.objective(model, pm.Minimize, pm.dot(r, r))
+    pm.constraint(model, P["C"] * x, "<=", P["d"])
+    model.enable_qp_pack()
+    model.initialize()
+    sink = model.qp_host_sink()
+    for step in range(3):
+        for key in vals:
+            P[key].val = rng.random(vals[key].shape)
+        model.update()
+        model.synchronize()
+        qp = model.qp_arrays()
+        for key in ("P_x", "q", "A_x", "l", "u"):
+            assert np.array_equal(sink[key][0], qp[key]), key
+        assert sink["c0"][0] == qp["c0"]
+        A, b = P["A"].val, P["b"].val
+        Qo = 2 * A.T @ A
+        assert_close(sink["P_x"][0], np.concatenate([Qo[:j + 1, j] for j in range(n)]), 1e-10, "P_x")
+        assert np.array_equal(sink["A_x"][0], P["C"].val.T.ravel())
+        assert np.all(np.isneginf(sink["l"][0])) and np.array_equal(sink["u"][0], P["d"].val)
