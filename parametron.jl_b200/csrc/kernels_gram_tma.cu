@@ -41,6 +41,8 @@ struct GramTmaKernelArgs {
     int64_t tiles_per_inst, total_tiles;
     int64_t full_tiles;   // tiles [0, full_tiles) are one unit each; the rest are cut into nslices k-slices
     int32_t nslices;
+    const int32_t* gate;  // see GramArgs::gate
+    int32_t gate_cols;
     int32_t* counters;    // [total_tiles - full_tiles] arrival counters, zero between launches
     double* workspace;    // [(total_tiles - full_tiles) * nslices][64][256] partial accumulators
     int64_t total_units;
@@ -108,10 +110,10 @@ __device__ __forceinline__ Unit decode_unit(const GramTmaKernelArgs& a, int64_t 
     }
     w.inst = tile / a.tiles_per_inst;
     int64_t tl = tile - w.inst * a.tiles_per_inst;
-    if (SYRK) {  // upper-triangular tile (ti <= tj), row-major enumeration
-        int ti = 0, rowlen = a.tiles_n;
-        while (tl >= rowlen) { tl -= rowlen; --rowlen; ++ti; }
-        w.ti = ti; w.tj = ti + (int)tl;
+    if (SYRK) {  // upper-triangular tile (ti <= tj), column-major enumeration: tile column tj holds tiles ti = 0..tj
+        int tj = 0;
+        while (tl >= tj + 1) { tl -= tj + 1; ++tj; }
+        w.ti = (int)tl; w.tj = tj;
     } else {
         w.ti = (int)(tl / a.tiles_n);
         w.tj = (int)(tl - (int64_t)w.ti * a.tiles_n);
@@ -179,6 +181,17 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
             for (int64_t u = blockIdx.x; u < a.total_units; u += gridDim.x) {
                 const Unit w = decode_unit<SYRK>(a, u);
                 const bool diag = SYRK && w.ti == w.tj;
+                if (SYRK && a.gate) {
+                    // wait until the column chunk holding this tile's right-most panel has been uploaded (ti <= tj: the left
+                    // panel is in the same or an earlier chunk); the flag is written by the copy engine after the data
+                    const int32_t* flag = a.gate + ((int64_t)(w.tj + 1) * BM - 1 < a.n ? ((int64_t)(w.tj + 1) * BM - 1) : (a.n - 1)) / a.gate_cols;
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                        if (!v) __nanosleep(200);
+                    } while (!v);
+                    asm volatile("fence.proxy.async;" ::: "memory");  // order the generic-proxy flag read before the async-proxy TMA reads
+                }
                 for (int kt = w.kt0; kt < w.kt1; ++kt, ++it) {
                     const int s = it % kTStages;
                     mb_wait(&empty_bar[s], ((it / kTStages) & 1) ^ 1);
@@ -357,7 +370,8 @@ GramSplitPlan plan_gram_split(bool syrk, int64_t k, int64_t n, int64_t p, int64_
 // to the cp.async kernel of kernels_gram.cu.
 static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs, const double* Y, int64_t ldy, int64_t ybs, int64_t k,
                             int64_t n, int64_t p, double* out, int64_t ldo, int64_t obs, const int32_t* map, AlphaDev scale, int accumulate,
-                            const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+                            const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream, const int32_t* gate = nullptr,
+                            int32_t gate_cols = 0) {
     if (batch > 1 && (xbs == 0 || ybs == 0)) return false;
     GramTmaKernelArgs a{};
     const int bm = sc.plan.bm == 64 ? 64 : kTBM;
@@ -375,6 +389,7 @@ static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs
     a.full_tiles = split ? a.total_tiles - sc.plan.split_tiles : a.total_tiles;
     a.counters = sc.counters;
     a.workspace = sc.workspace;
+    a.gate = gate; a.gate_cols = gate_cols;
     a.total_units = a.full_tiles + (a.total_tiles - a.full_tiles) * a.nslices;
     const int grid = (int)(a.total_units < sm_count ? a.total_units : sm_count);
     if (bm == 64) {
@@ -387,9 +402,13 @@ static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs
     return true;
 }
 
+bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k, int64_t n, int64_t batch) {
+    return encode_fn() != nullptr && ld % 2 == 0 && ((uintptr_t)X & 15) == 0 && !(batch > 1 && (bstride % 2 != 0 || bstride == 0)) && k > 0 && n > 0;
+}
+
 bool launch_gram_syrk_tma(const GramArgs& g, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
     return launch_tma_impl(true, g.X, g.ldx, g.x_bstride, g.X, g.ldx, g.x_bstride, g.k, g.n, g.n, g.H, g.ldh, g.h_bstride, g.map, g.scale,
-                           g.accumulate, sc, batch, sm_count, stream);
+                           g.accumulate, sc, batch, sm_count, stream, g.gate, g.gate_cols);
 }
 
 bool launch_gemm_tn_tma(const GemmTNArgs& g, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {

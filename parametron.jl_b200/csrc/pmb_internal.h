@@ -221,7 +221,15 @@ struct pmb_ctx {
     // two-branch update graph: objective chain on the context stream, constraint chain on an auxiliary stream
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork0 = nullptr, ev_fork1 = nullptr, ev_join = nullptr;
-    bool h2d_in_graph = false;           // HOST Parameters are copied by memcpy nodes of the graph (pinned, pointer fixed at initialize)
+    bool h2d_in_graph = false;
+    // upload/compute overlap of the objective's Gram operand (a pinned HOST Parameter used by nothing else): the matrix travels in
+    // column chunks on its own stream while the flag-gated Gram kernel already consumes the chunks that have landed
+    int pipe_param = -1;
+    int32_t* pipe_gate = nullptr;        // device flags, one per chunk
+    int32_t* pipe_ones = nullptr;        // pinned host array of ones (source of the flag copies)
+    int32_t pipe_chunks = 0, pipe_gate_cols = 0;
+    cudaStream_t h2d_stream = nullptr;
+    cudaEvent_t ev_h2d_done = nullptr, ev_aux_h2d = nullptr, ev_aux_kernels = nullptr;           // HOST Parameters are copied by memcpy nodes of the graph (pinned, pointer fixed at initialize)
     // host sinks of the packed QP (pmb_qp_set_host_sink): D2H memcpy nodes at the end of each branch
     double *sink_Px = nullptr, *sink_q = nullptr, *sink_c0 = nullptr, *sink_Ax = nullptr, *sink_l = nullptr, *sink_u = nullptr;
     // solver-side ingest (pmb_enable_qp_pack): packed upper-triangular P, stacked CSC A, row bounds

@@ -90,6 +90,11 @@ struct GramArgs {
     const int32_t* map;    // [n] 0-based output index of source column i; null = identity
     AlphaDev scale;
     int32_t accumulate;    // 0: overwrite, 1: +=
+    // Arrival gating (upload/compute overlap): X is being copied host->device in chunks of `gate_cols` columns while the kernel
+    // runs; gate[c] becomes non-zero (written by a stream-ordered copy AFTER chunk c) when columns [c*gate_cols, (c+1)*gate_cols)
+    // have landed.  Tiles are enumerated column-major, so early tiles only need early chunks.  null = no gating.
+    const int32_t* gate;
+    int32_t gate_cols;
 };
 void launch_gram_syrk(const GramArgs& a, int64_t batch, int sm_count, cudaStream_t stream);
 // general TN product  M (n x p, ld) = X' * Y  (scratch for dot(f, h) with f != h and for A * Vector{AffineFunction})
@@ -117,6 +122,7 @@ struct GramScratch {
 bool launch_gram_syrk_tma(const GramArgs& a, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
 bool launch_gemm_tn_tma(const GemmTNArgs& a, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
 void configure_gram_tma_kernels();
+bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k, int64_t n, int64_t batch);
 
 // ---------------- small kernels ---------------------------------------------------------------
 void launch_tick(unsigned long long* counter, cudaStream_t stream);

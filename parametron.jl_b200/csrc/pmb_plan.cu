@@ -322,6 +322,7 @@ struct DenseSide {
     int64_t gbs = 0;
     double cx = 1.0;
     double cg = 1.0;            // the offsets are cg * g[...]
+    int whole_node = -1;        // X is exactly this (whole) matrix node, read in place
 };
 
 static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps, int64_t nb) {
@@ -345,6 +346,7 @@ static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps,
         const MatTerm& m = f.mats[0];
         const Node& sn = c->nodes[m.mat];
         s.X = sn.dptr + m.src_col_off * sn.rows; s.ldx = sn.rows; s.xbs = sn.bstride; s.ncols = m.cols; s.cx = m.a.c;
+        if (m.src_col_off == 0 && m.cols == sn.cols && sn.bsr_b == 0) s.whole_node = m.mat;
         s.map = upload(c, map);
         if (has_off && g_direct) {
             const Node& gn = c->nodes[f.offs[0].vec];
@@ -387,7 +389,9 @@ struct QuadTarget {
     double* q = nullptr;
     double* c0 = nullptr;
 };
-static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool want_Q) {
+static int count_refs(pmb_ctx* c, int id);
+
+static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool want_Q, bool is_objective = false) {
     const int64_t N = c->nvars, nb = c->batch;
     QuadTarget T;
     double* qc = dalloc<double>(c, nb * (N + 1), true);
@@ -426,6 +430,25 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
             ga.X = F.X; ga.ldx = F.ldx; ga.x_bstride = F.xbs; ga.k = F.k; ga.n = F.ncols;
             ga.H = T.Q; ga.ldh = N; ga.h_bstride = N * N; ga.map = F.map;
             ga.scale = scaled(a, 2.0 * F.cx * F.cx); ga.accumulate = overwrite ? 0 : 1;
+            // upload/compute overlap: the operand is a pinned HOST Parameter nothing else reads -> gate the kernel on chunk arrival
+            if (is_objective && overwrite && c->h2d_in_graph && nb == 1 && F.whole_node >= 0 && c->pipe_param < 0 && c->use_tma &&
+                !getenv("PMB_NO_PIPE")) {
+                const Node& pn = c->nodes[(size_t)F.whole_node];
+                const int64_t tile_cols = (F.ncols + 127) / 128;
+                if (pn.nop == NOP_PARAM && pn.pmode == PMB_PARAM_HOST && tile_cols >= 8 && count_refs(c, F.whole_node) == 1 &&
+                    gram_tma_applicable(F.X, F.ldx, F.xbs, F.k, F.ncols, nb)) {
+                    c->pipe_param = F.whole_node;
+                    c->pipe_gate_cols = (int32_t)(((tile_cols + 7) / 8) * 128);       // 8 chunks of whole 128-column panels
+                    c->pipe_chunks = (int32_t)((F.ncols + c->pipe_gate_cols - 1) / c->pipe_gate_cols);
+                    c->pipe_gate = dalloc<int32_t>(c, c->pipe_chunks, true);
+                    void* hp = nullptr;
+                    CK(cudaHostAlloc(&hp, sizeof(int32_t) * (size_t)c->pipe_chunks, cudaHostAllocDefault));
+                    c->pinned.push_back(hp);
+                    c->pipe_ones = (int32_t*)hp;
+                    for (int q = 0; q < c->pipe_chunks; ++q) c->pipe_ones[q] = 1;
+                    ga.gate = c->pipe_gate; ga.gate_cols = c->pipe_gate_cols;
+                }
+            }
             s.gram = ga;
             s.gscratch = make_gram_scratch(c, true, ga.k, ga.n, ga.n, nb);
             st.push_back(s);
@@ -525,8 +548,36 @@ static void plan_objective(pmb_ctx* c) {
         c->q = qc; c->c0 = qc + c->batch * c->nvars;
         return;
     }
-    QuadTarget T = plan_quadratic(c, quad_of(c, c->obj_node), c->obj_const, c->obj_kind == PMB_KIND_QUAD);
+    QuadTarget T = plan_quadratic(c, quad_of(c, c->obj_node), c->obj_const, c->obj_kind == PMB_KIND_QUAD, true);
     c->Q = T.Q; c->q = T.q; c->c0 = T.c0;
+}
+
+// how many places read numeric node `id` (other numeric nodes, the objective, every constraint form)
+static int count_refs_aff(const AffForm& f, int id) {
+    int n = 0;
+    for (auto& t : f.mats) n += (t.mat == id) + (t.a.node == id);
+    for (auto& t : f.units) n += (t.a.node == id);
+    for (auto& t : f.offs) n += (t.vec == id) + (t.a.node == id);
+    for (auto& t : f.sps) n += (t.mat == id) + (t.a.node == id);
+    return n;
+}
+static int count_refs_quad(const QuadForm& q, int id) {
+    int n = count_refs_aff(q.aff, id);
+    for (auto& g : q.grams) n += (g.a.node == id) + count_refs_aff(g.f, id) + (g.same ? 0 : count_refs_aff(g.h, id));
+    for (auto& b : q.bilins) n += (b.mat == id) + (b.a.node == id);
+    for (auto& t : q.coos) n += (t.a.node == id);
+    return n;
+}
+static int count_refs(pmb_ctx* c, int id) {
+    int n = 0;
+    for (auto& nd : c->nodes) {
+        if (!nd.needed) continue;
+        for (int in : nd.in) n += (in == id);
+        for (auto& t : nd.lin) n += (t.src == id) + (t.a.node == id);
+    }
+    if (c->obj_node >= 0) n += count_refs_quad(quad_of(c, c->obj_node), id);
+    for (auto& con : c->cons) n += con.is_quad ? count_refs_quad(*con.quad, id) : count_refs_aff(con.form, id);
+    return n;
 }
 
 // ---- run ---------------------------------------------------------------------------------------
@@ -584,13 +635,6 @@ void build_update_graph(pmb_ctx* ctx) {
     const int64_t N = ctx->nvars;
     if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
     if (ctx->graph) { cudaGraphDestroy(ctx->graph); ctx->graph = nullptr; }
-    // HOST Parameters can live inside the graph (memcpy nodes) when their buffers are pinned and fixed from here on
-    ctx->h2d_in_graph = ctx->use_graph;
-    for (auto& n : ctx->nodes) {
-        if (!n.needed || n.nop != NOP_PARAM || n.pmode != PMB_PARAM_HOST) continue;
-        unsigned int flags = 0;
-        if (!n.hptr || cudaHostGetFlags(&flags, n.hptr) != cudaSuccess) { ctx->h2d_in_graph = false; (void)cudaGetLastError(); }
-    }
     if (ctx->use_graph && !ctx->steps.empty()) {
         if (!ctx->aux_stream) {
             CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
@@ -608,7 +652,9 @@ void build_update_graph(pmb_ctx* ctx) {
             };
             auto h2d = [&](bool main_branch, cudaStream_t on) {
                 if (!ctx->h2d_in_graph) return;
-                for (auto& n : ctx->nodes) {
+                for (size_t ni = 0; ni < ctx->nodes.size(); ++ni) {
+                    Node& n = ctx->nodes[ni];
+                    if ((int)ni == ctx->pipe_param) continue;  // travels in chunks on its own stream (below)
                     if (!n.needed || n.nop != NOP_PARAM || n.pmode != PMB_PARAM_HOST || n.used_main != main_branch) continue;
                     CK(cudaMemcpyAsync(n.dptr, n.hptr, (size_t)(ctx->batch * n.numel) * sizeof(double), cudaMemcpyHostToDevice, on));
                 }
@@ -618,14 +664,40 @@ void build_update_graph(pmb_ctx* ctx) {
             };
             const int64_t nb = ctx->batch;
             run_phase(0, main_s);                                        // prologue: generators, zeroing, tick
+            const bool pipe = ctx->pipe_param >= 0 && ctx->h2d_in_graph;
+            if (pipe) CK(cudaMemsetAsync(ctx->pipe_gate, 0, sizeof(int32_t) * (size_t)ctx->pipe_chunks, main_s));
             CK(cudaEventRecord(ctx->ev_fork0, main_s));
             CK(cudaStreamWaitEvent(aux_s, ctx->ev_fork0, 0));
             h2d(false, aux_s);                                           // constraint-only Parameters travel on the aux branch
+            if (pipe) {
+                // the Gram operand: column chunks, each followed by its arrival flag, on a dedicated copy stream -- queued behind the
+                // (small) constraint Parameters so that the constraint chain can run and leave before the Gram takes every SM
+                if (!ctx->h2d_stream) {
+                    CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+                    CK(cudaEventCreateWithFlags(&ctx->ev_h2d_done, cudaEventDisableTiming));
+                    CK(cudaEventCreateWithFlags(&ctx->ev_aux_h2d, cudaEventDisableTiming));
+                    CK(cudaEventCreateWithFlags(&ctx->ev_aux_kernels, cudaEventDisableTiming));
+                }
+                CK(cudaEventRecord(ctx->ev_aux_h2d, aux_s));
+                CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_aux_h2d, 0));
+                const Node& pn = ctx->nodes[(size_t)ctx->pipe_param];
+                for (int q = 0; q < ctx->pipe_chunks; ++q) {
+                    const int64_t c0 = (int64_t)q * ctx->pipe_gate_cols, c1 = std::min<int64_t>(pn.cols, c0 + ctx->pipe_gate_cols);
+                    CK(cudaMemcpyAsync(pn.dptr + c0 * pn.rows, pn.hptr + c0 * pn.rows, (size_t)((c1 - c0) * pn.rows) * sizeof(double),
+                                       cudaMemcpyHostToDevice, ctx->h2d_stream));
+                    CK(cudaMemcpyAsync(ctx->pipe_gate + q, ctx->pipe_ones + q, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->h2d_stream));
+                }
+                CK(cudaEventRecord(ctx->ev_h2d_done, ctx->h2d_stream));
+            }
             h2d(true, main_s);
             run_phase(1, main_s);                                        // derived numeric nodes (shared by both chains)
             CK(cudaEventRecord(ctx->ev_fork1, main_s));
             CK(cudaStreamWaitEvent(aux_s, ctx->ev_fork1, 0));
             run_phase(3, aux_s);                                         // constraint blocks (+ stacked-A pack)
+            if (pipe) {  // the persistent Gram holds every SM until the upload is over: let the constraint kernels go first
+                CK(cudaEventRecord(ctx->ev_aux_kernels, aux_s));
+                CK(cudaStreamWaitEvent(main_s, ctx->ev_aux_kernels, 0));
+            }
             sink(ctx->sink_Ax, ctx->qp_Ax, nb * ctx->qp_nnzA, aux_s);
             sink(ctx->sink_l, ctx->qp_l, nb * ctx->qp_m, aux_s);
             sink(ctx->sink_u, ctx->qp_u, nb * ctx->qp_m, aux_s);
@@ -635,6 +707,7 @@ void build_update_graph(pmb_ctx* ctx) {
             sink(ctx->sink_q, ctx->q, nb * N, main_s);
             sink(ctx->sink_c0, ctx->c0, nb, main_s);
             CK(cudaStreamWaitEvent(main_s, ctx->ev_join, 0));
+            if (pipe) CK(cudaStreamWaitEvent(main_s, ctx->ev_h2d_done, 0));
         } catch (...) {
             ctx->stream = main_s;
             cudaGraph_t g = nullptr;
@@ -701,6 +774,10 @@ int pmb_ctx_destroy(pmb_ctx* c) {
     if (c->ev_fork1) cudaEventDestroy(c->ev_fork1);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->ev_h2d_done) cudaEventDestroy(c->ev_h2d_done);
+    if (c->ev_aux_h2d) cudaEventDestroy(c->ev_aux_h2d);
+    if (c->ev_aux_kernels) cudaEventDestroy(c->ev_aux_kernels);
     for (void* p : c->allocs) cudaFree(p);
     for (void* p : c->pinned) cudaFreeHost(p);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -742,6 +819,13 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
     ctx->d_counter = (unsigned long long*)dalloc<unsigned long long>(ctx, 1, true);
     (void)any_uniform;
     ctx->d_ticket = (unsigned int*)dalloc<unsigned int>(ctx, 1, true);
+    // HOST Parameters can live inside the graph (memcpy nodes) when their buffers are pinned and fixed from here on
+    ctx->h2d_in_graph = ctx->use_graph;
+    for (auto& n : ctx->nodes) {
+        if (!n.needed || n.nop != NOP_PARAM || n.pmode != PMB_PARAM_HOST) continue;
+        unsigned int flags = 0;
+        if (!n.hptr || cudaHostGetFlags(&flags, n.hptr) != cudaSuccess) { ctx->h2d_in_graph = false; (void)cudaGetLastError(); }
+    }
     const size_t nn = ctx->nodes.size();
     size_t tagged = 0;
     auto tag_phase = [&](int ph) {
@@ -826,6 +910,8 @@ int pmb_update(pmb_ctx* ctx) {
         if (!(graph_path && ctx->h2d_in_graph))
             CK(cudaMemcpyAsync(n.dptr, n.hptr, (size_t)(ctx->batch * n.numel) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (!(graph_path && ctx->h2d_in_graph) && ctx->pipe_param >= 0)  // eager paths upload everything up front: open every gate
+        CK(cudaMemcpyAsync(ctx->pipe_gate, ctx->pipe_ones, sizeof(int32_t) * (size_t)ctx->pipe_chunks, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->timing) {
         collect_timing(ctx);
         for (size_t i = 0; i < ctx->steps.size(); ++i) {

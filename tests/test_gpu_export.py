@@ -168,3 +168,35 @@ def test_qp_host_sink_filled_by_the_update_graph():
         assert_close(sink["P_x"][0], np.concatenate([Qo[:j + 1, j] for j in range(n)]), 1e-10, "P_x")
         assert np.array_equal(sink["A_x"][0], P["C"].val.T.ravel())
         assert np.all(np.isneginf(sink["l"][0])) and np.array_equal(sink["u"][0], P["d"].val)
+
+
+@pytest.mark.parametrize("n,k", [(1024, 192), (1152, 130)])
+def test_upload_compute_overlap_gated_gram(n, k):
+    """n >= 1024 (8 tile columns) with a pinned HOST matrix used only by the objective: the matrix is uploaded in column chunks
+    while the flag-gated Gram kernel consumes them (pmb_plan.cu build_update_graph).  Results must not depend on the overlap."""
+    import parametron_b200 as pm
+    m = 16
+    rng = np.random.default_rng(n + k)
+    vals = {"A": rng.standard_normal((k, n)), "b": rng.standard_normal(k), "C": rng.standard_normal((m, n)), "d": rng.standard_normal(m)}
+    model = pm.Model()
+    x = model.variables(n)
+    P = {key: pm.Parameter(model, val=v) for key, v in vals.items()}
+    r = P["A"] * x - P["b"]
+    pm.objective(model, pm.Minimize, pm.dot(r, r))
+    pm.constraint(model, P["C"] * x, "==", P["d"])
+    model.enable_qp_pack()
+    model.initialize()
+    sink = model.qp_host_sink()
+    for step in range(4):
+        for key in vals:
+            P[key].val = rng.standard_normal(vals[key].shape)
+        model.update()
+        model.synchronize()
+        A, b = P["A"].val, P["b"].val
+        Q, q, c0 = model.objective_arrays()
+        assert_close(Q, 2 * A.T @ A, 1e-10, "Q"); assert_close(q, -2 * A.T @ b, 1e-10, "q"); assert_close([c0], [b @ b], 1e-10, "c0")
+        assert np.array_equal(Q, Q.T)
+        iu = np.triu_indices(n)
+        assert np.array_equal(sink["P_x"][0], Q.T[iu[1], iu[0]][np.lexsort((iu[0], iu[1]))]) or \
+            np.array_equal(sink["P_x"][0], np.concatenate([Q[:j + 1, j] for j in range(n)]))
+        assert np.array_equal(sink["A_x"][0], P["C"].val.T.ravel())
