@@ -43,6 +43,9 @@ struct GramTmaKernelArgs {
     int32_t nslices;
     const int32_t* gate;  // see GramArgs::gate
     int32_t gate_cols;
+    double* packed_dev;   // see GramArgs::packed_*
+    double* packed_host;
+    int64_t packed_bstride;
     int32_t* counters;    // [total_tiles - full_tiles] arrival counters, zero between launches
     double* workspace;    // [(total_tiles - full_tiles) * nslices][64][256] partial accumulators
     int64_t total_units;
@@ -123,9 +126,11 @@ __device__ __forceinline__ Unit decode_unit(const GramTmaKernelArgs& a, int64_t 
     return w;
 }
 
-template <bool SYRK, bool ADD, int BM>
+template <bool SYRK, bool ADD, int BM, bool PACKED>
 __device__ __forceinline__ void store_tile(const GramTmaKernelArgs& a, double (&acc)[BM / 32][BM / 32][4], double* out, double sc, int64_t i0,
-                                           int64_t j0, bool diag, int wm, int wn, int pg, int t) {
+                                           int64_t j0, bool diag, int wm, int wn, int pg, int t, int64_t inst) {
+    double* pk_dev = (PACKED && a.packed_dev) ? a.packed_dev + inst * a.packed_bstride : nullptr;
+    double* pk_host = (PACKED && a.packed_host) ? a.packed_host + inst * a.packed_bstride : nullptr;
 #pragma unroll
     for (int mi = 0; mi < BM / 32; ++mi) {
 #pragma unroll
@@ -141,6 +146,12 @@ __device__ __forceinline__ void store_tile(const GramTmaKernelArgs& a, double (&
                         const int64_t om = a.map ? a.map[m] : m, on = a.map ? a.map[nn] : nn;
                         double* p1 = out + om + on * a.ldo;
                         *p1 = ADD ? *p1 + v : v;
+                        if (PACKED && (!diag || m <= nn)) {  // each unordered pair exactly once
+                            const int64_t lo = om < on ? om : on, hi = om < on ? on : om;
+                            const int64_t idx = hi * (hi + 1) / 2 + lo;
+                            if (pk_dev) pk_dev[idx] = v;
+                            if (pk_host) __stcs(pk_host + idx, v);
+                        }
                         if (!diag) {
                             double* p2 = out + on + om * a.ldo;
                             *p2 = ADD ? *p2 + v : v;
@@ -293,8 +304,9 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
         const double sc = a.scale.ptr ? a.scale.c * a.scale.ptr[w.inst * a.scale.bstride] : a.scale.c;
         double* out = a.out + w.inst * a.o_bstride;
         const int64_t i0 = (int64_t)w.ti * BM, j0 = (int64_t)w.tj * BM;
-        if (a.accumulate) store_tile<SYRK, true, BM>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t);
-        else store_tile<SYRK, false, BM>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t);
+        if (a.accumulate) store_tile<SYRK, true, BM, false>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t, w.inst);
+        else if (SYRK && (a.packed_dev || a.packed_host)) store_tile<SYRK, false, BM, true>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t, w.inst);
+        else store_tile<SYRK, false, BM, false>(a, acc, out, sc, i0, j0, diag, wm, wn, pg, t, w.inst);
     }
 }
 
@@ -371,7 +383,7 @@ GramSplitPlan plan_gram_split(bool syrk, int64_t k, int64_t n, int64_t p, int64_
 static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs, const double* Y, int64_t ldy, int64_t ybs, int64_t k,
                             int64_t n, int64_t p, double* out, int64_t ldo, int64_t obs, const int32_t* map, AlphaDev scale, int accumulate,
                             const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream, const int32_t* gate = nullptr,
-                            int32_t gate_cols = 0) {
+                            int32_t gate_cols = 0, double* packed_dev = nullptr, double* packed_host = nullptr, int64_t packed_bstride = 0) {
     if (batch > 1 && (xbs == 0 || ybs == 0)) return false;
     GramTmaKernelArgs a{};
     const int bm = sc.plan.bm == 64 ? 64 : kTBM;
@@ -390,6 +402,7 @@ static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs
     a.counters = sc.counters;
     a.workspace = sc.workspace;
     a.gate = gate; a.gate_cols = gate_cols;
+    a.packed_dev = packed_dev; a.packed_host = packed_host; a.packed_bstride = packed_bstride;
     a.total_units = a.full_tiles + (a.total_tiles - a.full_tiles) * a.nslices;
     const int grid = (int)(a.total_units < sm_count ? a.total_units : sm_count);
     if (bm == 64) {
@@ -408,7 +421,8 @@ bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k
 
 bool launch_gram_syrk_tma(const GramArgs& g, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
     return launch_tma_impl(true, g.X, g.ldx, g.x_bstride, g.X, g.ldx, g.x_bstride, g.k, g.n, g.n, g.H, g.ldh, g.h_bstride, g.map, g.scale,
-                           g.accumulate, sc, batch, sm_count, stream, g.gate, g.gate_cols);
+                           g.accumulate, sc, batch, sm_count, stream, g.gate, g.gate_cols, g.accumulate ? nullptr : g.packed_dev,
+                           g.accumulate ? nullptr : g.packed_host, g.packed_bstride);
 }
 
 bool launch_gemm_tn_tma(const GemmTNArgs& g, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {

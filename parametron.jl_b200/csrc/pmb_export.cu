@@ -3,6 +3,8 @@
 //   pmb_enable_qp_pack / pmb_get_qp -- value-only updates of an OSQP-style (P upper CSC, q, A CSC, l, u), replacing the
 //                                      MOI.set sink (moi_interop.jl:134,171)
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <limits>
 
 #include "pmb_host.h"
@@ -24,10 +26,27 @@ void plan_qp_pack(pmb_ctx* c) {
         c->qp_Pp = upload(c, Pp);
         c->qp_Pi = upload(c, Pi);
         c->qp_Px = dalloc<double>(c, nb * c->qp_nnzP, true);
-        Step s;
-        s.type = ST_PACK_P; s.cls = KC_PACK; s.batch = nb;
-        s.src = c->Q; s.n = N; s.src_bstride = N * N; s.out = c->qp_Px; s.out_bstride = c->qp_nnzP;
-        (c->obj_const ? c->init_steps : c->steps).push_back(s);
+        // If the Hessian is produced by ONE overwriting TMA Gram launch, its epilogue writes the packed upper triangle itself: no pack
+        // launch.  (Writing the host sink from the epilogue as well -- posted PCIe writes of 64-byte segments -- was measured and
+        // rejected: e2e 5.71 -> 6.93 ms at cfg2; the sink stays a D2H copy node.)
+        Step* gram = nullptr;
+        int ngram_like = 0;
+        for (auto& st : c->steps) {
+            if (st.type == ST_GRAM && st.gram.H == c->Q) { gram = &st; ++ngram_like; }
+            if ((st.type == ST_BILINEAR && st.bl.H == c->Q) || (st.type == ST_COO && st.coo.H == c->Q) || (st.type == ST_SCATTER_SYM && st.ss.H == c->Q))
+                ++ngram_like;
+        }
+        if (!c->obj_const && ngram_like == 1 && gram && gram->gram.accumulate == 0 && c->use_tma && !getenv("PMB_NO_FUSED_PACK") &&
+            gram_tma_applicable(gram->gram.X, gram->gram.ldx, gram->gram.x_bstride, gram->gram.k, gram->gram.n, nb)) {
+            gram->gram.packed_dev = c->qp_Px;
+            gram->gram.packed_bstride = c->qp_nnzP;
+            c->qp_P_fused = true;
+        } else {
+            Step s;
+            s.type = ST_PACK_P; s.cls = KC_PACK; s.batch = nb;
+            s.src = c->Q; s.n = N; s.src_bstride = N * N; s.out = c->qp_Px; s.out_bstride = c->qp_nnzP;
+            (c->obj_const ? c->init_steps : c->steps).push_back(s);
+        }
     } else {
         c->qp_Pp = upload(c, std::vector<int64_t>((size_t)N + 1, 0));
     }

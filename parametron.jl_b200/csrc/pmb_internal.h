@@ -234,6 +234,7 @@ struct pmb_ctx {
     double *sink_Px = nullptr, *sink_q = nullptr, *sink_c0 = nullptr, *sink_Ax = nullptr, *sink_l = nullptr, *sink_u = nullptr;
     // solver-side ingest (pmb_enable_qp_pack): packed upper-triangular P, stacked CSC A, row bounds
     bool qp_pack = false;
+    bool qp_P_fused = false;   // P_x is written by the Gram epilogue (no pack launch; host sink written directly)
     int64_t qp_m = 0, qp_nnzP = 0, qp_nnzA = 0;
     double *qp_Px = nullptr, *qp_Ax = nullptr, *qp_l = nullptr, *qp_u = nullptr;
     int64_t *qp_Pp = nullptr, *qp_Pi = nullptr, *qp_Ap = nullptr, *qp_Ai = nullptr;

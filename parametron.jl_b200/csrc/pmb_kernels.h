@@ -95,6 +95,12 @@ struct GramArgs {
     // have landed.  Tiles are enumerated column-major, so early tiles only need early chunks.  null = no gating.
     const int32_t* gate;
     int32_t gate_cols;
+    // Fused solver-side ingest: besides H, the epilogue writes the UPPER triangle in packed CSC order (column j holds rows 0..j,
+    // P_x[j(j+1)/2 + i]) to a device buffer (packed_host: same, to mapped pinned host memory -- kept for experiments, measured
+    // slower than a D2H copy).  Only legal when this launch is the only writer of H (accumulate == 0).  null = off.
+    double* packed_dev;
+    double* packed_host;
+    int64_t packed_bstride;
 };
 void launch_gram_syrk(const GramArgs& a, int64_t batch, int sm_count, cudaStream_t stream);
 // general TN product  M (n x p, ld) = X' * Y  (scratch for dot(f, h) with f != h and for A * Vector{AffineFunction})
