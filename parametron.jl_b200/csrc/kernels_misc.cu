@@ -29,10 +29,6 @@ __device__ __forceinline__ double block_sum_256(double v) {
     return r;
 }
 
-// ---------------- update counter -------------------------------------------------------------
-__global__ void tick_kernel(unsigned long long* c) { *c += 1ULL; }
-void launch_tick(unsigned long long* counter, cudaStream_t stream) { tick_kernel<<<1, 1, 0, stream>>>(counter); }
-
 // ---------------- Philox4x32-10 ----------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -43,39 +39,6 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
         c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-}
-
-__global__ void __launch_bounds__(256) philox_uniform_kernel(double* out, int64_t numel, int64_t batch, uint64_t seed, double scale,
-                                                             const unsigned long long* update_counter) {
-    const uint32_t upd = (uint32_t)(*update_counter);
-    const int64_t pairs = (numel + 1) / 2;
-    const bool vec_ok = (numel % 2 == 0) && (((uintptr_t)out & 15) == 0);
-    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
-        double* o = out + inst * numel;
-        for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * blockDim.x) {
-            uint32_t c[4] = {(uint32_t)p, (uint32_t)((uint64_t)p >> 32), (uint32_t)inst, upd};
-            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-            double d0 = (double)((((uint64_t)c[1] << 32) | c[0]) >> 11) * (1.0 / 9007199254740992.0) * scale;
-            double d1 = (double)((((uint64_t)c[3] << 32) | c[2]) >> 11) * (1.0 / 9007199254740992.0) * scale;
-            if (vec_ok) {
-                *reinterpret_cast<double2*>(o + 2 * p) = make_double2(d0, d1);
-            } else {
-                o[2 * p] = d0;
-                if (2 * p + 1 < numel) o[2 * p + 1] = d1;
-            }
-        }
-    }
-}
-void launch_philox_uniform(double* out, int64_t numel, int64_t batch, uint64_t seed, double scale,
-                           const unsigned long long* update_counter, int sm_count, cudaStream_t stream) {
-    if (numel == 0) return;
-    int64_t pairs = (numel + 1) / 2;
-    int64_t bx = (pairs + 255) / 256;
-    int64_t cap = (int64_t)sm_count * 16;
-    if (bx > cap) bx = cap;
-    int64_t by = batch < 65535 ? batch : 65535;
-    if (bx * by > cap * 4 && by > 1) { bx = bx * 1; }
-    philox_uniform_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(out, numel, batch, seed, scale, update_counter);
 }
 
 // ---------------- fused prologue: every built-in Parameter generator + the zeroing of (q, c0) + the update tick -------------

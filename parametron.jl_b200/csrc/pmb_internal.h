@@ -131,7 +131,7 @@ struct Node {
 enum KernelClass { KC_AFFINE = 0, KC_GRAM, KC_GEMM, KC_PHILOX, KC_H2D, KC_REDUCE, KC_MISC, KC_PACK, KC_COUNT };
 
 enum StepType {
-    ST_TICK, ST_PHILOX, ST_H2D, ST_MEMSET, ST_LINCOMB, ST_TRANSPOSE, ST_GEMV, ST_DOT, ST_SPROD, ST_AFFINE, ST_GRAM, ST_GEMM,
+    ST_MEMSET, ST_LINCOMB, ST_TRANSPOSE, ST_GEMV, ST_DOT, ST_SPROD, ST_AFFINE, ST_GRAM, ST_GEMM,
     ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM, ST_PROLOGUE, ST_GEMV_DOT, ST_PACK_P, ST_PACK_A
 };
 

@@ -131,7 +131,6 @@ void configure_gram_tma_kernels();
 bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k, int64_t n, int64_t batch);
 
 // ---------------- small kernels ---------------------------------------------------------------
-void launch_tick(unsigned long long* counter, cudaStream_t stream);
 // fused prologue of one update: all built-in Parameter generators (kind 0: Philox uniform fill, per instance) + zero fills
 // (kind 1: numel doubles in total) + the update-counter tick (published by the last block to finish)
 struct FillJob {
@@ -144,9 +143,6 @@ struct FillJob {
 };
 void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, unsigned long long* counter, unsigned int* ticket,
                      cudaStream_t stream);
-// Philox4x32-10 uniform fill: out[b*numel + e] = scale * U[0,1), counter = (pair index, instance, update counter), key = seed
-void launch_philox_uniform(double* out, int64_t numel, int64_t batch, uint64_t seed, double scale,
-                           const unsigned long long* update_counter, int sm_count, cudaStream_t stream);
 // out[i] = cst[i] + sum_t alpha_t * src_t[off_t + i]
 struct LinCombTermDev { const double* src; int64_t src_bstride; int64_t src_off; AlphaDev alpha; };
 void launch_lincomb(double* out, int64_t out_bstride, int64_t n, const LinCombTermDev* terms, int nterms,

@@ -584,7 +584,6 @@ static int count_refs(pmb_ctx* c, int id) {
 static void run_step(pmb_ctx* c, const Step& s) {
     cudaStream_t st = c->stream;
     switch (s.type) {
-        case ST_TICK: launch_tick(c->d_counter, st); break;
         case ST_PROLOGUE: launch_prologue(s.jobs, s.njobs, s.job_blocks, s.batch, c->d_counter, c->d_ticket, st); break;
         case ST_GEMV_DOT: launch_gemv_t_dot(s.gemv, s.dot, s.batch, st); break;
         case ST_PACK_P: launch_pack_upper(s.src, s.n, s.src_bstride, s.out, s.out_bstride, s.batch, st); break;
@@ -592,7 +591,6 @@ static void run_step(pmb_ctx* c, const Step& s) {
             launch_pack_constraints(c->qp_blocks_dev, (int)c->cons.size(), c->nvars, c->qp_Ax, c->qp_nnzA, c->qp_l, c->qp_u, c->qp_m, s.batch,
                                     c->sm_count, st);
             break;
-        case ST_PHILOX: launch_philox_uniform(s.out, s.n, s.batch, s.seed, s.scale, c->d_counter, c->sm_count, st); break;
         case ST_MEMSET: CK(cudaMemsetAsync(s.out, 0, (size_t)s.n * sizeof(double), st)); break;
         case ST_LINCOMB: launch_lincomb(s.out, s.out_bstride, s.n, s.lterms, s.nl, s.cst, s.batch, st); break;
         case ST_TRANSPOSE: launch_transpose(s.out, s.out_bstride, s.src, s.src_bstride, s.n, s.n2, s.batch, st); break;
@@ -814,10 +812,7 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
         if (con.is_quad) mark_quad(ctx, *con.quad);
         else mark_aff(ctx, con.form);
     }
-    bool any_uniform = false;
-    for (auto& n : ctx->nodes) any_uniform = any_uniform || (n.needed && n.nop == NOP_PARAM && n.pmode == PMB_PARAM_UNIFORM);
     ctx->d_counter = (unsigned long long*)dalloc<unsigned long long>(ctx, 1, true);
-    (void)any_uniform;
     ctx->d_ticket = (unsigned int*)dalloc<unsigned int>(ctx, 1, true);
     // HOST Parameters can live inside the graph (memcpy nodes) when their buffers are pinned and fixed from here on
     ctx->h2d_in_graph = ctx->use_graph;
