@@ -28,7 +28,7 @@ constexpr int kTKT = 16;
 constexpr int kTStages = 6;
 constexpr int kTConsumerWarps = 8;
 constexpr int kTThreads = (kTConsumerWarps + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup (setmaxnreg is per warpgroup)
-constexpr int kTSmemBytes = kTStages * 2 * kTBM * kTKT * 8 + 1024;  // 192 KB + slack to align the ring to the 1 KB swizzle period
+constexpr int kTSmemBytes = kTStages * 2 * kTBM * kTKT * 8 + 1024 + kTStages * 128;  // 192 KB ring + 1 KB alignment slack + g slots
 
 struct GramTmaKernelArgs {
     CUtensorMap tmx, tmy;
@@ -46,6 +46,11 @@ struct GramTmaKernelArgs {
     double* packed_dev;   // see GramArgs::packed_*
     double* packed_host;
     int64_t packed_bstride;
+    const double* gvec; int64_t g_bstride;   // see GramArgs::gvec (fused q / c0)
+    double* qout; int64_t q_bstride;
+    double* c0out;
+    AlphaDev qscale, cscale;
+    double* qworkspace;
     int32_t* counters;    // [total_tiles - full_tiles] arrival counters, zero between launches
     double* workspace;    // [(total_tiles - full_tiles) * nslices][64][256] partial accumulators
     int64_t total_units;
@@ -76,6 +81,11 @@ __device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_dst),
                  "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(s_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gmem_src),
+                 "r"(bytes), "r"(s_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
@@ -166,7 +176,7 @@ __device__ __forceinline__ void store_tile(const GramTmaKernelArgs& a, double (&
     }
 }
 
-template <bool SYRK, int BM>
+template <bool SYRK, int BM, bool FUSEQ>
 __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_constant__ GramTmaKernelArgs a) {
     constexpr int MI = BM / 32, NI = BM / 32;      // warp tile (BM/2) x (BM/4) = MI x NI fragments of 16 x 8
     constexpr int kPanelBytes = BM * kTKT * 8;     // one operand panel of one stage: BM columns x 128 bytes
@@ -174,8 +184,11 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
     __shared__ __align__(8) uint64_t full_bar[kTStages];
     __shared__ __align__(8) uint64_t empty_bar[kTStages];
     __shared__ int arrival_flag;
+    __shared__ double qred[kTConsumerWarps * 32 + 8];   // fused q / c0 partial sums of one unit
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ring = (s_u32(smem_raw) + 1023u) & ~1023u;  // the 128-byte swizzle pattern repeats every 1024 bytes
+    const uint32_t gring = ring + (uint32_t)kTStages * 2 * kTBM * kTKT * 8;  // 128-byte slots: 16 entries of gvec per stage
+    constexpr bool fuse_q = SYRK && FUSEQ;  // compiled out of the large-problem instantiations: it costs MMA-loop scheduling freedom
 
     if (tid == 0) {
 #pragma unroll
@@ -207,7 +220,10 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
                     const int s = it % kTStages;
                     mb_wait(&empty_bar[s], ((it / kTStages) & 1) ^ 1);
                     const uint32_t stage = ring + (uint32_t)s * 2 * kPanelBytes;
-                    mb_expect_tx(&full_bar[s], diag ? kPanelBytes : 2 * kPanelBytes);
+                    const int64_t krem = a.k - (int64_t)kt * kTKT;
+                    const uint32_t gbytes = (diag && fuse_q) ? (uint32_t)((krem < kTKT ? krem : kTKT) * 8) : 0u;
+                    mb_expect_tx(&full_bar[s], (diag ? kPanelBytes : 2 * kPanelBytes) + gbytes);
+                    if (gbytes) bulk_load_1d(gring + (uint32_t)s * 128, a.gvec + w.inst * a.g_bstride + (int64_t)kt * kTKT, gbytes, &full_bar[s]);
                     tma_load_3d(stage, &a.tmx, kt * kTKT, w.ti * BM, (int)w.inst, &full_bar[s]);
                     if (!diag) tma_load_3d(stage + kPanelBytes, &a.tmy, kt * kTKT, w.tj * BM, (int)w.inst, &full_bar[s]);
                 }
@@ -240,9 +256,28 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
 #pragma unroll
                 for (int r = 0; r < 4; ++r) acc[mi][ni][r] = 0.0;
 
+        // fused linear part: thread -> (column qcol of the diagonal tile, k-group qkg)
+        constexpr int KG = (kTConsumerWarps * 32) / BM, KPT = kTKT / KG;
+        const int qcol = tid % BM, qkg = tid / BM;
+        const bool do_q = fuse_q && diag;
+        double qacc = 0.0, cacc = 0.0;
+
         for (int kt = w.kt0; kt < w.kt1; ++kt, ++it) {
             const int s = it % kTStages;
             mb_wait(&full_bar[s], (it / kTStages) & 1);
+            if (do_q) {
+                const uint32_t sX = ring + (uint32_t)s * 2 * kPanelBytes + (uint32_t)qcol * 128;
+                const uint32_t sG = gring + (uint32_t)s * 128;
+#pragma unroll
+                for (int j = 0; j < KPT; ++j) {
+                    const int kk = qkg * KPT + j;
+                    if ((int64_t)kt * kTKT + kk < a.k) {
+                        const double gv = lds_f64(sG + kk * 8);
+                        qacc += lds_f64(sX + ((((kk >> 1) ^ (qcol & 7))) << 4) + (kk & 1) * 8) * gv;
+                        if (qcol == 0) cacc += gv * gv;
+                    }
+                }
+            }
             const uint32_t sA = ring + (uint32_t)s * 2 * kPanelBytes + a_row;
             const uint32_t sB = ring + (uint32_t)s * 2 * kPanelBytes + (diag ? 0u : (uint32_t)kPanelBytes) + b_row;
 #pragma unroll
@@ -262,6 +297,28 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
             }
             __syncwarp();
             if (lane == 0) mb_arrive(&empty_bar[s]);  // this warp is done reading the stage
+        }
+
+        // ---- fused linear part: reduce the k-groups of this unit ----
+        double qv = 0.0, cv = 0.0;
+        if (do_q) {
+            qred[tid] = qacc;
+            if (qcol == 0) qred[kTConsumerWarps * 32 + qkg] = cacc;
+            consumer_bar();
+            if (tid < BM) {
+#pragma unroll
+                for (int gq = 0; gq < KG; ++gq) qv += qred[gq * BM + tid];
+            }
+            if (tid == 0) {
+#pragma unroll
+                for (int gq = 0; gq < KG; ++gq) cv += qred[kTConsumerWarps * 32 + gq];
+            }
+            consumer_bar();  // qred is reused by the next unit
+            if (w.nslices > 1) {
+                double* qw = a.qworkspace + (w.split_id * w.nslices + w.slice) * (int64_t)(BM + 1);
+                if (tid < BM) __stcg(qw + tid, qv);
+                if (tid == 0) __stcg(qw + BM, cv);
+            }
         }
 
         // ---- k-slices: park the partial, the last arriver sums all partials of the tile in slice order ----
@@ -290,6 +347,14 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
                 for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
                     for (int r = 0; r < 4; ++r) acc[mi][ni][r] = 0.0;
+            if (do_q) {
+                qv = 0.0; cv = 0.0;
+                const double* qw = a.qworkspace + (w.split_id * w.nslices) * (int64_t)(BM + 1);
+                for (int sl = 0; sl < w.nslices; ++sl, qw += BM + 1) {
+                    if (tid < BM) qv += __ldcg(qw + tid);
+                    if (tid == 0) cv += __ldcg(qw + BM);
+                }
+            }
             const double* wr = a.workspace + (w.split_id * w.nslices * (MI * NI * 4)) * (int64_t)(kTConsumerWarps * 32) + tid;
             for (int sl = 0; sl < w.nslices; ++sl, wr += (MI * NI * 4) * (kTConsumerWarps * 32)) {
 #pragma unroll
@@ -298,6 +363,19 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
                     for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
                         for (int r = 0; r < 4; ++r) acc[mi][ni][r] += __ldcg(wr + ((mi * NI + ni) * 4 + r) * (kTConsumerWarps * 32));
+            }
+        }
+        // ---- fused linear part: one writer per column of q (this diagonal tile), tile (0,0) owns c0 ----
+        if (do_q) {
+            const int64_t col = (int64_t)w.ti * BM + tid;
+            if (tid < BM && col < a.n) {
+                const double qs = a.qscale.ptr ? a.qscale.c * a.qscale.ptr[w.inst * a.qscale.bstride] : a.qscale.c;
+                double* dst = a.qout + w.inst * a.q_bstride + (a.map ? a.map[col] : col);
+                *dst += qs * qv;
+            }
+            if (tid == 0 && w.ti == 0) {
+                const double cs = a.cscale.ptr ? a.cscale.c * a.cscale.ptr[w.inst * a.cscale.bstride] : a.cscale.c;
+                a.c0out[w.inst] += cs * cv;
             }
         }
         // ---- epilogue: scale, (scatter by variable map), both triangles ----
@@ -311,10 +389,11 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
 }
 
 void configure_gram_tma_kernels() {
-    cudaFuncSetAttribute(gram_tma_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
-    cudaFuncSetAttribute(gram_tma_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
-    cudaFuncSetAttribute(gram_tma_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
-    cudaFuncSetAttribute(gram_tma_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<true, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<false, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<true, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<true, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
+    cudaFuncSetAttribute(gram_tma_kernel<false, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes);
 }
 
 // ---- host: tensor maps and the unit decomposition ------------------------------------------------
@@ -383,7 +462,8 @@ GramSplitPlan plan_gram_split(bool syrk, int64_t k, int64_t n, int64_t p, int64_
 static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs, const double* Y, int64_t ldy, int64_t ybs, int64_t k,
                             int64_t n, int64_t p, double* out, int64_t ldo, int64_t obs, const int32_t* map, AlphaDev scale, int accumulate,
                             const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream, const int32_t* gate = nullptr,
-                            int32_t gate_cols = 0, double* packed_dev = nullptr, double* packed_host = nullptr, int64_t packed_bstride = 0) {
+                            int32_t gate_cols = 0, double* packed_dev = nullptr, double* packed_host = nullptr, int64_t packed_bstride = 0,
+                            const GramArgs* fused = nullptr) {
     if (batch > 1 && (xbs == 0 || ybs == 0)) return false;
     GramTmaKernelArgs a{};
     const int bm = sc.plan.bm == 64 ? 64 : kTBM;
@@ -403,14 +483,19 @@ static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs
     a.workspace = sc.workspace;
     a.gate = gate; a.gate_cols = gate_cols;
     a.packed_dev = packed_dev; a.packed_host = packed_host; a.packed_bstride = packed_bstride;
+    if (fused && fused->gvec && sc.qworkspace_ok) {
+        a.gvec = fused->gvec; a.g_bstride = fused->g_bstride; a.qout = fused->qout; a.q_bstride = fused->q_bstride; a.c0out = fused->c0out;
+        a.qscale = fused->qscale; a.cscale = fused->cscale; a.qworkspace = sc.qworkspace;
+    }
     a.total_units = a.full_tiles + (a.total_tiles - a.full_tiles) * a.nslices;
     const int grid = (int)(a.total_units < sm_count ? a.total_units : sm_count);
     if (bm == 64) {
-        if (syrk) gram_tma_kernel<true, 64><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
-        else gram_tma_kernel<false, 64><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+        if (syrk && a.gvec) gram_tma_kernel<true, 64, true><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+        else if (syrk) gram_tma_kernel<true, 64, false><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+        else gram_tma_kernel<false, 64, false><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
     } else {
-        if (syrk) gram_tma_kernel<true, 128><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
-        else gram_tma_kernel<false, 128><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+        if (syrk) gram_tma_kernel<true, 128, false><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
+        else gram_tma_kernel<false, 128, false><<<grid, kTThreads, kTSmemBytes, stream>>>(a);
     }
     return true;
 }
@@ -419,10 +504,17 @@ bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k
     return encode_fn() != nullptr && ld % 2 == 0 && ((uintptr_t)X & 15) == 0 && !(batch > 1 && (bstride % 2 != 0 || bstride == 0)) && k > 0 && n > 0;
 }
 
+// the fused linear part exists only in the small-problem (64-tile, less than one wave) instantiation
+bool gram_fused_linear_supported(int64_t k, int64_t n, int64_t batch, int sm_count) {
+    const GramSplitPlan pl = plan_gram_split(true, k, n, n, batch, sm_count);
+    const int64_t t128 = ((n + kTBM - 1) / kTBM) * ((n + kTBM - 1) / kTBM + 1) / 2 * batch;
+    return pl.bm == 64 && t128 < sm_count;
+}
+
 bool launch_gram_syrk_tma(const GramArgs& g, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
     return launch_tma_impl(true, g.X, g.ldx, g.x_bstride, g.X, g.ldx, g.x_bstride, g.k, g.n, g.n, g.H, g.ldh, g.h_bstride, g.map, g.scale,
                            g.accumulate, sc, batch, sm_count, stream, g.gate, g.gate_cols, g.accumulate ? nullptr : g.packed_dev,
-                           g.accumulate ? nullptr : g.packed_host, g.packed_bstride);
+                           g.accumulate ? nullptr : g.packed_host, g.packed_bstride, &g);
 }
 
 bool launch_gemm_tn_tma(const GemmTNArgs& g, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {

@@ -101,6 +101,13 @@ struct GramArgs {
     double* packed_dev;
     double* packed_host;
     int64_t packed_bstride;
+    // Fused linear part (TMA kernel only): while a DIAGONAL tile's panel sits in shared memory the consumers also accumulate
+    //   q[map[col]] += qscale * sum_k X[k, col] * gvec[k]      and (tile (0,0))   c0 += cscale * sum_k gvec[k]^2
+    // which removes the second pass over X (the gemv + dot launch).  gvec == null: off.  Requires k even, gvec 16-byte aligned.
+    const double* gvec; int64_t g_bstride;
+    double* qout; int64_t q_bstride;
+    double* c0out;
+    AlphaDev qscale, cscale;
 };
 void launch_gram_syrk(const GramArgs& a, int64_t batch, int sm_count, cudaStream_t stream);
 // general TN product  M (n x p, ld) = X' * Y  (scratch for dot(f, h) with f != h and for A * Vector{AffineFunction})
@@ -124,10 +131,13 @@ struct GramScratch {
     GramSplitPlan plan;
     int32_t* counters;   // [split_tiles], zero between launches
     double* workspace;   // [workspace_doubles]
+    double* qworkspace;  // [split_tiles * nslices * (bm + 1)] partial (q, c0) sums of the fused linear part
+    int32_t qworkspace_ok;  // the planner provided what the fused linear part needs
 };
 bool launch_gram_syrk_tma(const GramArgs& a, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
 bool launch_gemm_tn_tma(const GemmTNArgs& a, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
 void configure_gram_tma_kernels();
+bool gram_fused_linear_supported(int64_t k, int64_t n, int64_t batch, int sm_count);
 bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k, int64_t n, int64_t batch);
 
 // ---------------- small kernels ---------------------------------------------------------------

@@ -44,7 +44,9 @@ static GramScratch make_gram_scratch(pmb_ctx* c, bool syrk, int64_t k, int64_t n
     if (sc.plan.nslices > 1) {
         sc.counters = dalloc<int32_t>(c, sc.plan.split_tiles, true);
         sc.workspace = dalloc<double>(c, sc.plan.workspace_doubles);
+        sc.qworkspace = dalloc<double>(c, sc.plan.split_tiles * sc.plan.nslices * (sc.plan.bm + 1));
     }
+    sc.qworkspace_ok = 1;
     return sc;
 }
 
@@ -453,7 +455,17 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
             s.gscratch = make_gram_scratch(c, true, ga.k, ga.n, ga.n, nb);
             st.push_back(s);
             c->gram_flops += F.k * F.ncols * (F.ncols + 1) + 2 * F.k * F.ncols + 2 * F.k;
-            if (F.g) {
+            // small (latency-bound) problems only: one launch fewer.  For large problems the extra work in the MMA loop costs more
+            // than the separate gemv+dot launch (measured at cfg2: Gram 2.09 -> 2.39 ms against a 34 us gemv).
+            const bool fuse_lin = F.g && c->use_tma && !getenv("PMB_NO_FUSED_Q") && F.k % 2 == 0 && aligned16(F.g) && (nb == 1 || F.gbs % 2 == 0) &&
+                                  gram_tma_applicable(F.X, F.ldx, F.xbs, F.k, F.ncols, nb) &&
+                                  gram_fused_linear_supported(F.k, F.ncols, nb, c->sm_count);
+            if (fuse_lin) {
+                // q[map] += 2 a cx cg X'g and c0 += a cg^2 g.g are accumulated by the Gram kernel itself (diagonal tiles)
+                Step& gs = st.back();
+                gs.gram.gvec = F.g; gs.gram.g_bstride = F.gbs; gs.gram.qout = T.q; gs.gram.q_bstride = N; gs.gram.c0out = T.c0;
+                gs.gram.qscale = scaled(a, 2.0 * F.cx * F.cg); gs.gram.cscale = scaled(a, F.cg * F.cg);
+            } else if (F.g) {
                 Step v;
                 v.type = ST_GEMV; v.cls = KC_REDUCE; v.batch = nb;
                 GemvArgs g{};

@@ -257,3 +257,25 @@ def test_block_sparse_small_against_literal_oracle():
     Cd, dd = model.block_arrays(0)
     assert np.array_equal(Cd, oblocks[0][0]) and np.array_equal(dd, oblocks[0][1])
     assert model.block_view(0).nterms == rows * cols  # what the reference emits: every entry, zeros included
+
+
+@pytest.mark.parametrize("env", ["PMB_NO_TMA", "PMB_NO_GRAPH"])
+def test_fallback_paths_agree(env, monkeypatch):
+    """The cp.async Gram / LDG-STG affine fallbacks (PMB_NO_TMA=1) and eager launches (PMB_NO_GRAPH=1) produce the same arrays
+    as the default TMA + CUDA-graph path (the switches are read when the context is created)."""
+    import parametron_b200 as pm
+    n, k, m = 384, 320, 96
+    rng = np.random.default_rng(12)
+    host = {"A": rng.standard_normal((k, n)), "b": rng.standard_normal(k), "C": rng.standard_normal((m, n)), "d": rng.standard_normal(m)}
+    outs = []
+    for on in (False, True):
+        if on:
+            monkeypatch.setenv(env, "1")
+        model, _ = ls_model(pm, n, k, m, mode="host", host=host)
+        model.initialize()
+        model.update()
+        assert model.stats()["uses_cuda_graph"] == (0 if (on and env == "PMB_NO_GRAPH") else 1)
+        outs.append(model.objective_arrays() + model.block_arrays(0))
+        model.close()
+    for a, b_ in zip(*outs):
+        assert_close(a, b_, 1e-12, env)
