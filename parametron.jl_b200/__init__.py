@@ -2,10 +2,10 @@
 
 The directory name contains a dot, so import it through the root-level shim:  `import parametron_b200 as pm`.
 """
-from . import _capi, shard
+from . import _capi, macros, shard
 from ._capi import (AlreadyInitialized, DimensionMismatch, PmbError, Unsupported, LIB_PATH)
 from .model import (Expr, Maximize, Minimize, Model, Parameter, Variable, adjoint, bilinear, constraint, dot, objective,
                     transpose, vcat, vect)
 
 __all__ = ["Model", "Parameter", "Variable", "Expr", "Minimize", "Maximize", "adjoint", "transpose", "dot", "bilinear", "vcat",
-           "vect", "objective", "constraint", "shard", "PmbError", "DimensionMismatch", "AlreadyInitialized", "Unsupported", "LIB_PATH"]
+           "vect", "objective", "constraint", "shard", "macros", "PmbError", "DimensionMismatch", "AlreadyInitialized", "Unsupported", "LIB_PATH"]

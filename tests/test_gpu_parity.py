@@ -506,3 +506,39 @@ def test_quadratic_constraint_blocks():
         Q, q, c0 = d.model.block_quadratic(1)
         assert_close(Q, Qo, 1e-10, "Qc"); assert_close(q, qo, 1e-10, "qc"); assert_close([c0], [c0o], 1e-10, "c0c")
         assert d.model.block_view(1).set_kind == 1 and d.model.block_view(1).is_scalar == 1
+
+
+def test_string_macros_read_like_the_reference():
+    """README.md:31-56 written with the string macros (the @expression / @objective / @constraint analogues) gives the same
+    arrays as the operator-overload API; test/model.jl:66's objective uses the 3-argument `*` rule."""
+    import parametron_b200 as pm
+    from parametron_b200.macros import constraint, expression, objective
+    from oracle import dense as D
+    n, m_ = 8, 2
+    rng = np.random.default_rng(1234)
+    Av, bv, Cv, dv = rng.random((n, n)), rng.random(n), rng.random((m_, n)), rng.random(m_)
+    model = pm.Model()
+    x = model.variables(n)
+    A, b, C_, d = (pm.Parameter(model, val=v) for v in (Av, bv, Cv, dv))
+    residual = expression(model, "A * x - b", A=A, x=x, b=b)
+    objective(model, pm.Minimize, "residual ⋅ residual", residual=residual)
+    constraint(model, "C * x == d", C=C_, x=x, d=d)
+    constraint(model, "[C * x; x] >= [d; lo]", C=C_, x=x, d=d, lo=np.zeros(n))
+    model.initialize()
+    model.update()
+    Q, q, c0 = model.objective_arrays()
+    Qo, qo, c0o = D.least_squares_objective(Av, bv, np.arange(1, n + 1), n)
+    assert_close(Q, Qo, 1e-10, "Q"); assert_close(q, qo, 1e-10, "q"); assert_close([c0], [c0o], 1e-10, "c0")
+    C1, d1 = model.block_arrays(1)          # Zeros bucket comes after Nonnegatives
+    assert np.array_equal(C1, Cv) and np.array_equal(d1, -dv)
+    C0, d0 = model.block_arrays(0)
+    assert np.array_equal(C0, np.vstack([Cv, np.eye(n)])) and np.array_equal(d0, np.concatenate([-dv, np.zeros(n)]))
+    # test/model.jl:66
+    m2 = pm.Model()
+    y = m2.variables(3)
+    Qp, r, s = pm.Parameter(m2, val=np.eye(3)), pm.Parameter(m2, val=np.array([1.0, 2.0, 3.0])), pm.Parameter(m2, f=lambda: np.float64(0.5))
+    objective(m2, pm.Minimize, "transpose(x) * Q * x + r ⋅ x + s", x=y, Q=Qp, r=r, s=s)
+    m2.initialize()
+    m2.update()
+    Q2, q2, c2 = m2.objective_arrays()
+    assert np.array_equal(Q2, 2 * np.eye(3)) and np.array_equal(q2, [1.0, 2.0, 3.0]) and c2 == 0.5
