@@ -1,0 +1,161 @@
+# ParametronB200.jl -- the Julia `ccall` shim a Parametron.jl maintainer would add to route `update!` through libpmb200.so.
+#
+# WRITTEN, NOT EXECUTED: neither this container nor the GPU box has Julia (SURVEY.md section 8c).  Every symbol bound here is
+# declared in include/parametron_b200.h and is exercised through the equivalent Python ctypes binding
+# (parametron.jl_b200/_capi.py), so signatures and argument order are the tested ones.
+#
+# Usage inside Parametron.jl (src/model.jl):
+#   Model(optimizer)                -> also `ctx = ParametronB200.Ctx()`
+#   Variable(m)                     -> `ParametronB200.add_variables!(m.ctx, 1)`                       (model.jl:49-53)
+#   Parameter(f, val, m)            -> `ParametronB200.register_parameter!(m.ctx, p, val)`             (parameter.jl:57)
+#   optimize_toplevel(expr)         -> emit the matching `ParametronB200.matvec/dot_/add/sub/mul/...`  (lazyexpression.jl:184-302)
+#   setobjective! / add_constraint  -> `set_objective!` / `add_constraint!`                            (model.jl:60-98)
+#   initialize!(m)                  -> `initialize!(m.ctx, varmap)`                                    (model.jl:117-122)
+#   update!(m)                      -> `update!(m.ctx)`                                                (model.jl:132-143)
+module ParametronB200
+
+const lib = joinpath(@__DIR__, "..", "parametron.jl_b200", "lib", "libpmb200.so")
+
+# status codes (include/parametron_b200.h)
+const PMB_OK, PMB_EINVAL, PMB_EDIM, PMB_EINITIALIZED, PMB_ENOTINIT, PMB_ECUDA, PMB_EUNSUPPORTED, PMB_ENOMEM = 0, -1, -2, -3, -4, -5, -6, -7
+const KIND_NUM_SCALAR, KIND_NUM_VECTOR, KIND_NUM_MATRIX, KIND_VARVEC, KIND_AFFVEC, KIND_AFF, KIND_QUAD, KIND_ADJVEC = 0:7
+const MINIMIZE, MAXIMIZE = 0, 1
+const SET_NONNEGATIVE, SET_NONPOSITIVE, SET_ZERO = 0, 1, 2
+const PARAM_DEVICE, PARAM_HOST, PARAM_UNIFORM = 0, 1, 2
+
+struct PmbError <: Exception
+    code::Cint
+    msg::String
+end
+
+mutable struct Ctx
+    ptr::Ptr{Cvoid}
+    roots::Vector{Any}   # keeps Parameters / buffers alive while the library holds their pointers
+end
+
+function check(ctx::Ctx, code::Cint)
+    code == PMB_OK && return nothing
+    msg = unsafe_string(ccall((:pmb_last_error, lib), Cstring, (Ptr{Cvoid},), ctx.ptr))
+    code == PMB_EDIM && throw(DimensionMismatch(msg))          # functions.jl:669,755,780-781,845,877
+    code == PMB_EINITIALIZED && error(msg)                     # "Model has already been initialized." model.jl:50,61,69
+    throw(PmbError(code, msg))
+end
+
+function Ctx(; device::Integer = 0, stream::Ptr{Cvoid} = C_NULL, batch::Integer = 1)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    code = ccall((:pmb_ctx_create, lib), Cint, (Cint, Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), device, stream, batch, out)
+    code == PMB_OK || error("pmb_ctx_create failed ($code): a B200 and libpmb200.so are required, there is no CPU fallback")
+    ctx = Ctx(out[], Any[])
+    finalizer(c -> ccall((:pmb_ctx_destroy, lib), Cint, (Ptr{Cvoid},), c.ptr), ctx)
+    ctx
+end
+
+# ---- variables / parameters -------------------------------------------------------------------------------------------
+function add_variables!(ctx::Ctx, n::Integer)                       # Variable(m::Model), model.jl:49-53
+    first = Ref{Int64}(0)
+    check(ctx, ccall((:pmb_add_variables, lib), Cint, (Ptr{Cvoid}, Int64, Ref{Int64}), ctx.ptr, n, first))
+    first[]
+end
+
+_shape(val) = ndims(val) == 0 ? (0, 0, 0) : ndims(val) == 1 ? (1, length(val), 0) : (2, size(val, 1), size(val, 2))
+
+# the in-place update function of a Parameter, called exactly once per update! (parameter.jl:93-102)
+function _host_callback(val::Ptr{Float64}, rows::Int64, cols::Int64, batch::Int64, user::Ptr{Cvoid})::Cvoid
+    p = unsafe_pointer_to_objref(user)
+    p.f(p.val[])
+    nothing
+end
+
+function register_parameter!(ctx::Ctx, p, val::Array{Float64})      # Parameter(f, val, model), parameter.jl:57
+    node = Ref{Int32}(0)
+    nd, r, c = _shape(val)
+    check(ctx, ccall((:pmb_param_create, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Cint, Ref{Int32}), ctx.ptr, nd, r, c, PARAM_HOST, node))
+    cb = @cfunction(_host_callback, Cvoid, (Ptr{Float64}, Int64, Int64, Int64, Ptr{Cvoid}))
+    push!(ctx.roots, p); push!(ctx.roots, val)
+    check(ctx, ccall((:pmb_param_set_host_ptr, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Cvoid}, Any), ctx.ptr, node[], val, cb, p))
+    node[]                                                          # Julia arrays are column-major: no re-layout
+end
+
+function register_device_parameter!(ctx::Ctx, dptr::Ptr{Float64}, dims::Tuple)   # Parameter(model; val = CuArray), parameter.jl:88
+    node = Ref{Int32}(0)
+    nd = length(dims); r = nd >= 1 ? dims[1] : 0; c = nd == 2 ? dims[2] : 0
+    check(ctx, ccall((:pmb_param_create, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Cint, Ref{Int32}), ctx.ptr, nd, r, c, PARAM_DEVICE, node))
+    check(ctx, ccall((:pmb_param_set_device_ptr, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), ctx.ptr, node[], dptr))
+    node[]
+end
+
+function constant(ctx::Ctx, val::Union{Float64, Array{Float64}})    # constant folding, lazyexpression.jl:189-192
+    node = Ref{Int32}(0)
+    nd, r, c = _shape(val)
+    buf = val isa Float64 ? [val] : val
+    check(ctx, ccall((:pmb_const_numeric, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}, Ref{Int32}), ctx.ptr, nd, r, c, buf, node))
+    node[]
+end
+
+function varvec(ctx::Ctx, indices::Vector{Int64})                   # Vector{Variable}
+    node = Ref{Int32}(0)
+    check(ctx, ccall((:pmb_varvec, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ref{Int32}), ctx.ptr, length(indices), indices, node))
+    node[]
+end
+
+# ---- one @expression rewrite rule = one call (lazyexpression.jl:198-302) ------------------------------------------------
+for (jl, c) in ((:matvec, :pmb_op_matvec), (:dot_, :pmb_op_dot), (:add, :pmb_op_add), (:sub, :pmb_op_sub), (:mul, :pmb_op_mul))
+    @eval function $jl(ctx::Ctx, a::Int32, b::Int32)
+        out = Ref{Int32}(0)
+        check(ctx, ccall(($(QuoteNode(c)), lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ref{Int32}), ctx.ptr, a, b, out))
+        out[]
+    end
+end
+for (jl, c) in ((:adjoint_, :pmb_op_adjoint), (:vect_, :pmb_op_vect))
+    @eval function $jl(ctx::Ctx, a::Int32)
+        out = Ref{Int32}(0)
+        check(ctx, ccall(($(QuoteNode(c)), lib), Cint, (Ptr{Cvoid}, Int32, Ref{Int32}), ctx.ptr, a, out))
+        out[]
+    end
+end
+function bilinear(ctx::Ctx, xT::Int32, Q::Int32, y::Int32)           # transpose(x) * Q * y, lazyexpression.jl:219-226
+    out = Ref{Int32}(0)
+    check(ctx, ccall((:pmb_op_bilinear, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Int32}), ctx.ptr, xT, Q, y, out))
+    out[]
+end
+function vcat_(ctx::Ctx, parts::Vector{Int32})                       # vcat!, functions.jl:969-994
+    out = Ref{Int32}(0)
+    check(ctx, ccall((:pmb_op_vcat, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ref{Int32}), ctx.ptr, length(parts), parts, out))
+    out[]
+end
+
+# ---- model ----------------------------------------------------------------------------------------------------------------
+set_objective!(ctx::Ctx, sense::Integer, node::Int32) =
+    check(ctx, ccall((:pmb_set_objective, lib), Cint, (Ptr{Cvoid}, Cint, Int32), ctx.ptr, sense, node))
+add_constraint!(ctx::Ctx, node::Int32, set::Integer) =
+    check(ctx, ccall((:pmb_add_constraint, lib), Cint, (Ptr{Cvoid}, Int32, Cint, Ptr{Int32}), ctx.ptr, node, set, C_NULL))
+# initialize!(m): varmap[i] = idxmap[MOI.VariableIndex(i)].value (mapindices!, model.jl:100-107)
+initialize!(ctx::Ctx, varmap::Vector{Int64}) = check(ctx, ccall((:pmb_initialize, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}), ctx.ptr, varmap))
+update!(ctx::Ctx) = check(ctx, ccall((:pmb_update, lib), Cint, (Ptr{Cvoid},), ctx.ptr))      # update!(m::Model), model.jl:132-143
+synchronize(ctx::Ctx) = check(ctx, ccall((:pmb_synchronize, lib), Cint, (Ptr{Cvoid},), ctx.ptr))
+
+struct ObjectiveView
+    kind::Int32; sense::Int32; is_constant::Int32; nvars::Int64
+    Q::Ptr{Float64}; q::Ptr{Float64}; c0::Ptr{Float64}
+end
+function objective_view(ctx::Ctx)                                    # replaces MOI.set(optimizer, ObjectiveFunction{F}(), f), moi_interop.jl:134
+    v = Ref{ObjectiveView}()
+    check(ctx, ccall((:pmb_get_objective, lib), Cint, (Ptr{Cvoid}, Ref{ObjectiveView}), ctx.ptr, v))
+    v[]
+end
+
+struct BlockView
+    set_kind::Int32; is_scalar::Int32; is_constant::Int32; bucket::Int32
+    rows::Int64; nvars::Int64; C::Ptr{Float64}; d::Ptr{Float64}; nterms::Int64
+    is_sparse::Int32; nnz::Int64; vals::Ptr{Float64}; sp_rows::Ptr{Int32}; sp_cols::Ptr{Int32}
+    Q::Ptr{Float64}
+end
+function block_view(ctx::Ctx, update_pos::Integer)                   # replaces MOI.set(optimizer, ConstraintFunction(), ci, f), :171
+    v = Ref{BlockView}()
+    check(ctx, ccall((:pmb_get_block, lib), Cint, (Ptr{Cvoid}, Int32, Ref{BlockView}), ctx.ptr, update_pos, v))
+    v[]
+end
+
+# With CUDA.jl a device-aware solver wraps the views without copies, e.g.
+#   v = objective_view(ctx); Q = unsafe_wrap(CuArray, CuPtr{Float64}(UInt(v.Q)), (v.nvars, v.nvars))
+end # module

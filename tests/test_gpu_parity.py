@@ -542,3 +542,31 @@ def test_string_macros_read_like_the_reference():
     m2.update()
     Q2, q2, c2 = m2.objective_arrays()
     assert np.array_equal(Q2, 2 * np.eye(3)) and np.array_equal(q2, [1.0, 2.0, 3.0]) and c2 == 0.5
+
+
+def test_two_models_interleaved():
+    """Two live contexts on one device (each with its own stream, graph and buffers) updated alternately do not interfere."""
+    import parametron_b200 as pm
+    rng = np.random.default_rng(47)
+    models = []
+    for n in (20, 33):
+        Av, bv = rng.random((n + 3, n)), rng.random(n + 3)
+        m = pm.Model()
+        x = m.variables(n)
+        A, b = pm.Parameter(m, val=Av), pm.Parameter(m, val=bv)
+        r = A * x - b
+        pm.objective(m, pm.Minimize, pm.dot(r, r))
+        pm.constraint(m, A * x, "<=", b)
+        m.initialize()
+        models.append((m, A, b))
+    for step in range(3):
+        for m, A, b in models:
+            A.val = rng.random(A.val.shape); b.val = rng.random(b.val.shape)
+            m.update()
+        for m, A, b in models:
+            Q, q, c0 = m.objective_arrays()
+            assert_close(Q, 2 * A.val.T @ A.val, 1e-10, "Q"); assert_close(q, -2 * A.val.T @ b.val, 1e-10, "q")
+            Cb, db = m.block_arrays(0)
+            assert np.array_equal(Cb, A.val) and np.array_equal(db, -b.val)
+    for m, _, _ in models:
+        m.close()
