@@ -1,0 +1,497 @@
+// K2i -- certified int8-slice Gram on the 5th-generation tensor cores (tcgen05 kind::i8, accumulators in TMEM).
+//
+// Same reference semantics as kernels_gram_tma.cu (vecdot! + muladd!, functions.jl:548-576,702-709, then the symmetric MOI
+// Hessian of moi_interop.jl:45-62:  H = scale * X'X, both triangles), but the fp64 contraction is carried out EXACTLY in
+// integer arithmetic, because tcgen05 has no f64 kind and the DMMA pipe (37 TFLOP/s) is ~100x slower than the int8 pipe:
+//
+//   1. slice kernel: every column j of X is scaled by 1 / sigma_j (sigma_j = largest magnitude / 0.99), rounded to a 47-bit signed
+//      fixed-point integer and cut into 6 balanced base-256 digits d_0..d_5 in [-128, 127] (int8 planes, K-major like X).  The same
+//      pass records, per instance, max sigma_j, max ||x_j||^2, max ||x_j / sigma_j||_1 and the largest 2-norm of every digit plane.
+//   2. Gram kernel <NS planes, BN>: for an output tile (128 columns i) x (BN columns j) all digit-plane products with s + t <= NS-1
+//      are issued as tcgen05.mma kind::i8 (M=128, N=BN, K=32) from TMA-loaded, 64-byte-swizzled shared-memory panels; planes with
+//      equal s + t share an int32 accumulator in TMEM (NS accumulators x BN columns <= 512 TMEM columns).  Integer accumulation is
+//      exact, so the result does not depend on tiling, k order or the number of SMs.
+//   3. epilogue: the NS int32 accumulators are combined by a Horner chain in fp64 (one rounding at 2^-53), scaled by
+//      sigma_i sigma_j 2^(-8 NS - 6) and by the caller's alpha, scattered through the variable map and written to both triangles
+//      (and, when asked, to the packed upper triangle P_x).
+//
+// What is dropped are the digit products with s + t >= NS and the representation error of the planes used.  gram_i8_level()
+// (pmb_kernels.h, shared with the fp64 kernel) bounds both with the recorded norms and picks, per instance, the smallest NS in {5, 6}
+// whose worst-case error is below tol * max |H| (max |H| of a Gram matrix is its largest diagonal entry) -- the north_star tolerance
+// is relative to the largest magnitude of the array.  The <5, 96> and <6, 80> launches each process the instances of their level;
+// instances that cannot be certified (wide dynamic range inside the matrix, non-finite values) are left to the fp64 DMMA kernel.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <math_constants.h>
+#include <cstdlib>
+
+#include "pmb_kernels.h"
+
+namespace pmb {
+
+constexpr int kI8BM = 128;          // tile rows = tcgen05 M (one TMEM lane per row)
+constexpr int kI8KC = 64;           // k (bytes) per pipeline stage: one 64-byte swizzle span, two K=32 MMAs per digit-plane pair
+constexpr int kI8Threads = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kI8TmemCols = 512;
+
+template <int NS, int BN>
+struct I8Cfg {
+    static constexpr int kITile = kI8BM * kI8KC;   // bytes of one digit plane of the row panel
+    static constexpr int kJTile = BN * kI8KC;
+    static constexpr int kStageBytes = NS * (kITile + kJTile);
+    static constexpr int kStages = (227 * 1024 - 2048) / kStageBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+    static_assert(NS * BN <= kI8TmemCols, "accumulators do not fit TMEM");
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "tcgen05 kind::i8, M = 128: N % 16 == 0");
+    static_assert(kStages >= 2, "pipeline needs two stages");
+};
+
+struct GramI8KernelArgs {
+    CUtensorMap tmi, tmj;   // digit planes (kp, n, 6, batch) uint8; boxes (64, 128, 1, 1) and (64, BN, 1, 1), 64-byte swizzle
+    int64_t k, kp, n;
+    const double* sigma;    // [batch][n]
+    const unsigned long long* stats;
+    double tol;
+    int32_t force_ns;
+    double* out; int64_t ldo, o_bstride;
+    const int32_t* map;
+    AlphaDev scale;
+    int32_t accumulate;
+    double* packed_dev; int64_t packed_bstride;
+    int32_t tiles_j;
+    int64_t tiles_per_inst, total_tiles;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------------------
+namespace i8 {
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(s_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(s_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(slot_in_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, issued by ONE thread for the whole CTA (SASS UTCIMMA)
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+// 16 consecutive TMEM columns of this thread's lane (lane = 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// shared-memory matrix descriptor of a K-major panel stored as rows of 64 bytes under the 64-byte swizzle (what the TMA box
+// (64 bytes, rows) with CU_TENSOR_MAP_SWIZZLE_64B writes): 8-row groups are 512 bytes apart (SBO), LBO is unused (1), Blackwell
+// descriptor version 1, layout type 4 = SWIZZLE_64B.  A K step of 32 bytes advances the start address by 32.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+}  // namespace i8
+
+// ---- slice kernel --------------------------------------------------------------------------------------------------------------
+struct GramI8SliceArgs {
+    const double* X; int64_t ldx, x_bstride;
+    int64_t k, kp, n, batch;
+    int8_t* slices;        // [batch][6][n][kp]
+    double* sigma;         // [batch][n]
+    unsigned long long* stats;
+};
+
+__device__ __forceinline__ void load4(const double* x, int64_t r0, int64_t k, bool vec, double (&v)[4]) {
+    if (vec && r0 + 3 < k) {
+        const double2 p = __ldg((const double2*)(x + r0)), q = __ldg((const double2*)(x + r0 + 2));
+        v[0] = p.x; v[1] = p.y; v[2] = q.x; v[3] = q.y;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = r0 + e < k ? __ldg(x + r0 + e) : 0.0;
+    }
+}
+
+// one warp per column: pass 1 = largest magnitude, sum of squares, 1-norm; pass 2 (re-read, L1/L2) = fixed-point digits
+__global__ void __launch_bounds__(256) gram_i8_slice_kernel(const GramI8SliceArgs a) {
+    constexpr int NP = kGramI8Planes;
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
+    const bool vec = (a.ldx % 2 == 0) && (((uintptr_t)a.X & 15) == 0) && (a.x_bstride % 2 == 0);
+    for (int64_t c = wid; c < a.batch * a.n; c += nw) {
+        const int64_t inst = c / a.n, j = c - inst * a.n;
+        const double* x = a.X + inst * a.x_bstride + j * a.ldx;
+        double amax = 0.0, ss = 0.0, l1 = 0.0;
+        bool bad = false;
+        for (int64_t r0 = (int64_t)lane * 4; r0 < a.k; r0 += 128) {
+            double v[4];
+            load4(x, r0, a.k, vec, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double av = fabs(v[e]);
+                bad |= !(av <= DBL_MAX);
+                amax = fmax(amax, av);
+                l1 += av;
+                ss = fma(v[e], v[e], ss);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+            bad |= (bool)__shfl_xor_sync(0xffffffffu, (int)bad, o);
+        }
+        if (amax > 0.0 && !(amax >= 1e-150 && amax <= 1e150)) bad = true;
+        const bool zero = !(amax > 0.0) || bad;
+        const double sigma = zero ? 1.0 : amax / 0.99;
+        const double mult = zero ? 0.0 : ldexp(0.99 / amax, 8 * NP - 1);   // x -> fixed point with 47 fractional bits of x / sigma
+        int8_t* dst = a.slices + ((inst * NP) * a.n + j) * a.kp;
+        uint32_t dsq[NP];
+#pragma unroll
+        for (int s = 0; s < NP; ++s) dsq[s] = 0u;
+        for (int64_t r0 = (int64_t)lane * 4; r0 < a.kp; r0 += 128) {
+            double v[4];
+            load4(x, r0, a.k, vec, v);
+            uint32_t w[NP];
+#pragma unroll
+            for (int s = 0; s < NP; ++s) w[s] = 0u;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                long long X = zero ? 0ll : __double2ll_rn(v[t] * mult);
+#pragma unroll
+                for (int s = NP - 1; s >= 1; --s) {
+                    const int d = (int)(signed char)(X & 0xFF);
+                    w[s] |= (uint32_t)(d & 0xFF) << (8 * t);
+                    dsq[s] += (uint32_t)(d * d);
+                    X = (X - d) >> 8;
+                }
+                w[0] |= (uint32_t)((int)X & 0xFF) << (8 * t);
+                dsq[0] += (uint32_t)((int)X * (int)X);
+            }
+#pragma unroll
+            for (int s = 0; s < NP; ++s) *(uint32_t*)(dst + (int64_t)s * a.n * a.kp + r0) = w[s];
+        }
+#pragma unroll
+        for (int s = 0; s < NP; ++s)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) dsq[s] += __shfl_xor_sync(0xffffffffu, dsq[s], o);
+        if (lane == 0) {
+            a.sigma[c] = sigma;
+            unsigned long long* st = a.stats + inst * kGramI8StatsStride;
+            if (bad) atomicMax(st, (unsigned long long)__double_as_longlong(CUDART_INF));
+            else if (amax > 0.0) {
+                atomicMax(st, (unsigned long long)__double_as_longlong(sigma));
+                atomicMax(st + 1, (unsigned long long)__double_as_longlong(ss));
+                atomicMax(st + 2, (unsigned long long)__double_as_longlong(l1 / sigma));
+#pragma unroll
+                for (int s = 0; s < NP; ++s) atomicMax(st + 3 + s, (unsigned long long)dsq[s]);
+            }
+        }
+    }
+}
+
+// ---- Gram kernel ---------------------------------------------------------------------------------------------------------------
+struct I8Unit { int64_t inst; int ti, tj; };
+
+// upper tiles, column-major: tile column tj (BN wide) holds the row tiles ti = 0 .. (last column of tj) / 128
+template <int BN>
+__device__ __forceinline__ I8Unit i8_decode(const GramI8KernelArgs& a, int64_t u) {
+    I8Unit w;
+    w.inst = u / a.tiles_per_inst;
+    int64_t tl = u - w.inst * a.tiles_per_inst;
+    int tj = 0;
+    for (;; ++tj) {
+        const int64_t lastcol = ((int64_t)(tj + 1) * BN < a.n ? (int64_t)(tj + 1) * BN : a.n) - 1;
+        const int64_t cnt = lastcol / kI8BM + 1;
+        if (tl < cnt) break;
+        tl -= cnt;
+    }
+    w.ti = (int)tl; w.tj = tj;
+    return w;
+}
+
+// this launch (NS planes) owns the instance?
+template <int NS>
+__device__ __forceinline__ bool i8_runs(const GramI8KernelArgs& a, int64_t inst) {
+    return a.force_ns ? a.force_ns == NS : gram_i8_level(a.stats, inst, a.tol) == NS;
+}
+
+template <int NS, int BN>
+__global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_constant__ GramI8KernelArgs a) {
+    using C = I8Cfg<NS, BN>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[C::kStages];
+    __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar, tmem_empty_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ double sfj[BN];       // sigma_j 2^(-4 NS - 3) of the tile's columns
+    __shared__ int32_t mapj[BN];     // output index of the tile's columns
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ring = (i8::s_u32(smem_raw) + 1023u) & ~1023u;
+    const int nkc = (int)(a.kp / kI8KC);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < C::kStages; ++s) { i8::mb_init(&full_bar[s], 1); i8::mb_init(&empty_bar[s], 1); }
+        i8::mb_init(&tmem_full_bar, 1);
+        i8::mb_init(&tmem_empty_bar, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) i8::tmem_alloc(&tmem_slot, kI8TmemCols);
+    i8::tc_fence_before();
+    __syncthreads();
+    i8::tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t u = blockIdx.x; u < a.total_tiles; u += gridDim.x) {
+                const I8Unit w = i8_decode<BN>(a, u);
+                if (!i8_runs<NS>(a, w.inst)) continue;
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int s = it % C::kStages;
+                    i8::mb_wait(&empty_bar[s], ((it / C::kStages) & 1) ^ 1);
+                    const uint32_t stage = ring + (uint32_t)s * C::kStageBytes;
+                    i8::mb_expect_tx(&full_bar[s], C::kStageBytes);
+#pragma unroll
+                    for (int sl = 0; sl < NS; ++sl)
+                        i8::tma_load_4d(stage + sl * C::kITile, &a.tmi, kc * kI8KC, w.ti * kI8BM, sl, (int)w.inst, &full_bar[s]);
+#pragma unroll
+                    for (int sl = 0; sl < NS; ++sl)
+                        i8::tma_load_4d(stage + NS * C::kITile + sl * C::kJTile, &a.tmj, kc * kI8KC, w.tj * BN, sl, (int)w.inst, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread, all digit-plane pairs with s + t <= NS - 1, level s + t -> TMEM columns [(s+t) BN, +BN) =====
+        if (lane == 0) {
+            // instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed int8 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24
+            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kI8BM >> 4) << 24);
+            uint32_t it = 0, tile_it = 0;
+            for (int64_t u = blockIdx.x; u < a.total_tiles; u += gridDim.x) {
+                const I8Unit w = i8_decode<BN>(a, u);
+                if (!i8_runs<NS>(a, w.inst)) continue;
+                i8::mb_wait(&tmem_empty_bar, (tile_it & 1) ^ 1);   // the epilogue has drained the previous tile
+                i8::tc_fence_after();
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int s = it % C::kStages;
+                    i8::mb_wait(&full_bar[s], (it / C::kStages) & 1);
+                    i8::tc_fence_after();
+                    const uint32_t stage = ring + (uint32_t)s * C::kStageBytes;
+#pragma unroll
+                    for (int kk = 0; kk < kI8KC / 32; ++kk) {
+#pragma unroll
+                        for (int lvl = 0; lvl < NS; ++lvl) {
+#pragma unroll
+                            for (int si = 0; si <= lvl; ++si) {
+                                const int sj = lvl - si;
+                                const uint64_t ad = i8::smem_desc_sw64(stage + si * C::kITile + kk * 32);
+                                const uint64_t bd = i8::smem_desc_sw64(stage + NS * C::kITile + sj * C::kJTile + kk * 32);
+                                i8::mma_i8(tmem_base + (uint32_t)(lvl * BN), ad, bd, idesc, (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    i8::mma_commit(&empty_bar[s]);   // the stage may be refilled once these MMAs have read it
+                }
+                i8::mma_commit(&tmem_full_bar);
+                ++tile_it;
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, warp w owns TMEM lanes 32 (w % 4) .. +31 = tile rows =====
+        const int q = warp & 3;
+        const int et = tid - 64;   // 0 .. 127
+        uint32_t tile_it = 0;
+        for (int64_t u = blockIdx.x; u < a.total_tiles; u += gridDim.x) {
+            const I8Unit w = i8_decode<BN>(a, u);
+            if (!i8_runs<NS>(a, w.inst)) continue;
+            const int64_t i0 = (int64_t)w.ti * kI8BM, j0 = (int64_t)w.tj * BN;
+            const double* sg = a.sigma + w.inst * a.n;
+            if (et < BN) {
+                const int64_t gj = j0 + et;
+                sfj[et] = gj < a.n ? sg[gj] * exp2(-4.0 * NS - 3.0) : 0.0;
+                mapj[et] = gj < a.n ? (a.map ? a.map[gj] : (int32_t)gj) : 0;
+            }
+            const int m = q * 32 + lane;
+            const int64_t gi = i0 + m;
+            const bool row_ok = gi < a.n;
+            const double sc = a.scale.ptr ? a.scale.c * a.scale.ptr[w.inst * a.scale.bstride] : a.scale.c;
+            const double fi = row_ok ? sc * (sg[gi] * exp2(-4.0 * NS - 3.0)) : 0.0;
+            const int64_t om = row_ok ? (a.map ? a.map[gi] : gi) : 0;
+            double* out = a.out + w.inst * a.o_bstride;
+            double* pk = a.packed_dev ? a.packed_dev + w.inst * a.packed_bstride : nullptr;
+            i8::epi_bar();   // sfj / mapj visible
+            i8::mb_wait(&tmem_full_bar, tile_it & 1);
+            i8::tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                int32_t acc[NS][16];
+#pragma unroll
+                for (int l = 0; l < NS; ++l) i8::tmem_ld16(trow + (uint32_t)(l * BN + c0), acc[l]);
+                i8::tmem_ld_wait();
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    double t = (double)acc[0][jj];
+#pragma unroll
+                    for (int l = 1; l < NS; ++l) t = fma(t, 256.0, (double)acc[l][jj]);
+                    const int64_t gj = j0 + c0 + jj;
+                    if (row_ok && gj < a.n && gi <= gj) {   // every unordered pair of columns exactly once
+                        const double v = t * fi * sfj[c0 + jj];
+                        const int64_t on = mapj[c0 + jj];
+                        double* p1 = out + om + on * a.ldo;
+                        if (a.accumulate) *p1 += v; else *p1 = v;
+                        if (gi != gj) {
+                            double* p2 = out + on + om * a.ldo;
+                            if (a.accumulate) *p2 += v; else *p2 = v;
+                        }
+                        if (pk) {
+                            const int64_t lo = om < on ? om : on, hi = om < on ? on : om;
+                            pk[hi * (hi + 1) / 2 + lo] = v;
+                        }
+                    }
+                }
+            }
+            i8::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) i8::mb_arrive(&tmem_empty_bar);
+            i8::epi_bar();   // sfj / mapj are rewritten for the next tile
+            ++tile_it;
+        }
+    }
+    i8::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        i8::tc_fence_after();
+        i8::tmem_dealloc(tmem_base, kI8TmemCols);
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFnI8)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnI8 encode_fn_i8() {
+    static EncodeTiledFnI8 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFnI8)p;
+    }
+    return fn;
+}
+
+static bool make_plane_map(CUtensorMap* tm, const int8_t* base, int64_t kp, int64_t n, int64_t batch, int box_rows) {
+    EncodeTiledFnI8 enc = encode_fn_i8();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)kp, (cuuint64_t)n, (cuuint64_t)kGramI8Planes, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)kp, (cuuint64_t)kp * n, (cuuint64_t)kp * n * kGramI8Planes};
+    cuuint32_t box[4] = {(cuuint32_t)kI8KC, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+GramI8Plan plan_gram_i8(int64_t k, int64_t n, int64_t batch) {
+    GramI8Plan p{};
+    if (!encode_fn_i8() || k <= 0 || n <= 0) return p;
+    if (k * kGramI8Planes * 16384 >= (int64_t)1 << 31) return p;   // int32 accumulators: (s + t + 1) * k * 128 * 128 must stay below 2^31
+    if (n >= ((int64_t)1 << 31) / 2 || batch >= ((int64_t)1 << 31)) return p;
+    p.ok = 1;
+    p.kp = (k + 127) / 128 * 128;
+    p.slice_bytes = batch * kGramI8Planes * n * p.kp;
+    return p;
+}
+
+void configure_gram_i8_kernels() {
+    cudaFuncSetAttribute(gram_i8_kernel<5, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 96>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_kernel<6, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6, 80>::kSmemBytes);
+}
+
+bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+    if (!sc.plan.ok || !sc.slices || g.packed_host || g.gate) return false;
+    cudaMemsetAsync(sc.stats, 0, sizeof(unsigned long long) * kGramI8StatsStride * (size_t)batch, stream);
+    GramI8SliceArgs s{};
+    s.X = g.X; s.ldx = g.ldx; s.x_bstride = g.x_bstride; s.k = g.k; s.kp = sc.plan.kp; s.n = g.n; s.batch = batch;
+    s.slices = sc.slices; s.sigma = sc.sigma; s.stats = sc.stats;
+    const int64_t cols = batch * g.n;
+    const int sgrid = (int)std::min<int64_t>((cols + 7) / 8, (int64_t)sm_count * 8);
+    gram_i8_slice_kernel<<<sgrid, 256, 0, stream>>>(s);
+    return true;
+}
+
+template <int NS, int BN>
+static bool launch_i8_impl(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+    GramI8KernelArgs a{};
+    if (!make_plane_map(&a.tmi, sc.slices, sc.plan.kp, g.n, batch, kI8BM)) return false;
+    if (!make_plane_map(&a.tmj, sc.slices, sc.plan.kp, g.n, batch, BN)) return false;
+    a.k = g.k; a.kp = sc.plan.kp; a.n = g.n; a.sigma = sc.sigma; a.stats = sc.stats; a.tol = sc.tol; a.force_ns = sc.force_ns;
+    a.out = g.H; a.ldo = g.ldh; a.o_bstride = g.h_bstride; a.map = g.map; a.scale = g.scale; a.accumulate = g.accumulate;
+    a.packed_dev = g.accumulate ? nullptr : g.packed_dev; a.packed_bstride = g.packed_bstride;
+    a.tiles_j = (int)((g.n + BN - 1) / BN);
+    int64_t tpi = 0;
+    for (int tj = 0; tj < a.tiles_j; ++tj) tpi += (std::min<int64_t>((int64_t)(tj + 1) * BN, g.n) - 1) / kI8BM + 1;
+    a.tiles_per_inst = tpi;
+    a.total_tiles = tpi * batch;
+    const int grid = (int)std::min<int64_t>(a.total_tiles, sm_count);
+    gram_i8_kernel<NS, BN><<<grid, kI8Threads, I8Cfg<NS, BN>::kSmemBytes, stream>>>(a);
+    return true;
+}
+
+bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+    if (!sc.plan.ok || !sc.slices || g.packed_host || g.gate) return false;
+    bool ok = true;
+    if (sc.force_ns != 6) ok = ok && launch_i8_impl<5, 96>(g, sc, batch, sm_count, stream);
+    if (sc.force_ns != 5) ok = ok && launch_i8_impl<6, 80>(g, sc, batch, sm_count, stream);
+    return ok;
+}
+
+}  // namespace pmb

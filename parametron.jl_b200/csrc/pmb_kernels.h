@@ -108,6 +108,9 @@ struct GramArgs {
     double* qout; int64_t q_bstride;
     double* c0out;
     AlphaDev qscale, cscale;
+    // Certified int8-slice path (kernels_gram_i8.cu) ran first: skip the instances it certified.  null = compute everything.
+    const unsigned long long* cert_stats;
+    double cert_tol;
 };
 void launch_gram_syrk(const GramArgs& a, int64_t batch, int sm_count, cudaStream_t stream);
 // general TN product  M (n x p, ld) = X' * Y  (scratch for dot(f, h) with f != h and for A * Vector{AffineFunction})
@@ -139,6 +142,60 @@ bool launch_gemm_tn_tma(const GemmTNArgs& a, const GramScratch& sc, int64_t batc
 void configure_gram_tma_kernels();
 bool gram_fused_linear_supported(int64_t k, int64_t n, int64_t batch, int sm_count);
 bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k, int64_t n, int64_t batch);
+
+// ---------------- K2i: certified int8-slice Gram on tcgen05 (kernels_gram_i8.cu) ----------------------------------------------
+// Every column j of X is scaled by 1 / sigma_j (sigma_j = largest magnitude / 0.99) and rounded to a 47-bit fixed-point integer cut
+// into kGramI8Planes balanced base-256 digits (int8 planes).  The Gram kernel multiplies the leading NS = 5 or 6 planes.
+// Per-instance statistics written by the slice kernel (unsigned long long[kGramI8StatsStride]):
+//   [0] bits of max_j sigma_j (0: every column is zero; +inf: non-finite or out-of-range data)   [1] bits of max_j ||x_j||_2^2
+//   [2] bits of max_j ||x_j / sigma_j||_1                                                          [3 + s] max_j sum_r d_s[r, j]^2
+constexpr int kGramI8Planes = 6;
+constexpr int kGramI8StatsStride = 16;
+#ifdef __CUDACC__
+// Number of digit planes (5 or 6) whose worst-case error -- representation error of the planes used plus every dropped digit
+// product, bounded with the measured column norms -- is below tol * max |H| (max |H| of a Gram matrix = its largest diagonal entry);
+// 0: not certifiable, the fp64 DMMA kernel computes this instance.
+__device__ __forceinline__ int gram_i8_level(const unsigned long long* stats, int64_t inst, double tol) {
+    const unsigned long long* st = stats + inst * kGramI8StatsStride;
+    if (st[0] == 0ull) return 5;                       // all-zero operand: every digit is zero
+    const double sig = __longlong_as_double((long long)st[0]);
+    if (!(sig < 1e200)) return 0;
+    const double ss = __longlong_as_double((long long)st[1]), l1 = __longlong_as_double((long long)st[2]);
+    double R[kGramI8Planes];
+#pragma unroll
+    for (int s = 0; s < kGramI8Planes; ++s) R[s] = sqrt((double)st[3 + s]);
+#pragma unroll
+    for (int ns = 5; ns <= kGramI8Planes; ++ns) {
+        double by = 2.0 * 1.1 * exp2(-8.0 * ns) * l1;  // sum_r (|y_ri| + |y_rj|) * |representation error|
+#pragma unroll
+        for (int s = 1; s < ns; ++s)
+#pragma unroll
+            for (int t = 1; t < ns; ++t)
+                if (s + t >= ns) by += exp2(-14.0 - 8.0 * (s + t)) * R[s] * R[t];   // dropped digit products (Cauchy-Schwarz)
+        if (1.01 * sig * sig * by <= tol * ss) return ns;
+    }
+    return 0;
+}
+#endif
+struct GramI8Plan {
+    int32_t ok;            // path applicable
+    int64_t kp;            // k rounded up to 128
+    int64_t slice_bytes;   // batch * kGramI8Planes * n * kp
+};
+GramI8Plan plan_gram_i8(int64_t k, int64_t n, int64_t batch);
+struct GramI8Scratch {
+    GramI8Plan plan;
+    int8_t* slices;              // [batch][kGramI8Planes][n][kp]
+    double* sigma;               // [batch][n]
+    unsigned long long* stats;   // [batch][kGramI8StatsStride]
+    double tol;                  // certification tolerance (relative to max |H|)
+    int32_t force_ns;            // experiments: 5 / 6 = run that many planes whatever the certificate says, 0 = adaptive
+};
+// memset(stats) + slice kernel (gram_i8_slice) and the two tcgen05 Gram launches, 5 and 6 planes, of which at most one does work per
+// instance (gram_i8_mma).  false: not applicable (the caller runs the fp64 kernel alone).
+bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
+bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
+void configure_gram_i8_kernels();
 
 // ---------------- small kernels ---------------------------------------------------------------
 // fused prologue of one update: all built-in Parameter generators (kind 0: Philox uniform fill, per instance) + zero fills
