@@ -246,6 +246,14 @@ typedef struct {
     int64_t gram_algorithmic_flops;     /* SYRK count k*N*(N+1) + 2kN + 2k per Gram term, one instance */
 } pmb_stats;
 int pmb_get_stats(pmb_ctx* ctx, pmb_stats* out);
+/* Precision mode of the objective-Hessian contraction (build phase).  The reference accumulates every product in Float64
+ * (functions.jl:548-576); the north_star tolerance is 1e-10 relative.  mode 1 (default): contractions large enough to amortise it run
+ * as exact integer products of int8 digit planes on the tcgen05 tensor cores whenever a worst-case error bound computed from the
+ * operand (tol, default 5e-11, relative to the largest |Q| entry) certifies the result -- per instance, 5 or 6 planes; everything
+ * else runs on the fp64 DMMA pipe.  mode 0: fp64 only.  modes 5 / 6: force that many planes (experiments, no certificate). */
+int pmb_set_gram_mode(pmb_ctx* ctx, int mode, double tol);
+/* instances of the most recent update whose contraction ran with 5 planes / 6 planes / in fp64: counts[3] */
+int pmb_gram_level_counts(pmb_ctx* ctx, int64_t* counts);
 /* time (ms, CUDA events on the context stream) of the most recent launch of each kernel class; class names via pmb_kernel_class_name */
 int pmb_enable_kernel_timing(pmb_ctx* ctx, int enable);
 int pmb_kernel_class_count(void);

@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <math_constants.h>
 #include <cstdlib>
 
@@ -484,6 +485,32 @@ static bool launch_i8_impl(const GramArgs& g, const GramI8Scratch& sc, int64_t b
     const int grid = (int)std::min<int64_t>(a.total_tiles, sm_count);
     gram_i8_kernel<NS, BN><<<grid, kI8Threads, I8Cfg<NS, BN>::kSmemBytes, stream>>>(a);
     return true;
+}
+
+__global__ void gram_i8_count_levels_kernel(const unsigned long long* stats, double tol, int force_ns, int64_t batch, unsigned long long* counts) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < batch; i += (int64_t)gridDim.x * blockDim.x) {
+        const int lv = force_ns ? force_ns : gram_i8_level(stats, i, tol);
+        atomicAdd(counts + (lv == 5 ? 0 : lv == 6 ? 1 : 2), 1ull);
+    }
+}
+
+void launch_gram_i8_count_levels(const GramI8Scratch& sc, int64_t batch, unsigned long long* counts_dev, cudaStream_t stream) {
+    const int grid = (int)std::min<int64_t>((batch + 255) / 256, 1024);
+    gram_i8_count_levels_kernel<<<grid, 256, 0, stream>>>(sc.stats, sc.tol, sc.force_ns, batch, counts_dev);
+}
+
+// Cost model (seconds) of one SYRK step, fitted to measurements on B200 (profiles/r01_n_*): the int8 path pays a fixed price
+// (slice pass over X, three launches, ~12 us of pipeline fill + epilogue per tile) that only large contractions amortise.
+bool gram_i8_pays_off(int64_t k, int64_t n, int64_t batch, int sm_count) {
+    if (const char* e = getenv("PMB_GRAM_I8_ALWAYS")) { if (atoi(e)) return true; }
+    int64_t tpi = 0;
+    for (int64_t tj = 0; tj * 96 < n; ++tj) tpi += (std::min<int64_t>((tj + 1) * 96, n) - 1) / kI8BM + 1;
+    const double tiles = (double)tpi * (double)batch;
+    const double waves = std::ceil(tiles / sm_count);
+    const double kp = (double)((k + 127) / 128 * 128);
+    const double t_i8 = waves * (kp / 32.0 * 15.0 * 48.0 / 1.45e9 * 1.15 + 12e-6) + (double)batch * n * (16.0 * k + 6.0 * kp) / 4.0e12 + 15e-6;
+    const double t_f64 = (double)batch * k * n * (n + 1) / 30e12 + 6e-6;
+    return t_i8 < t_f64;
 }
 
 bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {

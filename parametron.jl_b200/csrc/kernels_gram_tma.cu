@@ -51,6 +51,9 @@ struct GramTmaKernelArgs {
     double* c0out;
     AlphaDev qscale, cscale;
     double* qworkspace;
+    const unsigned long long* cert_stats;  // see GramArgs::cert_stats: instances certified for the int8 path are skipped here
+    double cert_tol;
+    int32_t cert_force;
     int32_t* counters;    // [total_tiles - full_tiles] arrival counters, zero between launches
     double* workspace;    // [(total_tiles - full_tiles) * nslices][64][256] partial accumulators
     int64_t total_units;
@@ -97,6 +100,10 @@ __device__ __forceinline__ void dmma_16x8x4(double (&c)[4], double a0, double a1
     asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                  : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
                  : "d"(a0), "d"(a1), "d"(b0));
+}
+// the certified int8-slice kernels (kernels_gram_i8.cu) own this instance: nothing to do here
+__device__ __forceinline__ bool skip_certified(const GramTmaKernelArgs& a, int64_t inst) {
+    return a.cert_stats && (a.cert_force || gram_i8_level(a.cert_stats, inst, a.cert_tol) != 0);
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTConsumerWarps * 32) : "memory"); }
 
@@ -204,6 +211,7 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
             uint32_t it = 0;
             for (int64_t u = blockIdx.x; u < a.total_units; u += gridDim.x) {
                 const Unit w = decode_unit<SYRK>(a, u);
+                if (SYRK && skip_certified(a, w.inst)) continue;
                 const bool diag = SYRK && w.ti == w.tj;
                 if (SYRK && a.gate) {
                     // wait until the column chunk holding this tile's right-most panel has been uploaded (ti <= tj: the left
@@ -247,6 +255,7 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
     uint32_t it = 0;
     for (int64_t u = blockIdx.x; u < a.total_units; u += gridDim.x) {
         const Unit w = decode_unit<SYRK>(a, u);
+        if (SYRK && skip_certified(a, w.inst)) continue;
         const bool diag = SYRK && w.ti == w.tj;
         double acc[MI][NI][4];
 #pragma unroll
@@ -487,6 +496,7 @@ static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs
         a.gvec = fused->gvec; a.g_bstride = fused->g_bstride; a.qout = fused->qout; a.q_bstride = fused->q_bstride; a.c0out = fused->c0out;
         a.qscale = fused->qscale; a.cscale = fused->cscale; a.qworkspace = sc.qworkspace;
     }
+    if (fused) { a.cert_stats = fused->cert_stats; a.cert_tol = fused->cert_tol; a.cert_force = fused->cert_force; }
     a.total_units = a.full_tiles + (a.total_tiles - a.full_tiles) * a.nslices;
     const int grid = (int)(a.total_units < sm_count ? a.total_units : sm_count);
     if (bm == 64) {

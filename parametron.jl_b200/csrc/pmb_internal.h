@@ -154,6 +154,7 @@ struct Step {
     GramScratch gscratch{};
     const FillJob* jobs = nullptr; int njobs = 0, job_blocks = 0;  // ST_PROLOGUE  // ST_GRAM / ST_GEMM: k-split plan, arrival counters and partial-tile workspace
     GramArgs gram{};
+    GramI8Scratch i8{};   // ST_GRAM: certified int8-slice path (slices == nullptr: fp64 only)
     GemmTNArgs gemm{};
     GemvArgs gemv{};
     DotArgs dot{};
@@ -244,6 +245,11 @@ struct pmb_ctx {
     cudaGraph_t graph = nullptr;
     bool use_graph = false;
     bool use_tma = true;
+    // Gram precision mode (pmb_set_gram_mode): 0 = fp64 DMMA only, 1 = certified int8 slices where they pay off (default),
+    // 5 / 6 = force that many digit planes on every SYRK step (experiments: no certificate, no fp64 fallback)
+    int gram_mode = 1;
+    double gram_tol = 5e-11;
+    unsigned long long* gram_counts = nullptr;   // device: instances per level {5 planes, 6 planes, fp64} of the last counted update
     bool timing = false;
     std::vector<cudaEvent_t> ev;         // 2 per step
     bool ev_pending = false;

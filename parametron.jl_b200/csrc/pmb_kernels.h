@@ -111,6 +111,7 @@ struct GramArgs {
     // Certified int8-slice path (kernels_gram_i8.cu) ran first: skip the instances it certified.  null = compute everything.
     const unsigned long long* cert_stats;
     double cert_tol;
+    int32_t cert_force;    // experiments: the int8 path was forced for every instance
 };
 void launch_gram_syrk(const GramArgs& a, int64_t batch, int sm_count, cudaStream_t stream);
 // general TN product  M (n x p, ld) = X' * Y  (scratch for dot(f, h) with f != h and for A * Vector{AffineFunction})
@@ -195,6 +196,10 @@ struct GramI8Scratch {
 // instance (gram_i8_mma).  false: not applicable (the caller runs the fp64 kernel alone).
 bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
 bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
+// counts[0..2] += number of instances whose certificate picked 5 planes / 6 planes / the fp64 kernel (introspection for tests and bench)
+void launch_gram_i8_count_levels(const GramI8Scratch& sc, int64_t batch, unsigned long long* counts_dev, cudaStream_t stream);
+// predicted seconds of the two ways to compute one SYRK step; the planner picks the int8 path when it is the faster one
+bool gram_i8_pays_off(int64_t k, int64_t n, int64_t batch, int sm_count);
 void configure_gram_i8_kernels();
 
 // ---------------- small kernels ---------------------------------------------------------------

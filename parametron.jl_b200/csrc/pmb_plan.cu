@@ -432,8 +432,22 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
             ga.X = F.X; ga.ldx = F.ldx; ga.x_bstride = F.xbs; ga.k = F.k; ga.n = F.ncols;
             ga.H = T.Q; ga.ldh = N; ga.h_bstride = N * N; ga.map = F.map;
             ga.scale = scaled(a, 2.0 * F.cx * F.cx); ga.accumulate = overwrite ? 0 : 1;
+            // certified int8-slice path on tcgen05 (kernels_gram_i8.cu): large contractions only, fp64 kernel keeps the uncertified instances
+            GramI8Scratch i8{};
+            if (c->gram_mode != 0 && c->use_tma && gram_tma_applicable(F.X, F.ldx, F.xbs, F.k, F.ncols, nb) &&
+                (c->gram_mode >= 5 || gram_i8_pays_off(F.k, F.ncols, nb, c->sm_count))) {
+                i8.plan = plan_gram_i8(F.k, F.ncols, nb);
+                if (i8.plan.ok) {
+                    i8.slices = dalloc<int8_t>(c, i8.plan.slice_bytes);
+                    i8.sigma = dalloc<double>(c, nb * F.ncols);
+                    i8.stats = dalloc<unsigned long long>(c, nb * kGramI8StatsStride, true);
+                    i8.tol = c->gram_tol;
+                    i8.force_ns = c->gram_mode >= 5 ? c->gram_mode : 0;
+                    ga.cert_stats = i8.stats; ga.cert_tol = i8.tol; ga.cert_force = i8.force_ns != 0;
+                }
+            }
             // upload/compute overlap: the operand is a pinned HOST Parameter nothing else reads -> gate the kernel on chunk arrival
-            if (is_objective && overwrite && c->h2d_in_graph && nb == 1 && F.whole_node >= 0 && c->pipe_param < 0 && c->use_tma &&
+            if (!i8.slices && is_objective && overwrite && c->h2d_in_graph && nb == 1 && F.whole_node >= 0 && c->pipe_param < 0 && c->use_tma &&
                 !getenv("PMB_NO_PIPE")) {
                 const Node& pn = c->nodes[(size_t)F.whole_node];
                 const int64_t tile_cols = (F.ncols + 127) / 128;
@@ -452,12 +466,13 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                 }
             }
             s.gram = ga;
+            s.i8 = i8;
             s.gscratch = make_gram_scratch(c, true, ga.k, ga.n, ga.n, nb);
             st.push_back(s);
             c->gram_flops += F.k * F.ncols * (F.ncols + 1) + 2 * F.k * F.ncols + 2 * F.k;
             // small (latency-bound) problems only: one launch fewer.  For large problems the extra work in the MMA loop costs more
             // than the separate gemv+dot launch (measured at cfg2: Gram 2.09 -> 2.39 ms against a 34 us gemv).
-            const bool fuse_lin = F.g && c->use_tma && !getenv("PMB_NO_FUSED_Q") && F.k % 2 == 0 && aligned16(F.g) && (nb == 1 || F.gbs % 2 == 0) &&
+            const bool fuse_lin = !i8.slices && F.g && c->use_tma && !getenv("PMB_NO_FUSED_Q") && F.k % 2 == 0 && aligned16(F.g) && (nb == 1 || F.gbs % 2 == 0) &&
                                   gram_tma_applicable(F.X, F.ldx, F.xbs, F.k, F.ncols, nb) &&
                                   gram_fused_linear_supported(F.k, F.ncols, nb, c->sm_count);
             if (fuse_lin) {
@@ -611,6 +626,12 @@ static void run_step(pmb_ctx* c, const Step& s) {
         case ST_SPROD: launch_scalar_prod(s.out, s.out_bstride, s.scale, s.s0, s.s0_bs, s.s1, s.s1_bs, s.batch, st); break;
         case ST_AFFINE: launch_affine_assemble(s.aff, s.batch, c->sm_count, st); break;
         case ST_GRAM:
+            if (s.i8.slices) {  // slice pass + 5- and 6-plane tcgen05 launches; the fp64 launch below skips what they certified
+                if (!launch_gram_i8_slice(s.gram, s.i8, s.batch, c->sm_count, st) || !launch_gram_i8_mma(s.gram, s.i8, s.batch, c->sm_count, st))
+                    fail(PMB_ECUDA, "int8-slice Gram launch refused");
+                if (!launch_gram_syrk_tma(s.gram, s.gscratch, s.batch, c->sm_count, st)) fail(PMB_ECUDA, "fp64 Gram (TMA) launch refused");
+                break;
+            }
             if (!(c->use_tma && launch_gram_syrk_tma(s.gram, s.gscratch, s.batch, c->sm_count, st)))
                 launch_gram_syrk(s.gram, s.batch, c->sm_count, st);
             break;
@@ -765,6 +786,8 @@ int pmb_ctx_create(int device, void* stream, int64_t batch, pmb_ctx** out) {
     configure_gram_kernels();
     configure_affine_tma_kernels();
     configure_gram_tma_kernels();
+    configure_gram_i8_kernels();
+    if (const char* gm = getenv("PMB_GRAM_MODE")) c->gram_mode = atoi(gm);
     const char* ng = getenv("PMB_NO_GRAPH");
     c->use_graph = !(ng && ng[0] == '1');
     const char* nt = getenv("PMB_NO_TMA");
@@ -895,7 +918,7 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
     }
     ctx->launches_per_update = 0;
     ctx->memcpy_per_update = 0;
-    for (auto& s : ctx->steps) if (s.type != ST_MEMSET) ctx->launches_per_update += 1;
+    for (auto& s : ctx->steps) if (s.type != ST_MEMSET) ctx->launches_per_update += (s.type == ST_GRAM && s.i8.slices) ? (s.i8.force_ns ? 3 : 4) : 1;
     for (auto& n : ctx->nodes) if (n.needed && n.nop == NOP_PARAM && n.pmode == PMB_PARAM_HOST) ctx->memcpy_per_update += 1;
     // constants: evaluated exactly once (constant folding lazyexpression.jl:189-192; isconstant moi_interop.jl:123,153)
     for (auto& s : ctx->init_steps) run_step(ctx, s);
@@ -1055,6 +1078,35 @@ int pmb_get_stats(pmb_ctx* ctx, pmb_stats* out) {
     out->uses_cuda_graph = ctx->graph_exec ? 1 : 0;
     out->affine_algorithmic_bytes = ctx->affine_bytes;
     out->gram_algorithmic_flops = ctx->gram_flops;
+    API_END(ctx)
+}
+
+int pmb_set_gram_mode(pmb_ctx* ctx, int mode, double tol) {
+    API_BEGIN(ctx)
+    if (ctx->initialized) fail(PMB_EINITIALIZED, "pmb_set_gram_mode after pmb_initialize");
+    if (mode != 0 && mode != 1 && mode != 5 && mode != 6) fail(PMB_EINVAL, "gram mode must be 0 (fp64), 1 (certified int8), 5 or 6 (forced planes)");
+    ctx->gram_mode = mode;
+    if (tol > 0) ctx->gram_tol = tol;
+    API_END(ctx)
+}
+
+int pmb_gram_level_counts(pmb_ctx* ctx, int64_t* counts) {
+    API_BEGIN(ctx)
+    if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_gram_level_counts before pmb_initialize");
+    if (!counts) fail(PMB_EINVAL, "null counts");
+    counts[0] = counts[1] = counts[2] = 0;
+    if (!ctx->gram_counts) ctx->gram_counts = dalloc<unsigned long long>(ctx, 3, true);
+    CK(cudaMemsetAsync(ctx->gram_counts, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    int64_t fp64_only = 0;
+    for (auto& s : ctx->steps) {
+        if (s.type != ST_GRAM) continue;
+        if (s.i8.slices) launch_gram_i8_count_levels(s.i8, s.batch, ctx->gram_counts, ctx->stream);
+        else fp64_only += s.batch;
+    }
+    unsigned long long h[3];
+    CK(cudaMemcpyAsync(h, ctx->gram_counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    counts[0] = (int64_t)h[0]; counts[1] = (int64_t)h[1]; counts[2] = (int64_t)h[2] + fp64_only;
     API_END(ctx)
 }
 

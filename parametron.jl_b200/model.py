@@ -253,13 +253,15 @@ class Model:
     """src/model.jl:1-30.  `optimizer` is an optional callable invoked by solve() with the model after update() -- the
     external solve itself is out of scope and untouched (north_star); results stay on the device."""
 
-    def __init__(self, optimizer=None, device=0, batch=1, stream=None):
+    def __init__(self, optimizer=None, device=0, batch=1, stream=None, gram_mode=None, gram_tol=0.0):
         self._lib = K.load()
         self._ctx = C.c_void_p()
         code = self._lib.pmb_ctx_create(int(device), C.c_void_p(stream) if stream else None, int(batch), C.byref(self._ctx))
         if code != K.OK:
             raise K.PmbError(code, f"pmb_ctx_create failed with {code}: a B200 (sm_100) and the CUDA runtime are required; "
                                    "there is no CPU fallback")
+        if gram_mode is not None:  # 0: fp64 DMMA only, 1: certified int8 digit planes on tcgen05 (default), 5 / 6: forced planes
+            self._ck(self._lib.pmb_set_gram_mode(self._ctx, int(gram_mode), float(gram_tol)))
         self.optimizer = optimizer
         self.device = int(device)
         self.batch = int(batch)
@@ -272,6 +274,12 @@ class Model:
     # -- plumbing
     def _ck(self, code):
         K.check(self._lib, self._ctx, code)
+
+    def gram_level_counts(self):
+        """instances of the last update whose Hessian contraction ran with (5 int8 planes, 6 int8 planes, fp64)"""
+        out = (C.c_int64 * 3)()
+        self._ck(self._lib.pmb_gram_level_counts(self._ctx, out))
+        return tuple(int(v) for v in out)
 
     def close(self):
         if self._ctx:

@@ -1,0 +1,185 @@
+"""GPU parity of the certified int8-slice Gram (csrc/kernels_gram_i8.cu: tcgen05 kind::i8, TMEM accumulators) against the dense
+oracle (needs a B200: -m gpu).  The contraction `vecdot!` + `muladd!` (functions.jl:548-576,702-709) is fp64 in the reference; the
+device may run it as exact integer products of 5 or 6 int8 digit planes when a worst-case bound certifies 1e-10 relative to the
+largest |Q| entry (the north_star tolerance, written per assert), otherwise on the fp64 DMMA pipe.  Covered: forced 5 / 6 planes,
+the adaptive certificate (uniform -> 5, wide dynamic range -> 6, non-finite / extreme -> fp64) per instance of one batch, ragged
+sizes, permuted index maps, accumulation with a second quadratic term, the packed P_x of the solver-side ingest, determinism."""
+import numpy as np
+import pytest
+
+from oracle import dense as D
+from tests.twin import assert_close
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def ls_model(pm, n, k, m, batch=1, gram_mode=1, qp=False):
+    model = pm.Model(batch=batch, gram_mode=gram_mode)
+    x = model.variables(n)
+    A, b, Cm, d = (pm.Parameter(model, shape=s, device=True) for s in ((k, n), (k,), (m, n), (m,)))
+    r = A * x - b
+    pm.objective(model, pm.Minimize, pm.dot(r, r))
+    pm.constraint(model, Cm * x, "==", d)
+    if qp:
+        model.enable_qp_pack()
+    return model, (A, b, Cm, d)
+
+
+def upload_all(params, vals, batch=1):
+    for p, v in zip(params, vals):
+        p.upload(v)
+
+
+@pytest.mark.parametrize("mode", [5, 6])
+@pytest.mark.parametrize("shape", [(128, 64), (200, 300), (520, 1000), (96, 8), (1, 2), (1, 1), (777, 130)])
+def test_forced_planes_match_dense_oracle(mode, shape):
+    import parametron_b200 as pm
+    n, k = shape
+    m = 3
+    rng = np.random.default_rng(n * 31 + k + mode)
+    vals = [rng.random(s) for s in ((k, n), (k,), (m, n), (m,))]
+    model, params = ls_model(pm, n, k, m, gram_mode=mode)
+    model.initialize()
+    upload_all(params, vals)
+    model.update()
+    Q, q, c0 = model.objective_arrays()
+    Qo, qo, c0o = D.least_squares_objective(vals[0], vals[1], np.arange(1, n + 1), n)
+    assert_close(Q, Qo, RTOL, "Q"); assert_close(q, qo, RTOL, "q"); assert_close([c0], [c0o], RTOL, "c0")
+    assert np.array_equal(Q, Q.T)
+    # odd k: the operand does not meet the 16-byte TMA alignment, the contraction stays on the fp64 kernels
+    assert model.gram_level_counts() == ((0, 0, 1) if k % 2 else (1, 0, 0) if mode == 5 else (0, 1, 0))
+    # exact integer accumulation: a second update with the same Parameters is bit-identical
+    model.update()
+    assert np.array_equal(model.objective_arrays()[0], Q)
+
+
+def test_adaptive_certificate_picks_level_per_instance(monkeypatch):
+    """one batch, four instances: uniform[0,1) -> 5 planes; columns spanning 6 decades -> 6 planes; a column of 1e-300 next to
+    1e+200 (outside the fixed-point range) -> fp64; an Inf entry -> fp64 (Inf/NaN propagate exactly as in the fp64 kernel)."""
+    import parametron_b200 as pm
+    monkeypatch.setenv("PMB_GRAM_I8_ALWAYS", "1")   # the size heuristic would keep this small problem on the fp64 kernel
+    n, k, m, B = 260, 384, 2, 4
+    rng = np.random.default_rng(7)
+    A = np.empty((B, k, n))
+    A[0] = rng.random((k, n))
+    A[1] = rng.standard_normal((k, n)) * 10.0 ** (6.0 * rng.random((k, n)) - 3.0)
+    A[2] = rng.standard_normal((k, n)); A[2][:, 3] *= 1e200; A[2][:, 5] *= 1e-300
+    A[3] = rng.standard_normal((k, n)); A[3][17, 11] = np.inf
+    b = rng.standard_normal((B, k))
+    Cm = rng.standard_normal((B, m, n))
+    d = rng.standard_normal((B, m))
+    model, params = ls_model(pm, n, k, m, batch=B, gram_mode=1)
+    model.initialize()
+    upload_all(params, (A, b, Cm, d))
+    model.update()
+    assert model.gram_level_counts() == (1, 1, 2)
+    Q, q, c0 = model.objective_arrays()
+    for inst in range(3):
+        with np.errstate(over="ignore", invalid="ignore"):
+            Qo, qo, c0o = D.least_squares_objective(A[inst], b[inst], np.arange(1, n + 1), n)
+        if inst < 2:
+            assert_close(Q[inst], Qo, RTOL, f"Q[{inst}]")
+        else:  # 1e400 overflows: compare the finite part and the pattern of infinities
+            fin = np.isfinite(Qo)
+            assert np.array_equal(np.isfinite(Q[inst]), fin)
+            assert_close(np.where(fin, Q[inst], 0.0)[np.ix_(np.arange(n) != 3, np.arange(n) != 3)],
+                         np.where(fin, Qo, 0.0)[np.ix_(np.arange(n) != 3, np.arange(n) != 3)], RTOL, f"Q[{inst}] finite part")
+    # the Inf entry poisons row/column 11 of instance 3 (Inf or NaN), everything else is finite and right
+    Q3 = Q[3]
+    assert not np.isfinite(Q3[11, :]).any() and not np.isfinite(Q3[:, 11]).any()
+    keep = np.arange(n) != 11
+    A3 = A[3].copy(); A3[17, 11] = 0.0
+    Qo3 = 2.0 * A3.T @ A3
+    assert_close(Q3[np.ix_(keep, keep)], Qo3[np.ix_(keep, keep)], RTOL, "Q[3] finite part")
+
+
+def test_adaptive_matches_fp64_mode_and_permuted_map(monkeypatch):
+    import parametron_b200 as pm
+    monkeypatch.setenv("PMB_GRAM_I8_ALWAYS", "1")
+    n, k, m = 300, 257, 65   # odd k: the unaligned load path of the slice kernel is not used (ld is even), ragged tiles are
+    rng = np.random.default_rng(3)
+    vals = [rng.standard_normal(s) for s in ((k + 1, n), (k + 1,), (m, n), (m,))]
+    perm = rng.permutation(n) + 1
+    outs = {}
+    for mode in (0, 1):
+        model, params = ls_model(pm, n, k + 1, m, gram_mode=mode)
+        model.initialize(idxmap=perm)
+        upload_all(params, vals)
+        model.update()
+        outs[mode] = model.objective_arrays()
+        lv = model.gram_level_counts()
+        assert lv == ((0, 0, 1) if mode == 0 else lv) and sum(lv) == 1
+        if mode == 1:
+            assert lv[2] == 0   # standard normal data certifies with 5 or 6 planes
+    Qo, qo, c0o = D.least_squares_objective(vals[0], vals[1], np.arange(1, n + 1), n, varmap=perm)
+    for mode in (0, 1):
+        assert_close(outs[mode][0], Qo, RTOL, f"Q mode {mode}"); assert_close(outs[mode][1], qo, RTOL, "q")
+    assert_close(outs[0][1], outs[1][1], 1e-13, "q across modes")   # q, c0 come from fp64 reductions in both modes
+
+
+def test_accumulating_gram_with_second_quadratic_term():
+    """objective = ||Ax - b||^2 + x'Px  (P constant): the Gram launch accumulates into a zeroed Q next to the bilinear scatter."""
+    import parametron_b200 as pm
+    n, k = 256, 192
+    rng = np.random.default_rng(11)
+    Av, bv = rng.random((k, n)), rng.random(k)
+    Pm = rng.standard_normal((n, n))
+    for mode in (5, 6, 0):
+        model = pm.Model(gram_mode=mode)
+        x = model.variables(n)
+        A = pm.Parameter(model, shape=(k, n), device=True)
+        b = pm.Parameter(model, shape=(k,), device=True)
+        P = pm.Parameter(model, shape=(n, n), device=True)
+        r = A * x - b
+        pm.objective(model, pm.Minimize, pm.dot(r, r) + pm.bilinear(pm.adjoint(x, model=model), P, x))
+        model.initialize()
+        A.upload(Av); b.upload(bv); P.upload(Pm)
+        model.update()
+        Q, q, c0 = model.objective_arrays()
+        Qo = 2.0 * Av.T @ Av + Pm + Pm.T
+        assert_close(Q, Qo, RTOL, f"Q mode {mode}")
+        assert_close(q, -2.0 * Av.T @ bv, RTOL, "q"); assert_close([c0], [bv @ bv], RTOL, "c0")
+
+
+def test_packed_upper_triangle_from_int8_epilogue():
+    import parametron_b200 as pm
+    n, k, m = 333, 512, 40
+    rng = np.random.default_rng(5)
+    vals = [rng.random(s) for s in ((k, n), (k,), (m, n), (m,))]
+    model, params = ls_model(pm, n, k, m, gram_mode=5, qp=True)
+    model.initialize()
+    upload_all(params, vals)
+    model.update()
+    qp = model.qp_arrays()
+    Qo = 2.0 * vals[0].T @ vals[0]
+    iu = np.triu_indices(n)
+    packed = np.empty(n * (n + 1) // 2)
+    packed[iu[1] * (iu[1] + 1) // 2 + iu[0]] = Qo[iu]
+    assert_close(qp["P_x"], packed, RTOL, "P_x")
+    assert_close(model.objective_arrays()[0], Qo, RTOL, "Q")
+
+
+def test_cfg2_size_properties_int8_default_mode():
+    """BASELINE.json configs[1] (n=4096, k=4096): the default mode certifies uniform data with 5 planes; size-independent checks."""
+    import parametron_b200 as pm
+    n = k = 4096
+    m = 8
+    rng = np.random.default_rng(0)
+    vals = [rng.random(s) for s in ((k, n), (k,), (m, n), (m,))]
+    model, params = ls_model(pm, n, k, m, gram_mode=1)
+    model.initialize()
+    upload_all(params, vals)
+    model.update()
+    assert model.gram_level_counts() == (1, 0, 0)
+    Q, q, c0 = model.objective_arrays()
+    assert np.array_equal(Q, Q.T)
+    scale = np.abs(Q).max()
+    assert np.abs(np.diag(Q) - 2.0 * np.einsum("ij,ij->j", vals[0], vals[0])).max() <= RTOL * scale
+    idx = rng.integers(0, n, size=(4000, 2))
+    ref = 2.0 * np.einsum("ij,ij->j", vals[0][:, idx[:, 0]], vals[0][:, idx[:, 1]])
+    assert np.abs(Q[idx[:, 0], idx[:, 1]] - ref).max() <= RTOL * scale
+    xs = rng.standard_normal(n)      # 1/2 x'Qx + q'x + c0 == ||Ax-b||^2   (test/model.jl:84)
+    lhs = 0.5 * xs @ Q @ xs + q @ xs + c0
+    rhs = float(np.sum((vals[0] @ xs - vals[1]) ** 2))
+    assert abs(lhs - rhs) <= 1e-9 * abs(rhs)
