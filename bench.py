@@ -3,7 +3,8 @@
 
 One "step" = one `update!`: every Parameter (A 4096x4096, b, C 1024x4096, d) re-evaluated once on the device
 (U[0,1) Philox, the stand-in for the reference's `rand!`, README.md:36-43) + one re-assembly of the objective
-(Q = 2A'A, q = -2A'b, c0 = b'b) and of the constraint block (C, -d), all resident in HBM.
+(Q = 2A'A, q = -2A'b, c0 = b'b) and of the constraint block (C, -d), all resident in HBM.  The Hessian contraction runs as exact
+int8 digit-plane products on the tcgen05 tensor cores when the per-instance error certificate allows (default mode), else in fp64.
 
   python bench.py [--gpus N --steps K --warmup W]              this implementation (one instance-shard per GPU, weak scaling)
   python bench.py --impl reference ...                          the reference's CPU path (literal term-list port, 1 thread)
@@ -29,6 +30,7 @@ N_VARS, K_ROWS, M_ROWS = 4096, 4096, 1024
 SEED = 1234
 METRIC = "QP re-parameterizations/sec (update!+coeff-assemble) at n=4096,m=1024"
 GRAM_DRAM_TRAFFIC_BYTES = 410174464 + 167363328    # ncu --set full, one launch of gram_tma_kernel<1,128> at cfg2
+GRAM_I8_DRAM_TRAFFIC_BYTES = None                   # filled from the ncu --set full capture of gram_i8_kernel<5,96> at cfg2
 AFFINE_DRAM_TRAFFIC_BYTES = 33626880 + 689664       # ncu --set full, one launch of affine_assemble_tma<0> at cfg2
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200: profiles/r01_probe_dmma.txt (mma.sync f64, all SMs)
 
@@ -246,10 +248,42 @@ def main():
         model.update()
     kt = model.kernel_times()
     model.enable_kernel_timing(False)
-    gram_ms = kt["gram_dmma"][0] / max(kt["gram_dmma"][1], 1)
+    levels = model.gram_level_counts()   # instances whose Hessian contraction ran with (5 int8 planes, 6 int8 planes, fp64)
+    per_launch = lambda key: kt[key][0] / max(kt[key][1], 1) if key in kt else 0.0
+    gram_ms = per_launch("gram_dmma")
+    i8_ms, slice_ms = per_launch("gram_i8_tcgen05"), per_launch("gram_i8_slice")
     aff_ms = kt["affine_assemble"][0] / max(kt["affine_assemble"][1], 1)
     peaks, peak_src = measured_peaks()
-    gram_tflops = st["gram_algorithmic_flops"] / (gram_ms * 1e-3) / 1e12
+    syrk_flops = K_ROWS * N_VARS * (N_VARS + 1)
+    if levels[0] + levels[1] > 0:
+        # dominant kernel: gram_i8_kernel<planes, BN> (tcgen05 kind::i8).  Algorithmic work = planes (planes + 1) / 2 exact int8 digit-plane
+        # products of the SYRK-counted contraction (k N (N + 1) ops each; redundant lower halves of diagonal tiles not counted)
+        planes = 5 if levels[0] else 6
+        nprod = planes * (planes + 1) // 2
+        i8_tops = nprod * syrk_flops / (i8_ms * 1e-3) / 1e12
+        i8_peak = 2.0 * peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        roofline = {"bound": "tensor", "kernel": f"gram_i8_kernel<{planes},{96 if planes == 5 else 80}> (Q = 2A'A as {nprod} exact int8 digit-plane products: "
+                                                 "TMA ring + tcgen05.mma kind::i8, int32 accumulators in TMEM)",
+                    "achieved": i8_tops, "peak": i8_peak, "unit": "TOP/s", "frac": i8_tops / i8_peak, "traffic": GRAM_I8_DRAM_TRAFFIC_BYTES,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_n_gram_i8_ncu_full.txt "
+                                      "(algorithmic: 101 MB of digit planes read + 134 MB of Q written)",
+                    "algorithmic_ops": int(nprod * syrk_flops), "avg_launch_ms": i8_ms,
+                    "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peak_src}): the int8 dense rate of tcgen05 is twice the bf16 rate "
+                                   "(4.5 vs 2.25 POP/s nominal); MEASURED_PEAKS.json has no int8 entry",
+                    "fp64_equivalent_tflops": syrk_flops / ((i8_ms + slice_ms) * 1e-3) / 1e12,
+                    "fp64_equivalent_note": f"SYRK-counted fp64 flops / (slice {slice_ms:.3f} ms + tcgen05 {i8_ms:.3f} ms); the fp64 DMMA pipe peaks at "
+                                            f"{FP64_DMMA_PEAK_TFLOPS} TFLOP/s (profiles/r01_probe_dmma.txt), the fp64 kernel reached 33 (profiles/r01_m_*)",
+                    "slice_kernel": {"avg_launch_ms": slice_ms, "algorithmic_bytes": 8 * K_ROWS * N_VARS + 6 * K_ROWS * N_VARS,
+                                     "achieved_gbs": (14 * K_ROWS * N_VARS) / (slice_ms * 1e-3) / 1e9 if slice_ms > 0 else None, "peak_gbs": peaks["hbm_gbs"]}}
+    else:
+        gram_tflops = st["gram_algorithmic_flops"] / (gram_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gram_tma_kernel<SYRK,128> (Q = 2A'A: TMA ring + warp-specialised fp64 DMMA)", "achieved": gram_tflops,
+                    "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gram_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": GRAM_DRAM_TRAFFIC_BYTES,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_e_gram_tma_ncu_full.txt "
+                                      "(algorithmic: 134 MB read of A + 134 MB write of Q)",
+                    "algorithmic_flops": int(st["gram_algorithmic_flops"]), "avg_launch_ms": gram_ms,
+                    "peak_source": "fp64 mma.sync (DMMA) peak measured on this pool's B200, profiles/r01_probe_dmma.txt; "
+                                   "MEASURED_PEAKS.json has no fp64 entry and tcgen05 has no f64 kind"}
     kernel_share = {k: v[0] / max(sum(x[0] for x in kt.values()), 1e-12) for k, v in kt.items()}
     # one affine-class launch per update here: the constraint block (16 B per stored coefficient + 16 B per row)
     aff_gbs = st["affine_algorithmic_bytes"] / (aff_ms * 1e-3) / 1e9 if aff_ms > 0 else None
@@ -310,13 +344,8 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(st["kernel_launches_per_update"]) * args.steps,
             "launches_per_update": int(st["kernel_launches_per_update"]), "cuda_graph": bool(st["uses_cuda_graph"]),
-            "roofline": {"bound": "tensor", "kernel": "gram_tma_kernel<SYRK,128> (Q = 2A'A: TMA ring + warp-specialised fp64 DMMA)", "achieved": gram_tflops,
-                         "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gram_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": GRAM_DRAM_TRAFFIC_BYTES,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_e_gram_tma_ncu_full.txt "
-                                           "(algorithmic: 134 MB read of A + 134 MB write of Q)",
-                         "algorithmic_flops": int(st["gram_algorithmic_flops"]), "avg_launch_ms": gram_ms,
-                         "peak_source": "fp64 mma.sync (DMMA) peak measured on this pool's B200, profiles/r01_probe_dmma.txt; "
-                                        "MEASURED_PEAKS.json has no fp64 entry and tcgen05 has no f64 kind"},
+            "roofline": roofline,
+            "gram_levels": {"int8_5_planes": levels[0], "int8_6_planes": levels[1], "fp64": levels[2]},
             "roofline_affine": {"bound": "hbm", "kernel": "affine_assemble_tma (C, -d): bulk-copy ring", "achieved": aff_gbs, "peak": peaks["hbm_gbs"],
                                 "unit": "GB/s", "frac": (aff_gbs / peaks["hbm_gbs"]) if aff_gbs else None, "traffic": AFFINE_DRAM_TRAFFIC_BYTES,
                                 "traffic_source": "profiles/r01_e_affine_tma_ncu_full.txt: 33.6 MB read; the 33.5 MB written stay in the 126 MB L2",

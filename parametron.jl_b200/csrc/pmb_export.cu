@@ -40,6 +40,8 @@ void plan_qp_pack(pmb_ctx* c) {
             gram_tma_applicable(gram->gram.X, gram->gram.ldx, gram->gram.x_bstride, gram->gram.k, gram->gram.n, nb)) {
             gram->gram.packed_dev = c->qp_Px;
             gram->gram.packed_bstride = c->qp_nnzP;
+            for (auto& st : c->steps)   // the int8-slice companion of the same contraction writes P_x from its own epilogue
+                if (st.type == ST_GRAM_I8_MMA && st.gram.H == c->Q) { st.gram.packed_dev = c->qp_Px; st.gram.packed_bstride = c->qp_nnzP; }
             c->qp_P_fused = true;
         } else {
             Step s;

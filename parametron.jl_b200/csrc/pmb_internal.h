@@ -128,11 +128,11 @@ struct Node {
     std::shared_ptr<QuadForm> quad;
 };
 
-enum KernelClass { KC_AFFINE = 0, KC_GRAM, KC_GEMM, KC_PHILOX, KC_H2D, KC_REDUCE, KC_MISC, KC_PACK, KC_COUNT };
+enum KernelClass { KC_AFFINE = 0, KC_GRAM, KC_GEMM, KC_PHILOX, KC_H2D, KC_REDUCE, KC_MISC, KC_PACK, KC_GRAM_I8, KC_GRAM_SLICE, KC_COUNT };
 
 enum StepType {
     ST_MEMSET, ST_LINCOMB, ST_TRANSPOSE, ST_GEMV, ST_DOT, ST_SPROD, ST_AFFINE, ST_GRAM, ST_GEMM,
-    ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM, ST_PROLOGUE, ST_GEMV_DOT, ST_PACK_P, ST_PACK_A
+    ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM, ST_PROLOGUE, ST_GEMV_DOT, ST_PACK_P, ST_PACK_A, ST_GRAM_I8_SLICE, ST_GRAM_I8_MMA
 };
 
 struct Step {

@@ -466,8 +466,16 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                 }
             }
             s.gram = ga;
-            s.i8 = i8;
             s.gscratch = make_gram_scratch(c, true, ga.k, ga.n, ga.n, nb);
+            if (i8.slices) {  // slice pass, then the 5- and 6-plane tcgen05 launches; the fp64 launch after them skips what they certified
+                Step sl;
+                sl.type = ST_GRAM_I8_SLICE; sl.cls = KC_GRAM_SLICE; sl.batch = nb; sl.gram = ga; sl.i8 = i8;
+                st.push_back(sl);
+                Step mm = sl;
+                mm.type = ST_GRAM_I8_MMA; mm.cls = KC_GRAM_I8;
+                st.push_back(mm);
+                s.i8 = i8;
+            }
             st.push_back(s);
             c->gram_flops += F.k * F.ncols * (F.ncols + 1) + 2 * F.k * F.ncols + 2 * F.k;
             // small (latency-bound) problems only: one launch fewer.  For large problems the extra work in the MMA loop costs more
@@ -625,10 +633,14 @@ static void run_step(pmb_ctx* c, const Step& s) {
         case ST_DOT: launch_dot(s.dot, s.batch, st); break;
         case ST_SPROD: launch_scalar_prod(s.out, s.out_bstride, s.scale, s.s0, s.s0_bs, s.s1, s.s1_bs, s.batch, st); break;
         case ST_AFFINE: launch_affine_assemble(s.aff, s.batch, c->sm_count, st); break;
+        case ST_GRAM_I8_SLICE:
+            if (!launch_gram_i8_slice(s.gram, s.i8, s.batch, c->sm_count, st)) fail(PMB_ECUDA, "int8-slice Gram: slice launch refused");
+            break;
+        case ST_GRAM_I8_MMA:
+            if (!launch_gram_i8_mma(s.gram, s.i8, s.batch, c->sm_count, st)) fail(PMB_ECUDA, "int8-slice Gram: tcgen05 launch refused");
+            break;
         case ST_GRAM:
-            if (s.i8.slices) {  // slice pass + 5- and 6-plane tcgen05 launches; the fp64 launch below skips what they certified
-                if (!launch_gram_i8_slice(s.gram, s.i8, s.batch, c->sm_count, st) || !launch_gram_i8_mma(s.gram, s.i8, s.batch, c->sm_count, st))
-                    fail(PMB_ECUDA, "int8-slice Gram launch refused");
+            if (s.i8.slices) {  // companion of the int8 steps: must be the TMA kernel, it is the one that skips certified instances
                 if (!launch_gram_syrk_tma(s.gram, s.gscratch, s.batch, c->sm_count, st)) fail(PMB_ECUDA, "fp64 Gram (TMA) launch refused");
                 break;
             }
@@ -755,7 +767,7 @@ void build_update_graph(pmb_ctx* ctx) {
 
 using namespace pmb;
 
-static const char* kClassNames[KC_COUNT] = {"affine_assemble", "gram_dmma", "gemm_tn_dmma", "philox_uniform", "h2d_stage", "reduce", "misc", "pack"};
+static const char* kClassNames[KC_COUNT] = {"affine_assemble", "gram_dmma", "gemm_tn_dmma", "philox_uniform", "h2d_stage", "reduce", "misc", "pack", "gram_i8_tcgen05", "gram_i8_slice"};
 
 extern "C" {
 
@@ -918,7 +930,7 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
     }
     ctx->launches_per_update = 0;
     ctx->memcpy_per_update = 0;
-    for (auto& s : ctx->steps) if (s.type != ST_MEMSET) ctx->launches_per_update += (s.type == ST_GRAM && s.i8.slices) ? (s.i8.force_ns ? 3 : 4) : 1;
+    for (auto& s : ctx->steps) if (s.type != ST_MEMSET) ctx->launches_per_update += (s.type == ST_GRAM_I8_MMA && !s.i8.force_ns) ? 2 : 1;
     for (auto& n : ctx->nodes) if (n.needed && n.nop == NOP_PARAM && n.pmode == PMB_PARAM_HOST) ctx->memcpy_per_update += 1;
     // constants: evaluated exactly once (constant folding lazyexpression.jl:189-192; isconstant moi_interop.jl:123,153)
     for (auto& s : ctx->init_steps) run_step(ctx, s);
