@@ -44,6 +44,7 @@ struct I8Cfg {
     static constexpr int kStageBytes = NS * (kITile + kJTile);
     static constexpr int kStages = (227 * 1024 - 2048) / kStageBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+    static constexpr int kGrp = 256 / BN;          // column-panel planes covered by one MMA (N = kGrp * BN <= 256)
     static_assert(NS * BN <= kI8TmemCols, "accumulators do not fit TMEM");
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "tcgen05 kind::i8, M = 128: N % 16 == 0");
     static_assert(kStages >= 2, "pipeline needs two stages");
@@ -145,6 +146,14 @@ struct GramI8SliceArgs {
     int8_t* slices;        // [batch][6][n][kp]
     double* sigma;         // [batch][n]
     unsigned long long* stats;
+    double tol;
+    // fused linear part of the least-squares objective (the pass reads X anyway):  q[map[j]] += qscale * sum_r X[r, j] g[r],
+    // c0 += cscale * sum_r g[r]^2 (by the group that owns column 0).  gvec == null: off
+    const double* gvec; int64_t g_bstride;
+    double* qout; int64_t q_bstride;
+    double* c0out;
+    const int32_t* map;
+    AlphaDev qscale, cscale;
 };
 
 __device__ __forceinline__ void load4(const double* x, int64_t r0, int64_t k, bool vec, double (&v)[4]) {
@@ -157,20 +166,28 @@ __device__ __forceinline__ void load4(const double* x, int64_t r0, int64_t k, bo
     }
 }
 
-// one warp per column: pass 1 = largest magnitude, sum of squares, 1-norm; pass 2 (re-read, L1/L2) = fixed-point digits
-__global__ void __launch_bounds__(256) gram_i8_slice_kernel(const GramI8SliceArgs a) {
-    constexpr int NP = kGramI8Planes;
-    const int lane = threadIdx.x & 31;
-    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
+// A group of T threads (one warp, or the whole CTA for long columns) owns one column of X at a time.  Columns of up to 16 T rows
+// stay in registers between the statistics pass (largest magnitude, 2-norm, 1-norm, X'g) and the digit pass: X is read ONCE.
+template <int T>
+__global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8SliceArgs a) {
+    constexpr int NP = kGramI8Planes, G = 256 / T, CIT = 4;   // CIT cached iterations of 4 rows per thread
+    __shared__ double red[8][5];
+    __shared__ unsigned int redu[8][NP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tig = threadIdx.x % T, grp = threadIdx.x / T;
     const bool vec = (a.ldx % 2 == 0) && (((uintptr_t)a.X & 15) == 0) && (a.x_bstride % 2 == 0);
-    for (int64_t c = wid; c < a.batch * a.n; c += nw) {
-        const int64_t inst = c / a.n, j = c - inst * a.n;
+    const bool gvecal = a.gvec && (((uintptr_t)a.gvec & 15) == 0) && (a.g_bstride % 2 == 0);
+    const bool cached = a.kp <= (int64_t)4 * T * CIT;
+    const int64_t total = a.batch * a.n;
+    for (int64_t c0 = (int64_t)blockIdx.x * G; c0 < total; c0 += (int64_t)gridDim.x * G) {   // uniform per CTA (block-wide barriers below)
+        const int64_t c = c0 + grp;
+        const bool live = c < total;
+        const int64_t inst = live ? c / a.n : 0, j = live ? c - inst * a.n : 0;
         const double* x = a.X + inst * a.x_bstride + j * a.ldx;
-        double amax = 0.0, ss = 0.0, l1 = 0.0;
+        const double* g = a.gvec ? a.gvec + inst * a.g_bstride : nullptr;
+        double vc[CIT][4];
+        double amax = 0.0, ss = 0.0, l1 = 0.0, dg = 0.0, gg = 0.0;
         bool bad = false;
-        for (int64_t r0 = (int64_t)lane * 4; r0 < a.k; r0 += 128) {
-            double v[4];
-            load4(x, r0, a.k, vec, v);
+        auto stat4 = [&](const double (&v)[4], int64_t r0) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const double av = fabs(v[e]);
@@ -179,13 +196,45 @@ __global__ void __launch_bounds__(256) gram_i8_slice_kernel(const GramI8SliceArg
                 l1 += av;
                 ss = fma(v[e], v[e], ss);
             }
+            if (g) {
+                double gv[4];
+                load4(g, r0, a.k, gvecal, gv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { dg = fma(v[e], gv[e], dg); gg = fma(gv[e], gv[e], gg); }
+            }
+        };
+        if (live) {
+            if (cached) {
+#pragma unroll
+                for (int it = 0; it < CIT; ++it) {
+                    const int64_t r0 = ((int64_t)it * T + tig) * 4;
+                    if (r0 < a.k) { load4(x, r0, a.k, vec, vc[it]); stat4(vc[it], r0); }
+                    else { vc[it][0] = vc[it][1] = vc[it][2] = vc[it][3] = 0.0; }
+                }
+            } else {
+                for (int64_t r0 = (int64_t)tig * 4; r0 < a.k; r0 += 4 * T) {
+                    double v[4];
+                    load4(x, r0, a.k, vec, v);
+                    stat4(v, r0);
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
             ss += __shfl_xor_sync(0xffffffffu, ss, o);
             l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+            dg += __shfl_xor_sync(0xffffffffu, dg, o);
+            gg += __shfl_xor_sync(0xffffffffu, gg, o);
             bad |= (bool)__shfl_xor_sync(0xffffffffu, (int)bad, o);
+        }
+        if (T == 256) {
+            if (lane == 0) { red[warp][0] = bad ? CUDART_INF : amax; red[warp][1] = ss; red[warp][2] = l1; red[warp][3] = dg; red[warp][4] = gg; }
+            __syncthreads();
+            amax = 0.0; ss = 0.0; l1 = 0.0; dg = 0.0; gg = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { amax = fmax(amax, red[w][0]); ss += red[w][1]; l1 += red[w][2]; dg += red[w][3]; gg += red[w][4]; }
+            bad = !(amax <= DBL_MAX);
         }
         if (amax > 0.0 && !(amax >= 1e-150 && amax <= 1e150)) bad = true;
         const bool zero = !(amax > 0.0) || bad;
@@ -195,9 +244,7 @@ __global__ void __launch_bounds__(256) gram_i8_slice_kernel(const GramI8SliceArg
         uint32_t dsq[NP];
 #pragma unroll
         for (int s = 0; s < NP; ++s) dsq[s] = 0u;
-        for (int64_t r0 = (int64_t)lane * 4; r0 < a.kp; r0 += 128) {
-            double v[4];
-            load4(x, r0, a.k, vec, v);
+        auto digits4 = [&](const double (&v)[4], int64_t r0) {
             uint32_t w[NP];
 #pragma unroll
             for (int s = 0; s < NP; ++s) w[s] = 0u;
@@ -216,12 +263,41 @@ __global__ void __launch_bounds__(256) gram_i8_slice_kernel(const GramI8SliceArg
             }
 #pragma unroll
             for (int s = 0; s < NP; ++s) *(uint32_t*)(dst + (int64_t)s * a.n * a.kp + r0) = w[s];
+        };
+        if (live) {
+            if (cached) {
+#pragma unroll
+                for (int it = 0; it < CIT; ++it) {
+                    const int64_t r0 = ((int64_t)it * T + tig) * 4;
+                    if (r0 < a.kp) digits4(vc[it], r0);
+                }
+            } else {
+                for (int64_t r0 = (int64_t)tig * 4; r0 < a.kp; r0 += 4 * T) {
+                    double v[4];
+                    load4(x, r0, a.k, vec, v);
+                    digits4(v, r0);
+                }
+            }
         }
 #pragma unroll
         for (int s = 0; s < NP; ++s)
 #pragma unroll
             for (int o = 16; o; o >>= 1) dsq[s] += __shfl_xor_sync(0xffffffffu, dsq[s], o);
-        if (lane == 0) {
+        if (T == 256) {
+            if (lane == 0) {
+#pragma unroll
+                for (int s = 0; s < NP; ++s) redu[warp][s] = dsq[s];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+                dsq[s] = 0u;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) dsq[s] += redu[w][s];
+            }
+            __syncthreads();   // red / redu are rewritten by the next column
+        }
+        if (live && tig == 0) {
             a.sigma[c] = sigma;
             unsigned long long* st = a.stats + inst * kGramI8StatsStride;
             if (bad) atomicMax(st, (unsigned long long)__double_as_longlong(CUDART_INF));
@@ -231,6 +307,20 @@ __global__ void __launch_bounds__(256) gram_i8_slice_kernel(const GramI8SliceArg
                 atomicMax(st + 2, (unsigned long long)__double_as_longlong(l1 / sigma));
 #pragma unroll
                 for (int s = 0; s < NP; ++s) atomicMax(st + 3 + s, (unsigned long long)dsq[s]);
+            }
+            if (g) {
+                const double qs = a.qscale.ptr ? a.qscale.c * a.qscale.ptr[inst * a.qscale.bstride] : a.qscale.c;
+                a.qout[inst * a.q_bstride + (a.map ? a.map[j] : j)] += qs * dg;
+                if (j == 0) {
+                    const double cs = a.cscale.ptr ? a.cscale.c * a.cscale.ptr[inst * a.cscale.bstride] : a.cscale.c;
+                    a.c0out[inst] += cs * gg;
+                }
+            }
+            // the group that finishes the instance's last column evaluates the certificate once for everybody
+            __threadfence();
+            if (atomicAdd(st + 14, 1ull) == (unsigned long long)(a.n - 1)) {
+                __threadfence();
+                st[15] = (unsigned long long)gram_i8_compute_level(st, a.tol);
             }
         }
     }
@@ -256,10 +346,15 @@ __device__ __forceinline__ I8Unit i8_decode(const GramI8KernelArgs& a, int64_t u
     return w;
 }
 
+// instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed int8 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24
+__device__ __forceinline__ constexpr uint32_t i8_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kI8BM >> 4) << 24);
+}
+
 // this launch (NS planes) owns the instance?
 template <int NS>
 __device__ __forceinline__ bool i8_runs(const GramI8KernelArgs& a, int64_t inst) {
-    return a.force_ns ? a.force_ns == NS : gram_i8_level(a.stats, inst, a.tol) == NS;
+    return a.force_ns ? a.force_ns == NS : gram_i8_level(a.stats, inst) == NS;
 }
 
 template <int NS, int BN>
@@ -275,6 +370,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ring = (i8::s_u32(smem_raw) + 1023u) & ~1023u;
     const int nkc = (int)(a.kp / kI8KC);
+    if (a.total_tiles == a.tiles_per_inst && !i8_runs<NS>(a, 0)) return;   // one instance and it is not ours: leave before touching TMEM
 
     if (tid == 0) {
 #pragma unroll
@@ -313,8 +409,6 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
     } else if (warp == 1) {
         // ===== MMA issuer: one thread, all digit-plane pairs with s + t <= NS - 1, level s + t -> TMEM columns [(s+t) BN, +BN) =====
         if (lane == 0) {
-            // instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed int8 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24
-            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kI8BM >> 4) << 24);
             uint32_t it = 0, tile_it = 0;
             for (int64_t u = blockIdx.x; u < a.total_tiles; u += gridDim.x) {
                 const I8Unit w = i8_decode<BN>(a, u);
@@ -328,14 +422,18 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                     const uint32_t stage = ring + (uint32_t)s * C::kStageBytes;
 #pragma unroll
                     for (int kk = 0; kk < kI8KC / 32; ++kk) {
+                        // plane s of the row panel against GRP consecutive planes t .. t+g-1 of the column panel in ONE instruction
+                        // (N = g BN): the planes are contiguous in shared memory and the levels s+t .. s+t+g-1 are adjacent TMEM column
+                        // blocks, so the row panel is read from shared memory 9 times per k step instead of 15 (21 for 6 planes).
+                        // Every level is first written by the s = 0 instructions (accumulate off at the first k step).
 #pragma unroll
-                        for (int lvl = 0; lvl < NS; ++lvl) {
+                        for (int si = 0; si < NS; ++si) {
+                            const uint64_t ad = i8::smem_desc_sw64(stage + si * C::kITile + kk * 32);
 #pragma unroll
-                            for (int si = 0; si <= lvl; ++si) {
-                                const int sj = lvl - si;
-                                const uint64_t ad = i8::smem_desc_sw64(stage + si * C::kITile + kk * 32);
+                            for (int sj = 0; sj <= NS - 1 - si; sj += C::kGrp) {
+                                const int gsz = (NS - si - sj) < C::kGrp ? (NS - si - sj) : C::kGrp;
                                 const uint64_t bd = i8::smem_desc_sw64(stage + NS * C::kITile + sj * C::kJTile + kk * 32);
-                                i8::mma_i8(tmem_base + (uint32_t)(lvl * BN), ad, bd, idesc, (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
+                                i8::mma_i8(tmem_base + (uint32_t)((si + sj) * BN), ad, bd, i8_idesc(gsz * BN), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
                             }
                         }
                     }
@@ -372,30 +470,55 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
             i8::mb_wait(&tmem_full_bar, tile_it & 1);
             i8::tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            // interior tile (strictly above the diagonal, no ragged edge), identity map, overwrite: unpredicated stores -- the direct
+            // triangle coalesces across the lanes (consecutive rows), the mirrored one is 16 consecutive doubles per thread (4 x 256-bit)
+            const bool fast = !a.map && !a.accumulate && i0 + kI8BM <= j0 && j0 + BN <= a.n && (a.ldo & 3) == 0 && (a.o_bstride & 3) == 0 &&
+                              (((uintptr_t)a.out) & 31) == 0;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 int32_t acc[NS][16];
 #pragma unroll
                 for (int l = 0; l < NS; ++l) i8::tmem_ld16(trow + (uint32_t)(l * BN + c0), acc[l]);
                 i8::tmem_ld_wait();
+                double v[16];
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
                     double t = (double)acc[0][jj];
 #pragma unroll
                     for (int l = 1; l < NS; ++l) t = fma(t, 256.0, (double)acc[l][jj]);
+                    v[jj] = t * fi * sfj[c0 + jj];
+                }
+                if (fast) {
+                    double* p1 = out + gi + (j0 + c0) * a.ldo;
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) p1[(int64_t)jj * a.ldo] = v[jj];
+                    double* p2 = out + (j0 + c0) + gi * a.ldo;
+#pragma unroll
+                    for (int jj = 0; jj < 16; jj += 4)
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p2 + jj), "d"(v[jj]), "d"(v[jj + 1]), "d"(v[jj + 2]), "d"(v[jj + 3]) : "memory");
+                    if (pk) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const int64_t gj = j0 + c0 + jj;
+                            pk[gj * (gj + 1) / 2 + gi] = v[jj];
+                        }
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
                     const int64_t gj = j0 + c0 + jj;
                     if (row_ok && gj < a.n && gi <= gj) {   // every unordered pair of columns exactly once
-                        const double v = t * fi * sfj[c0 + jj];
                         const int64_t on = mapj[c0 + jj];
                         double* p1 = out + om + on * a.ldo;
-                        if (a.accumulate) *p1 += v; else *p1 = v;
+                        if (a.accumulate) *p1 += v[jj]; else *p1 = v[jj];
                         if (gi != gj) {
                             double* p2 = out + on + om * a.ldo;
-                            if (a.accumulate) *p2 += v; else *p2 = v;
+                            if (a.accumulate) *p2 += v[jj]; else *p2 = v[jj];
                         }
                         if (pk) {
                             const int64_t lo = om < on ? om : on, hi = om < on ? on : om;
-                            pk[hi * (hi + 1) / 2 + lo] = v;
+                            pk[hi * (hi + 1) / 2 + lo] = v[jj];
                         }
                     }
                 }
@@ -462,10 +585,19 @@ bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t ba
     cudaMemsetAsync(sc.stats, 0, sizeof(unsigned long long) * kGramI8StatsStride * (size_t)batch, stream);
     GramI8SliceArgs s{};
     s.X = g.X; s.ldx = g.ldx; s.x_bstride = g.x_bstride; s.k = g.k; s.kp = sc.plan.kp; s.n = g.n; s.batch = batch;
-    s.slices = sc.slices; s.sigma = sc.sigma; s.stats = sc.stats;
+    s.slices = sc.slices; s.sigma = sc.sigma; s.stats = sc.stats; s.tol = sc.tol;
+    if (g.gvec) {
+        s.gvec = g.gvec; s.g_bstride = g.g_bstride; s.qout = g.qout; s.q_bstride = g.q_bstride; s.c0out = g.c0out; s.map = g.map;
+        s.qscale = g.qscale; s.cscale = g.cscale;
+    }
     const int64_t cols = batch * g.n;
-    const int sgrid = (int)std::min<int64_t>((cols + 7) / 8, (int64_t)sm_count * 8);
-    gram_i8_slice_kernel<<<sgrid, 256, 0, stream>>>(s);
+    if (sc.plan.kp > 1024) {   // long columns: the whole CTA owns one column (up to 4096 rows cached in registers)
+        const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * 4);
+        gram_i8_slice_kernel<256><<<sgrid, 256, 0, stream>>>(s);
+    } else {
+        const int sgrid = (int)std::min<int64_t>((cols + 7) / 8, (int64_t)sm_count * 4);
+        gram_i8_slice_kernel<32><<<sgrid, 256, 0, stream>>>(s);
+    }
     return true;
 }
 
@@ -489,7 +621,7 @@ static bool launch_i8_impl(const GramArgs& g, const GramI8Scratch& sc, int64_t b
 
 __global__ void gram_i8_count_levels_kernel(const unsigned long long* stats, double tol, int force_ns, int64_t batch, unsigned long long* counts) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < batch; i += (int64_t)gridDim.x * blockDim.x) {
-        const int lv = force_ns ? force_ns : gram_i8_level(stats, i, tol);
+        const int lv = force_ns ? force_ns : gram_i8_level(stats, i);
         atomicAdd(counts + (lv == 5 ? 0 : lv == 6 ? 1 : 2), 1ull);
     }
 }

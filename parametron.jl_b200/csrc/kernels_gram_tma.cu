@@ -103,7 +103,7 @@ __device__ __forceinline__ void dmma_16x8x4(double (&c)[4], double a0, double a1
 }
 // the certified int8-slice kernels (kernels_gram_i8.cu) own this instance: nothing to do here
 __device__ __forceinline__ bool skip_certified(const GramTmaKernelArgs& a, int64_t inst) {
-    return a.cert_stats && (a.cert_force || gram_i8_level(a.cert_stats, inst, a.cert_tol) != 0);
+    return a.cert_stats && (a.cert_force || gram_i8_level(a.cert_stats, inst) != 0);
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTConsumerWarps * 32) : "memory"); }
 
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
     const uint32_t gring = ring + (uint32_t)kTStages * 2 * kTBM * kTKT * 8;  // 128-byte slots: 16 entries of gvec per stage
     constexpr bool fuse_q = SYRK && FUSEQ;  // compiled out of the large-problem instantiations: it costs MMA-loop scheduling freedom
 
+    if (SYRK && a.total_tiles == a.tiles_per_inst && skip_certified(a, 0)) return;   // one instance, owned by the int8 path: nothing to do
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kTStages; ++s) { mb_init(&full_bar[s], 1); mb_init(&empty_bar[s], kTConsumerWarps); }

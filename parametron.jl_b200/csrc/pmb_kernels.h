@@ -151,20 +151,21 @@ bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k
 //   [0] bits of max_j sigma_j (0: every column is zero; +inf: non-finite or out-of-range data)   [1] bits of max_j ||x_j||_2^2
 //   [2] bits of max_j ||x_j / sigma_j||_1                                                          [3 + s] max_j sum_r d_s[r, j]^2
 constexpr int kGramI8Planes = 6;
-constexpr int kGramI8StatsStride = 16;
+constexpr int kGramI8StatsStride = 16;   // [14] columns sliced so far (arrival counter), [15] the certificate's verdict: planes (5 / 6) or 0 = fp64
 #ifdef __CUDACC__
 // Number of digit planes (5 or 6) whose worst-case error -- representation error of the planes used plus every dropped digit
 // product, bounded with the measured column norms -- is below tol * max |H| (max |H| of a Gram matrix = its largest diagonal entry);
-// 0: not certifiable, the fp64 DMMA kernel computes this instance.
-__device__ __forceinline__ int gram_i8_level(const unsigned long long* stats, int64_t inst, double tol) {
-    const unsigned long long* st = stats + inst * kGramI8StatsStride;
-    if (st[0] == 0ull) return 5;                       // all-zero operand: every digit is zero
-    const double sig = __longlong_as_double((long long)st[0]);
+// 0: not certifiable, the fp64 DMMA kernel computes this instance.  Evaluated ONCE per instance and update by the slice kernel
+// (the warp that slices the instance's last column) and stored in stats[15].
+__device__ __forceinline__ int gram_i8_compute_level(const unsigned long long* st, double tol) {
+    const unsigned long long s0 = __ldcg(st);
+    if (s0 == 0ull) return 5;                       // all-zero operand: every digit is zero
+    const double sig = __longlong_as_double((long long)s0);
     if (!(sig < 1e200)) return 0;
-    const double ss = __longlong_as_double((long long)st[1]), l1 = __longlong_as_double((long long)st[2]);
+    const double ss = __longlong_as_double((long long)__ldcg(st + 1)), l1 = __longlong_as_double((long long)__ldcg(st + 2));
     double R[kGramI8Planes];
 #pragma unroll
-    for (int s = 0; s < kGramI8Planes; ++s) R[s] = sqrt((double)st[3 + s]);
+    for (int s = 0; s < kGramI8Planes; ++s) R[s] = sqrt((double)__ldcg(st + 3 + s));
 #pragma unroll
     for (int ns = 5; ns <= kGramI8Planes; ++ns) {
         double by = 2.0 * 1.1 * exp2(-8.0 * ns) * l1;  // sum_r (|y_ri| + |y_rj|) * |representation error|
@@ -176,6 +177,9 @@ __device__ __forceinline__ int gram_i8_level(const unsigned long long* stats, in
         if (1.01 * sig * sig * by <= tol * ss) return ns;
     }
     return 0;
+}
+__device__ __forceinline__ int gram_i8_level(const unsigned long long* stats, int64_t inst) {
+    return (int)stats[inst * kGramI8StatsStride + 15];
 }
 #endif
 struct GramI8Plan {

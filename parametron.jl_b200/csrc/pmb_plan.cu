@@ -470,9 +470,13 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
             if (i8.slices) {  // slice pass, then the 5- and 6-plane tcgen05 launches; the fp64 launch after them skips what they certified
                 Step sl;
                 sl.type = ST_GRAM_I8_SLICE; sl.cls = KC_GRAM_SLICE; sl.batch = nb; sl.gram = ga; sl.i8 = i8;
+                if (F.g) {  // the slice pass reads X anyway: q[map] += 2 a cx cg X'g and c0 += a cg^2 g.g ride along (no gemv + dot launch)
+                    sl.gram.gvec = F.g; sl.gram.g_bstride = F.gbs; sl.gram.qout = T.q; sl.gram.q_bstride = N; sl.gram.c0out = T.c0;
+                    sl.gram.qscale = scaled(a, 2.0 * F.cx * F.cg); sl.gram.cscale = scaled(a, F.cg * F.cg);
+                }
                 st.push_back(sl);
-                Step mm = sl;
-                mm.type = ST_GRAM_I8_MMA; mm.cls = KC_GRAM_I8;
+                Step mm;
+                mm.type = ST_GRAM_I8_MMA; mm.cls = KC_GRAM_I8; mm.batch = nb; mm.gram = ga; mm.i8 = i8;
                 st.push_back(mm);
                 s.i8 = i8;
             }
@@ -488,7 +492,7 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                 Step& gs = st.back();
                 gs.gram.gvec = F.g; gs.gram.g_bstride = F.gbs; gs.gram.qout = T.q; gs.gram.q_bstride = N; gs.gram.c0out = T.c0;
                 gs.gram.qscale = scaled(a, 2.0 * F.cx * F.cg); gs.gram.cscale = scaled(a, F.cg * F.cg);
-            } else if (F.g) {
+            } else if (F.g && !i8.slices) {
                 Step v;
                 v.type = ST_GEMV; v.cls = KC_REDUCE; v.batch = nb;
                 GemvArgs g{};
