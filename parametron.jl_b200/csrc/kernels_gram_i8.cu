@@ -95,6 +95,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap
                  "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(s_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gmem_src),
+                 "r"(bytes), "r"(s_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
@@ -168,11 +173,65 @@ __device__ __forceinline__ void load4(const double* x, int64_t r0, int64_t k, bo
 
 // A group of T threads (one warp, or the whole CTA for long columns) owns one column of X at a time.  Columns of up to 16 T rows
 // stay in registers between the statistics pass (largest magnitude, 2-norm, 1-norm, X'g) and the digit pass: X is read ONCE.
-template <int T>
+// RING (T = 256, columns of at most 4096 rows, 16-byte aligned): the columns travel global -> shared memory as 1-D bulk copies
+// (cp.async.bulk on an mbarrier, SASS UBLKCP) three columns ahead of the arithmetic, so the HBM latency is off the dependent chain
+// load -> reduce -> digits -> store of a column.
+constexpr int kI8SliceRing = 3;
+template <int T, bool RING>
 __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8SliceArgs a) {
     constexpr int NP = kGramI8Planes, G = 256 / T, CIT = 4;   // CIT cached iterations of 4 rows per thread
+    static_assert(!RING || T == 256, "the ring feeds one column per CTA");
+    extern __shared__ __align__(128) unsigned char slice_smem[];
+    __shared__ __align__(8) uint64_t ring_full[kI8SliceRing];
     __shared__ double red[8][5];
     __shared__ unsigned int redu[8][NP];
+    const int64_t kpe = (a.k + 1) / 2 * 2;   // rows copied per column (ld is even on this path, so the pad row exists)
+    if (RING) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < kI8SliceRing; ++s) i8::mb_init(&ring_full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int s = 0; s < kI8SliceRing; ++s) {
+                const int64_t c = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+                if (c < a.batch * a.n) {
+                    const int64_t inst = c / a.n, j = c - inst * a.n;
+                    i8::mb_expect_tx(&ring_full[s], (uint32_t)(kpe * 8));
+                    i8::bulk_load_1d(i8::s_u32(slice_smem) + (uint32_t)(s * kpe * 8), a.X + inst * a.x_bstride + j * a.ldx, (uint32_t)(kpe * 8), &ring_full[s]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    uint32_t ring_it = 0;
+    // per-group running statistics (thread tig == 0 only)
+    int64_t acc_inst = 0;
+    unsigned long long acc_n = 0;
+    bool acc_bad = false;
+    double acc_sig = 0.0, acc_ss = 0.0, acc_l1 = 0.0;
+    uint32_t acc_dsq[NP];
+#pragma unroll
+    for (int s = 0; s < NP; ++s) acc_dsq[s] = 0u;
+    auto flush = [&]() {
+        if (!acc_n) return;
+        unsigned long long* st = a.stats + acc_inst * kGramI8StatsStride;
+        if (acc_bad) atomicMax(st, (unsigned long long)__double_as_longlong(CUDART_INF));
+        else if (acc_sig > 0.0) {
+            atomicMax(st, (unsigned long long)__double_as_longlong(acc_sig));
+            atomicMax(st + 1, (unsigned long long)__double_as_longlong(acc_ss));
+            atomicMax(st + 2, (unsigned long long)__double_as_longlong(acc_l1));
+#pragma unroll
+            for (int s = 0; s < NP; ++s) atomicMax(st + 3 + s, (unsigned long long)acc_dsq[s]);
+        }
+        // the group that completes the instance's column count evaluates the certificate once for everybody
+        __threadfence();
+        if (atomicAdd(st + 14, acc_n) + acc_n == (unsigned long long)a.n) {
+            __threadfence();
+            st[15] = (unsigned long long)gram_i8_compute_level(st, a.tol);
+        }
+        acc_n = 0; acc_bad = false; acc_sig = 0.0; acc_ss = 0.0; acc_l1 = 0.0;
+#pragma unroll
+        for (int s = 0; s < NP; ++s) acc_dsq[s] = 0u;
+    };
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tig = threadIdx.x % T, grp = threadIdx.x / T;
     const bool vec = (a.ldx % 2 == 0) && (((uintptr_t)a.X & 15) == 0) && (a.x_bstride % 2 == 0);
     const bool gvecal = a.gvec && (((uintptr_t)a.gvec & 15) == 0) && (a.g_bstride % 2 == 0);
@@ -184,6 +243,9 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
         const int64_t inst = live ? c / a.n : 0, j = live ? c - inst * a.n : 0;
         const double* x = a.X + inst * a.x_bstride + j * a.ldx;
         const double* g = a.gvec ? a.gvec + inst * a.g_bstride : nullptr;
+        const int rs = (int)(ring_it % kI8SliceRing);
+        const double* xs = (const double*)slice_smem + (int64_t)rs * kpe;
+        if (RING) i8::mb_wait(&ring_full[rs], (ring_it / kI8SliceRing) & 1);
         double vc[CIT][4];
         double amax = 0.0, ss = 0.0, l1 = 0.0, dg = 0.0, gg = 0.0;
         bool bad = false;
@@ -208,7 +270,15 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
 #pragma unroll
                 for (int it = 0; it < CIT; ++it) {
                     const int64_t r0 = ((int64_t)it * T + tig) * 4;
-                    if (r0 < a.k) { load4(x, r0, a.k, vec, vc[it]); stat4(vc[it], r0); }
+                    if (r0 < a.k) {
+                        if (RING) {
+                            const double2 p = *(const double2*)(xs + r0), q = *(const double2*)(xs + r0 + 2);   // r0 + 3 < kpe + 2 <= slot + pad
+                            vc[it][0] = p.x; vc[it][1] = r0 + 1 < a.k ? p.y : 0.0; vc[it][2] = r0 + 2 < a.k ? q.x : 0.0; vc[it][3] = r0 + 3 < a.k ? q.y : 0.0;
+                        } else {
+                            load4(x, r0, a.k, vec, vc[it]);
+                        }
+                        stat4(vc[it], r0);
+                    }
                     else { vc[it][0] = vc[it][1] = vc[it][2] = vc[it][3] = 0.0; }
                 }
             } else {
@@ -231,6 +301,15 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
         if (T == 256) {
             if (lane == 0) { red[warp][0] = bad ? CUDART_INF : amax; red[warp][1] = ss; red[warp][2] = l1; red[warp][3] = dg; red[warp][4] = gg; }
             __syncthreads();
+            if (RING && threadIdx.x == 0) {   // every thread holds its rows in registers: the slot can take the column 3 ahead
+                const int64_t cn = c0 + (int64_t)kI8SliceRing * gridDim.x;
+                if (cn < total) {
+                    const int64_t in2 = cn / a.n, j2 = cn - in2 * a.n;
+                    i8::mb_expect_tx(&ring_full[rs], (uint32_t)(kpe * 8));
+                    i8::bulk_load_1d(i8::s_u32(slice_smem) + (uint32_t)(rs * kpe * 8), a.X + in2 * a.x_bstride + j2 * a.ldx, (uint32_t)(kpe * 8), &ring_full[rs]);
+                }
+            }
+            ++ring_it;
             amax = 0.0; ss = 0.0; l1 = 0.0; dg = 0.0; gg = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) { amax = fmax(amax, red[w][0]); ss += red[w][1]; l1 += red[w][2]; dg += red[w][3]; gg += red[w][4]; }
@@ -244,25 +323,27 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
         uint32_t dsq[NP];
 #pragma unroll
         for (int s = 0; s < NP; ++s) dsq[s] = 0u;
+        // Balanced base-256 digits of the 48-bit two's-complement integer X without a carry chain: adding 0x80 to each of the five low
+        // bytes turns byte s of the sum into (digit + 128), XOR 0x80 maps that to the digit's int8 bit pattern; the top byte is the
+        // (signed) leading digit.  Byte b of the result belongs to plane 5 - b.  Four rows are transposed into one 32-bit word per plane
+        // with byte permutes; sum d^2 per plane is one dp4a.
         auto digits4 = [&](const double (&v)[4], int64_t r0) {
-            uint32_t w[NP];
-#pragma unroll
-            for (int s = 0; s < NP; ++s) w[s] = 0u;
+            uint32_t lo[4], hi[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                long long X = zero ? 0ll : __double2ll_rn(v[t] * mult);
-#pragma unroll
-                for (int s = NP - 1; s >= 1; --s) {
-                    const int d = (int)(signed char)(X & 0xFF);
-                    w[s] |= (uint32_t)(d & 0xFF) << (8 * t);
-                    dsq[s] += (uint32_t)(d * d);
-                    X = (X - d) >> 8;
-                }
-                w[0] |= (uint32_t)((int)X & 0xFF) << (8 * t);
-                dsq[0] += (uint32_t)((int)X * (int)X);
+                const long long X = zero ? 0ll : __double2ll_rn(v[t] * mult);
+                const unsigned long long Y = ((unsigned long long)X + 0x0000008080808080ull) ^ 0x0000008080808080ull;
+                lo[t] = (uint32_t)Y; hi[t] = (uint32_t)(Y >> 32);
             }
 #pragma unroll
-            for (int s = 0; s < NP; ++s) *(uint32_t*)(dst + (int64_t)s * a.n * a.kp + r0) = w[s];
+            for (int p = 0; p < NP; ++p) {
+                const int bidx = (NP - 1 - p) & 3;
+                const uint32_t* src = (NP - 1 - p) < 4 ? lo : hi;
+                const uint32_t sel = (uint32_t)bidx | ((uint32_t)(4 + bidx) << 4);
+                const uint32_t w = __byte_perm(__byte_perm(src[0], src[1], sel), __byte_perm(src[2], src[3], sel), 0x5410);
+                dsq[p] = (uint32_t)__dp4a((int)w, (int)w, (int)dsq[p]);
+                *(uint32_t*)(dst + (int64_t)p * a.n * a.kp + r0) = w;
+            }
         };
         if (live) {
             if (cached) {
@@ -299,31 +380,26 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
         }
         if (live && tig == 0) {
             a.sigma[c] = sigma;
-            unsigned long long* st = a.stats + inst * kGramI8StatsStride;
-            if (bad) atomicMax(st, (unsigned long long)__double_as_longlong(CUDART_INF));
-            else if (amax > 0.0) {
-                atomicMax(st, (unsigned long long)__double_as_longlong(sigma));
-                atomicMax(st + 1, (unsigned long long)__double_as_longlong(ss));
-                atomicMax(st + 2, (unsigned long long)__double_as_longlong(l1 / sigma));
-#pragma unroll
-                for (int s = 0; s < NP; ++s) atomicMax(st + 3 + s, (unsigned long long)dsq[s]);
-            }
             if (g) {
                 const double qs = a.qscale.ptr ? a.qscale.c * a.qscale.ptr[inst * a.qscale.bstride] : a.qscale.c;
-                a.qout[inst * a.q_bstride + (a.map ? a.map[j] : j)] += qs * dg;
+                atomicAdd(a.qout + inst * a.q_bstride + (a.map ? a.map[j] : j), qs * dg);   // one writer per entry: a fire-and-forget reduction
                 if (j == 0) {
                     const double cs = a.cscale.ptr ? a.cscale.c * a.cscale.ptr[inst * a.cscale.bstride] : a.cscale.c;
-                    a.c0out[inst] += cs * gg;
+                    atomicAdd(a.c0out + inst, cs * gg);
                 }
             }
-            // the group that finishes the instance's last column evaluates the certificate once for everybody
-            __threadfence();
-            if (atomicAdd(st + 14, 1ull) == (unsigned long long)(a.n - 1)) {
-                __threadfence();
-                st[15] = (unsigned long long)gram_i8_compute_level(st, a.tol);
+            // running maxima of this group's columns; the global atomics happen once per (group, instance), not once per column
+            if (acc_n && acc_inst != inst) flush();
+            acc_inst = inst; ++acc_n;
+            if (bad) acc_bad = true;
+            else if (amax > 0.0) {
+                acc_sig = fmax(acc_sig, sigma); acc_ss = fmax(acc_ss, ss); acc_l1 = fmax(acc_l1, l1 / sigma);
+#pragma unroll
+                for (int s = 0; s < NP; ++s) acc_dsq[s] = acc_dsq[s] > dsq[s] ? acc_dsq[s] : dsq[s];
             }
         }
     }
+    if (tig == 0) flush();
 }
 
 // ---- Gram kernel ---------------------------------------------------------------------------------------------------------------
@@ -578,6 +654,7 @@ GramI8Plan plan_gram_i8(int64_t k, int64_t n, int64_t batch) {
 void configure_gram_i8_kernels() {
     cudaFuncSetAttribute(gram_i8_kernel<5, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 96>::kSmemBytes);
     cudaFuncSetAttribute(gram_i8_kernel<6, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6, 80>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_slice_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SliceRing * 4096 * 8 + 64);
 }
 
 bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
@@ -591,12 +668,17 @@ bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t ba
         s.qscale = g.qscale; s.cscale = g.cscale;
     }
     const int64_t cols = batch * g.n;
-    if (sc.plan.kp > 1024) {   // long columns: the whole CTA owns one column (up to 4096 rows cached in registers)
+    const bool aligned = g.ldx % 2 == 0 && (((uintptr_t)g.X) & 15) == 0 && g.x_bstride % 2 == 0;
+    if (sc.plan.kp > 1024 && sc.plan.kp <= 4096 && aligned && !getenv("PMB_I8_NO_RING")) {   // bulk-copy ring, 2 CTAs per SM
+        const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * 2);
+        const size_t smem = (size_t)kI8SliceRing * (size_t)((g.k + 1) / 2 * 2) * 8 + 64;
+        gram_i8_slice_kernel<256, true><<<sgrid, 256, smem, stream>>>(s);
+    } else if (sc.plan.kp > 1024) {   // long columns: the whole CTA owns one column (up to 4096 rows cached in registers)
         const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * 4);
-        gram_i8_slice_kernel<256><<<sgrid, 256, 0, stream>>>(s);
+        gram_i8_slice_kernel<256, false><<<sgrid, 256, 0, stream>>>(s);
     } else {
         const int sgrid = (int)std::min<int64_t>((cols + 7) / 8, (int64_t)sm_count * 4);
-        gram_i8_slice_kernel<32><<<sgrid, 256, 0, stream>>>(s);
+        gram_i8_slice_kernel<32, false><<<sgrid, 256, 0, stream>>>(s);
     }
     return true;
 }
