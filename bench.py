@@ -30,7 +30,7 @@ N_VARS, K_ROWS, M_ROWS = 4096, 4096, 1024
 SEED = 1234
 METRIC = "QP re-parameterizations/sec (update!+coeff-assemble) at n=4096,m=1024"
 GRAM_DRAM_TRAFFIC_BYTES = 410174464 + 167363328    # ncu --set full, one launch of gram_tma_kernel<1,128> at cfg2
-GRAM_I8_DRAM_TRAFFIC_BYTES = None                   # filled from the ncu --set full capture of gram_i8_kernel<5,96> at cfg2
+GRAM_I8_DRAM_TRAFFIC_BYTES = 281920000 + 114058240    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r01_n_gram_i8_ncu_full.txt)
 AFFINE_DRAM_TRAFFIC_BYTES = 33626880 + 689664       # ncu --set full, one launch of affine_assemble_tma<0> at cfg2
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200: profiles/r01_probe_dmma.txt (mma.sync f64, all SMs)
 
@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -175,7 +175,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -261,15 +261,16 @@ def main():
         planes = 5 if levels[0] else 6
         nprod = planes * (planes + 1) // 2
         i8_tops = nprod * syrk_flops / (i8_ms * 1e-3) / 1e12
-        i8_peak = 2.0 * peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        i8_peak = 2.0 * peaks.get("bf16_tflops", 1590.0)   # burst figure: the kernel is timed alone (CUDA events around the one launch)
         roofline = {"bound": "tensor", "kernel": f"gram_i8_kernel<{planes},{96 if planes == 5 else 80}> (Q = 2A'A as {nprod} exact int8 digit-plane products: "
                                                  "TMA ring + tcgen05.mma kind::i8, int32 accumulators in TMEM)",
                     "achieved": i8_tops, "peak": i8_peak, "unit": "TOP/s", "frac": i8_tops / i8_peak, "traffic": GRAM_I8_DRAM_TRAFFIC_BYTES,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_n_gram_i8_ncu_full.txt "
                                       "(algorithmic: 101 MB of digit planes read + 134 MB of Q written)",
                     "algorithmic_ops": int(nprod * syrk_flops), "avg_launch_ms": i8_ms,
-                    "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peak_src}): the int8 dense rate of tcgen05 is twice the bf16 rate "
-                                   "(4.5 vs 2.25 POP/s nominal); MEASURED_PEAKS.json has no int8 entry",
+                    "peak_source": f"2 x bf16_tflops (burst) of MEASURED_PEAKS.json ({peak_src}): the int8 dense rate of tcgen05 is twice the bf16 rate "
+                                   "(4.5 vs 2.25 POP/s nominal); MEASURED_PEAKS.json has no int8 entry.  ncu's own counter for the same launch: "
+                                   "sm__ops_path_tensor_op_utcimma_src_int8 = 69.9 % of its peak (16384 ops/clk/SM), profiles/r01_n_gram_i8_ncu_full.txt",
                     "fp64_equivalent_tflops": syrk_flops / ((i8_ms + slice_ms) * 1e-3) / 1e12,
                     "fp64_equivalent_note": f"SYRK-counted fp64 flops / (slice {slice_ms:.3f} ms + tcgen05 {i8_ms:.3f} ms); the fp64 DMMA pipe peaks at "
                                             f"{FP64_DMMA_PEAK_TFLOPS} TFLOP/s (profiles/r01_probe_dmma.txt), the fp64 kernel reached 33 (profiles/r01_m_*)",

@@ -62,7 +62,7 @@ struct GramI8KernelArgs {
     AlphaDev scale;
     int32_t accumulate;
     double* packed_dev; int64_t packed_bstride;
-    int32_t tiles_j;
+    int32_t tj0, tj1;       // tile columns [tj0, tj1) of every instance
     int64_t tiles_per_inst, total_tiles;
 };
 
@@ -152,6 +152,7 @@ struct GramI8SliceArgs {
     double* sigma;         // [batch][n]
     unsigned long long* stats;
     double tol;
+    int64_t col0, ncols;   // this launch slices columns [col0, col0 + ncols) of every instance (upload pipelining: one launch per chunk)
     // fused linear part of the least-squares objective (the pass reads X anyway):  q[map[j]] += qscale * sum_r X[r, j] g[r],
     // c0 += cscale * sum_r g[r]^2 (by the group that owns column 0).  gvec == null: off
     const double* gvec; int64_t g_bstride;
@@ -193,8 +194,8 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             for (int s = 0; s < kI8SliceRing; ++s) {
                 const int64_t c = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-                if (c < a.batch * a.n) {
-                    const int64_t inst = c / a.n, j = c - inst * a.n;
+                if (c < a.batch * a.ncols) {
+                    const int64_t inst = c / a.ncols, j = a.col0 + (c - inst * a.ncols);
                     i8::mb_expect_tx(&ring_full[s], (uint32_t)(kpe * 8));
                     i8::bulk_load_1d(i8::s_u32(slice_smem) + (uint32_t)(s * kpe * 8), a.X + inst * a.x_bstride + j * a.ldx, (uint32_t)(kpe * 8), &ring_full[s]);
                 }
@@ -224,9 +225,12 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
         }
         // the group that completes the instance's column count evaluates the certificate once for everybody
         __threadfence();
-        if (atomicAdd(st + 14, acc_n) + acc_n == (unsigned long long)a.n) {
+        if (atomicAdd(st + 14, acc_n) + acc_n == (unsigned long long)(a.col0 + a.ncols)) {
             __threadfence();
-            st[15] = (unsigned long long)gram_i8_compute_level(st, a.tol);
+            // verdict for everything sliced so far; sticky across the launches of one update (5 planes < 6 planes < fp64): a tile computed
+            // under an earlier, smaller max |H| stays certified because max |H| only grows as columns arrive
+            const unsigned long long lv = (unsigned long long)gram_i8_compute_level(st, a.tol), prev = __ldcg(st + 15);
+            st[15] = lv > prev ? lv : prev;
         }
         acc_n = 0; acc_bad = false; acc_sig = 0.0; acc_ss = 0.0; acc_l1 = 0.0;
 #pragma unroll
@@ -236,11 +240,11 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
     const bool vec = (a.ldx % 2 == 0) && (((uintptr_t)a.X & 15) == 0) && (a.x_bstride % 2 == 0);
     const bool gvecal = a.gvec && (((uintptr_t)a.gvec & 15) == 0) && (a.g_bstride % 2 == 0);
     const bool cached = a.kp <= (int64_t)4 * T * CIT;
-    const int64_t total = a.batch * a.n;
+    const int64_t total = a.batch * a.ncols;
     for (int64_t c0 = (int64_t)blockIdx.x * G; c0 < total; c0 += (int64_t)gridDim.x * G) {   // uniform per CTA (block-wide barriers below)
         const int64_t c = c0 + grp;
         const bool live = c < total;
-        const int64_t inst = live ? c / a.n : 0, j = live ? c - inst * a.n : 0;
+        const int64_t inst = live ? c / a.ncols : 0, j = live ? a.col0 + (c - inst * a.ncols) : 0;
         const double* x = a.X + inst * a.x_bstride + j * a.ldx;
         const double* g = a.gvec ? a.gvec + inst * a.g_bstride : nullptr;
         const int rs = (int)(ring_it % kI8SliceRing);
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             if (RING && threadIdx.x == 0) {   // every thread holds its rows in registers: the slot can take the column 3 ahead
                 const int64_t cn = c0 + (int64_t)kI8SliceRing * gridDim.x;
                 if (cn < total) {
-                    const int64_t in2 = cn / a.n, j2 = cn - in2 * a.n;
+                    const int64_t in2 = cn / a.ncols, j2 = a.col0 + (cn - in2 * a.ncols);
                     i8::mb_expect_tx(&ring_full[rs], (uint32_t)(kpe * 8));
                     i8::bulk_load_1d(i8::s_u32(slice_smem) + (uint32_t)(rs * kpe * 8), a.X + in2 * a.x_bstride + j2 * a.ldx, (uint32_t)(kpe * 8), &ring_full[rs]);
                 }
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             __syncthreads();   // red / redu are rewritten by the next column
         }
         if (live && tig == 0) {
-            a.sigma[c] = sigma;
+            a.sigma[inst * a.n + j] = sigma;
             if (g) {
                 const double qs = a.qscale.ptr ? a.qscale.c * a.qscale.ptr[inst * a.qscale.bstride] : a.qscale.c;
                 atomicAdd(a.qout + inst * a.q_bstride + (a.map ? a.map[j] : j), qs * dg);   // one writer per entry: a fire-and-forget reduction
@@ -411,7 +415,7 @@ __device__ __forceinline__ I8Unit i8_decode(const GramI8KernelArgs& a, int64_t u
     I8Unit w;
     w.inst = u / a.tiles_per_inst;
     int64_t tl = u - w.inst * a.tiles_per_inst;
-    int tj = 0;
+    int tj = a.tj0;
     for (;; ++tj) {
         const int64_t lastcol = ((int64_t)(tj + 1) * BN < a.n ? (int64_t)(tj + 1) * BN : a.n) - 1;
         const int64_t cnt = lastcol / kI8BM + 1;
@@ -657,17 +661,19 @@ void configure_gram_i8_kernels() {
     cudaFuncSetAttribute(gram_i8_slice_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SliceRing * 4096 * 8 + 64);
 }
 
-bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0, int64_t col1) {
     if (!sc.plan.ok || !sc.slices || g.packed_host || g.gate) return false;
-    cudaMemsetAsync(sc.stats, 0, sizeof(unsigned long long) * kGramI8StatsStride * (size_t)batch, stream);
+    if (col1 < 0) col1 = g.n;
+    if (col0 == 0) cudaMemsetAsync(sc.stats, 0, sizeof(unsigned long long) * kGramI8StatsStride * (size_t)batch, stream);   // first (or only) chunk
     GramI8SliceArgs s{};
+    s.col0 = col0; s.ncols = col1 - col0;
     s.X = g.X; s.ldx = g.ldx; s.x_bstride = g.x_bstride; s.k = g.k; s.kp = sc.plan.kp; s.n = g.n; s.batch = batch;
     s.slices = sc.slices; s.sigma = sc.sigma; s.stats = sc.stats; s.tol = sc.tol;
     if (g.gvec) {
         s.gvec = g.gvec; s.g_bstride = g.g_bstride; s.qout = g.qout; s.q_bstride = g.q_bstride; s.c0out = g.c0out; s.map = g.map;
         s.qscale = g.qscale; s.cscale = g.cscale;
     }
-    const int64_t cols = batch * g.n;
+    const int64_t cols = batch * (col1 - col0);
     const bool aligned = g.ldx % 2 == 0 && (((uintptr_t)g.X) & 15) == 0 && g.x_bstride % 2 == 0;
     if (sc.plan.kp > 1024 && sc.plan.kp <= 4096 && aligned && !getenv("PMB_I8_NO_RING")) {   // bulk-copy ring, 2 CTAs per SM
         const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * 2);
@@ -684,18 +690,25 @@ bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t ba
 }
 
 template <int NS, int BN>
-static bool launch_i8_impl(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+static bool launch_i8_impl(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0, int64_t col1) {
     GramI8KernelArgs a{};
     if (!make_plane_map(&a.tmi, sc.slices, sc.plan.kp, g.n, batch, kI8BM)) return false;
     if (!make_plane_map(&a.tmj, sc.slices, sc.plan.kp, g.n, batch, BN)) return false;
     a.k = g.k; a.kp = sc.plan.kp; a.n = g.n; a.sigma = sc.sigma; a.stats = sc.stats; a.tol = sc.tol; a.force_ns = sc.force_ns;
     a.out = g.H; a.ldo = g.ldh; a.o_bstride = g.h_bstride; a.map = g.map; a.scale = g.scale; a.accumulate = g.accumulate;
     a.packed_dev = g.accumulate ? nullptr : g.packed_dev; a.packed_bstride = g.packed_bstride;
-    a.tiles_j = (int)((g.n + BN - 1) / BN);
+    // tile columns whose LAST column lies in [col0, col1): every tile column belongs to exactly one column range
+    const int ntj = (int)((g.n + BN - 1) / BN);
+    auto lastcol = [&](int tj) { return std::min<int64_t>((int64_t)(tj + 1) * BN, g.n) - 1; };
+    a.tj0 = 0;
+    while (a.tj0 < ntj && lastcol(a.tj0) < col0) ++a.tj0;
+    a.tj1 = a.tj0;
+    while (a.tj1 < ntj && lastcol(a.tj1) < col1) ++a.tj1;
     int64_t tpi = 0;
-    for (int tj = 0; tj < a.tiles_j; ++tj) tpi += (std::min<int64_t>((int64_t)(tj + 1) * BN, g.n) - 1) / kI8BM + 1;
+    for (int tj = a.tj0; tj < a.tj1; ++tj) tpi += lastcol(tj) / kI8BM + 1;
     a.tiles_per_inst = tpi;
     a.total_tiles = tpi * batch;
+    if (a.total_tiles == 0) return true;
     const int grid = (int)std::min<int64_t>(a.total_tiles, sm_count);
     gram_i8_kernel<NS, BN><<<grid, kI8Threads, I8Cfg<NS, BN>::kSmemBytes, stream>>>(a);
     return true;
@@ -704,7 +717,7 @@ static bool launch_i8_impl(const GramArgs& g, const GramI8Scratch& sc, int64_t b
 __global__ void gram_i8_count_levels_kernel(const unsigned long long* stats, double tol, int force_ns, int64_t batch, unsigned long long* counts) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < batch; i += (int64_t)gridDim.x * blockDim.x) {
         const int lv = force_ns ? force_ns : gram_i8_level(stats, i);
-        atomicAdd(counts + (lv == 5 ? 0 : lv == 6 ? 1 : 2), 1ull);
+        atomicAdd(counts + (lv == 5 ? 0 : lv == 6 ? 1 : 2), 1ull);   // anything else (kGramI8Fp64): the fp64 kernel
     }
 }
 
@@ -727,12 +740,24 @@ bool gram_i8_pays_off(int64_t k, int64_t n, int64_t batch, int sm_count) {
     return t_i8 < t_f64;
 }
 
-bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
+bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0, int64_t col1) {
     if (!sc.plan.ok || !sc.slices || g.packed_host || g.gate) return false;
+    if (col1 < 0) col1 = g.n;
     bool ok = true;
-    if (sc.force_ns != 6) ok = ok && launch_i8_impl<5, 96>(g, sc, batch, sm_count, stream);
-    if (sc.force_ns != 5) ok = ok && launch_i8_impl<6, 80>(g, sc, batch, sm_count, stream);
+    if (sc.force_ns != 6) ok = ok && launch_i8_impl<5, 96>(g, sc, batch, sm_count, stream, col0, col1);
+    if (sc.force_ns != 5) ok = ok && launch_i8_impl<6, 80>(g, sc, batch, sm_count, stream, col0, col1);
     return ok;
+}
+
+// flag[0] = 1 when any instance ended up on the fp64 path (the pipelined e2e graph has no fp64 launch: the host repairs)
+__global__ void gram_i8_flag_kernel(const unsigned long long* stats, int64_t batch, int32_t* flag) {
+    int bad = 0;
+    for (int64_t i = threadIdx.x; i < batch; i += blockDim.x) bad |= gram_i8_level(stats, i) != 5 && gram_i8_level(stats, i) != 6;
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) flag[0] = bad;
+}
+void launch_gram_i8_flag(const GramI8Scratch& sc, int64_t batch, int32_t* flag_dev, cudaStream_t stream) {
+    gram_i8_flag_kernel<<<1, 256, 0, stream>>>(sc.stats, batch, flag_dev);
 }
 
 }  // namespace pmb

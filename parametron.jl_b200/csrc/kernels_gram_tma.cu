@@ -103,7 +103,7 @@ __device__ __forceinline__ void dmma_16x8x4(double (&c)[4], double a0, double a1
 }
 // the certified int8-slice kernels (kernels_gram_i8.cu) own this instance: nothing to do here
 __device__ __forceinline__ bool skip_certified(const GramTmaKernelArgs& a, int64_t inst) {
-    return a.cert_stats && (a.cert_force || gram_i8_level(a.cert_stats, inst) != 0);
+    return a.cert_stats && (a.cert_force || gram_i8_level(a.cert_stats, inst) == 5 || gram_i8_level(a.cert_stats, inst) == 6);
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTConsumerWarps * 32) : "memory"); }
 

@@ -155,6 +155,7 @@ struct Step {
     const FillJob* jobs = nullptr; int njobs = 0, job_blocks = 0;  // ST_PROLOGUE  // ST_GRAM / ST_GEMM: k-split plan, arrival counters and partial-tile workspace
     GramArgs gram{};
     GramI8Scratch i8{};   // ST_GRAM: certified int8-slice path (slices == nullptr: fp64 only)
+    bool pipe8 = false;   // this Gram's operand is uploaded in column chunks; slice + tcgen05 launches run per chunk (build_update_graph)
     GemmTNArgs gemm{};
     GemvArgs gemv{};
     DotArgs dot{};
@@ -230,6 +231,21 @@ struct pmb_ctx {
     int32_t* pipe_ones = nullptr;        // pinned host array of ones (source of the flag copies)
     int32_t pipe_chunks = 0, pipe_gate_cols = 0;
     cudaStream_t h2d_stream = nullptr;
+    // int8 variant of the same overlap (pipe8): per arrived chunk one slice launch + one ranged tcgen05 Gram launch, and the finished
+    // columns of the packed P_x leave on a third stream while later chunks are still arriving.  The pipelined graph has no fp64
+    // launch: if the certificate refuses an instance, a flag reaches the host and pmb_synchronize replays a plain fp64 graph.
+    bool pipe8 = false;
+    std::vector<int64_t> pipe8_bounds;   // column boundaries of the chunks: 0 = b[0] < b[1] < ... = n, multiples of 480 = lcm(96, 80)
+    cudaStream_t d2h_stream = nullptr;
+    std::vector<cudaEvent_t> ev_chunk, ev_gram;
+    cudaEvent_t ev_d2h_done = nullptr;
+    int32_t* repair_flag_dev = nullptr;
+    int32_t* repair_flag_host = nullptr;
+    cudaGraph_t graph_fb = nullptr;
+    cudaGraphExec_t graph_exec_fb = nullptr;
+    bool fb_mode = false;                // run_step: fp64 replay (skip the tcgen05 launches, the fp64 kernel computes every instance)
+    bool pipe8_live = false;             // the current update graph is the pipelined one
+    int64_t repairs = 0;
     cudaEvent_t ev_h2d_done = nullptr, ev_aux_h2d = nullptr, ev_aux_kernels = nullptr;           // HOST Parameters are copied by memcpy nodes of the graph (pinned, pointer fixed at initialize)
     // host sinks of the packed QP (pmb_qp_set_host_sink): D2H memcpy nodes at the end of each branch
     double *sink_Px = nullptr, *sink_q = nullptr, *sink_c0 = nullptr, *sink_Ax = nullptr, *sink_l = nullptr, *sink_u = nullptr;

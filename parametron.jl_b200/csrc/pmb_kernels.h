@@ -151,17 +151,18 @@ bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k
 //   [0] bits of max_j sigma_j (0: every column is zero; +inf: non-finite or out-of-range data)   [1] bits of max_j ||x_j||_2^2
 //   [2] bits of max_j ||x_j / sigma_j||_1                                                          [3 + s] max_j sum_r d_s[r, j]^2
 constexpr int kGramI8Planes = 6;
-constexpr int kGramI8StatsStride = 16;   // [14] columns sliced so far (arrival counter), [15] the certificate's verdict: planes (5 / 6) or 0 = fp64
+constexpr int kGramI8StatsStride = 16;   // [14] columns sliced so far (arrival counter), [15] the certificate's verdict: 5 / 6 planes or kGramI8Fp64
+constexpr int kGramI8Fp64 = 64;          // verdict: not certifiable, the fp64 kernel owns the instance (0 = no verdict yet)
 #ifdef __CUDACC__
 // Number of digit planes (5 or 6) whose worst-case error -- representation error of the planes used plus every dropped digit
 // product, bounded with the measured column norms -- is below tol * max |H| (max |H| of a Gram matrix = its largest diagonal entry);
-// 0: not certifiable, the fp64 DMMA kernel computes this instance.  Evaluated ONCE per instance and update by the slice kernel
-// (the warp that slices the instance's last column) and stored in stats[15].
+// kGramI8Fp64: not certifiable, the fp64 DMMA kernel computes this instance.  Evaluated ONCE per instance and update by the slice
+// kernel (the group that slices the instance's last column) and stored in stats[15].
 __device__ __forceinline__ int gram_i8_compute_level(const unsigned long long* st, double tol) {
     const unsigned long long s0 = __ldcg(st);
     if (s0 == 0ull) return 5;                       // all-zero operand: every digit is zero
     const double sig = __longlong_as_double((long long)s0);
-    if (!(sig < 1e200)) return 0;
+    if (!(sig < 1e200)) return kGramI8Fp64;
     const double ss = __longlong_as_double((long long)__ldcg(st + 1)), l1 = __longlong_as_double((long long)__ldcg(st + 2));
     double R[kGramI8Planes];
 #pragma unroll
@@ -176,7 +177,7 @@ __device__ __forceinline__ int gram_i8_compute_level(const unsigned long long* s
                 if (s + t >= ns) by += exp2(-14.0 - 8.0 * (s + t)) * R[s] * R[t];   // dropped digit products (Cauchy-Schwarz)
         if (1.01 * sig * sig * by <= tol * ss) return ns;
     }
-    return 0;
+    return kGramI8Fp64;
 }
 __device__ __forceinline__ int gram_i8_level(const unsigned long long* stats, int64_t inst) {
     return (int)stats[inst * kGramI8StatsStride + 15];
@@ -198,8 +199,13 @@ struct GramI8Scratch {
 };
 // memset(stats) + slice kernel (gram_i8_slice) and the two tcgen05 Gram launches, 5 and 6 planes, of which at most one does work per
 // instance (gram_i8_mma).  false: not applicable (the caller runs the fp64 kernel alone).
-bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
-bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
+// [col0, col1): column range of this launch (upload pipelining: one slice + one Gram launch per arrived chunk); col1 < 0 = all columns.
+// The Gram launch of a range computes the tile columns whose last column lies in the range.
+bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0 = 0,
+                          int64_t col1 = -1);
+bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0 = 0,
+                        int64_t col1 = -1);
+void launch_gram_i8_flag(const GramI8Scratch& sc, int64_t batch, int32_t* flag_dev, cudaStream_t stream);
 // counts[0..2] += number of instances whose certificate picked 5 planes / 6 planes / the fp64 kernel (introspection for tests and bench)
 void launch_gram_i8_count_levels(const GramI8Scratch& sc, int64_t batch, unsigned long long* counts_dev, cudaStream_t stream);
 // predicted seconds of the two ways to compute one SYRK step; the planner picks the int8 path when it is the faster one

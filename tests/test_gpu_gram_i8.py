@@ -183,3 +183,40 @@ def test_cfg2_size_properties_int8_default_mode():
     lhs = 0.5 * xs @ Q @ xs + q @ xs + c0
     rhs = float(np.sum((vals[0] @ xs - vals[1]) ** 2))
     assert abs(lhs - rhs) <= 1e-9 * abs(rhs)
+
+
+@pytest.mark.parametrize("tol,expect_repairs", [(0.0, False), (1e-30, True)])
+def test_pipelined_upload_slice_gram_download(monkeypatch, tol, expect_repairs):
+    """Pinned HOST Gram operand with n >= 1920: the matrix is uploaded in column chunks (multiples of 480 columns), every arrived
+    chunk is sliced and its tile columns multiplied while later chunks are still on the bus, and the finished columns of the packed
+    P_x leave on a third stream (pmb_plan.cu capture_update_graph).  Results must not depend on the pipelining; with a tolerance
+    nothing can meet (1e-30) the certificate refuses the operand, the pipelined graph raises its flag and pmb_synchronize replays the
+    update on the fp64 kernel."""
+    import parametron_b200 as pm
+    monkeypatch.setenv("PMB_GRAM_I8_ALWAYS", "1")
+    n, k, m = 2000, 320, 16
+    rng = np.random.default_rng(n + k)
+    vals = {"A": rng.standard_normal((k, n)), "b": rng.standard_normal(k), "C": rng.standard_normal((m, n)), "d": rng.standard_normal(m)}
+    model = pm.Model(gram_mode=1, gram_tol=tol)
+    x = model.variables(n)
+    P = {key: pm.Parameter(model, val=v) for key, v in vals.items()}
+    r = P["A"] * x - P["b"]
+    pm.objective(model, pm.Minimize, pm.dot(r, r))
+    pm.constraint(model, P["C"] * x, "==", P["d"])
+    model.enable_qp_pack()
+    model.initialize()
+    sink = model.qp_host_sink()
+    for step in range(3):
+        for key in vals:
+            P[key].val = rng.standard_normal(vals[key].shape) * (1.0 + step)
+        model.update()
+        model.synchronize()
+        A, b = P["A"].val, P["b"].val
+        Q, q, c0 = model.objective_arrays()
+        assert_close(Q, 2 * A.T @ A, RTOL, "Q"); assert_close(q, -2 * A.T @ b, RTOL, "q"); assert_close([c0], [b @ b], RTOL, "c0")
+        assert np.array_equal(Q, Q.T)
+        assert np.array_equal(sink["P_x"][0], np.concatenate([Q[:j + 1, j] for j in range(n)]))
+        assert np.array_equal(sink["q"][0], q) and sink["c0"][0] == c0
+        assert np.array_equal(sink["A_x"][0], P["C"].val.T.ravel())
+        lv = model.gram_level_counts()
+        assert (lv[2] == 1) == expect_repairs
