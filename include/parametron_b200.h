@@ -236,6 +236,17 @@ int pmb_host_free(pmb_ctx* ctx, void* p);
 int pmb_memcpy_d2h(pmb_ctx* ctx, void* host, const void* dev, size_t bytes);  /* async on the context stream */
 int pmb_memcpy_h2d(pmb_ctx* ctx, void* dev, const void* host, size_t bytes);  /* async on the context stream */
 
+/* ---- result path: value.(model, x) / objectivevalue(model), model.jl:166-173 ----------------------------
+ * The external solver hands back its primal solution in OPTIMIZER variable order (MOI.VariablePrimal per optimizer index).
+ * pmb_set_primal stores it on the device (x: [batch][N]; on_device != 0: x is a device pointer, copied device-to-device on the context
+ * stream -- a device-resident solver never leaves the GPU).  pmb_value gathers model Variables through model_var_to_optimizer
+ * (value(m, x) = VariablePrimal[m.model_var_to_optimizer[x.index]]): out is [batch][nv], host (out_on_device == 0, synchronous) or
+ * device memory.  pmb_objective_value evaluates the objective the last update handed over, 1/2 x'Qx + q'x + c0 (q'x + c0 for an
+ * affine objective), at the stored solution on the device: out_host[batch]. */
+int pmb_set_primal(pmb_ctx* ctx, const double* x, int on_device);
+int pmb_value(pmb_ctx* ctx, int64_t nv, const int64_t* var_indices, double* out, int out_on_device);
+int pmb_objective_value(pmb_ctx* ctx, double* out_host);
+
 /* ---- introspection for tests / bench --------------------------------------------------------- */
 typedef struct {
     int64_t kernel_launches_per_update; /* launches of THIS library's kernels in one update */

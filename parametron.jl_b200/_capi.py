@@ -92,6 +92,9 @@ SIGNATURES = {
     "pmb_get_qp": (C.c_int, [C.c_void_p, C.POINTER(QpView)]),
     "pmb_qp_set_host_sink": (C.c_int, [C.c_void_p] * 7),
     "pmb_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "pmb_set_primal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "pmb_value": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]),
+    "pmb_objective_value": (C.c_int, [C.c_void_p, c_f64p]),
     "pmb_set_gram_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "pmb_gram_level_counts": (C.c_int, [C.c_void_p, c_i64p]),
     "pmb_enable_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),

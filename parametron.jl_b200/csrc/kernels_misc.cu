@@ -360,4 +360,16 @@ void launch_fill(double* p, int64_t n, double v, cudaStream_t stream) {
     fill_kernel<<<(unsigned)bx, 256, 0, stream>>>(p, n, v);
 }
 
+__global__ void gather_kernel(double* out, const double* x, const int64_t* idx, int64_t nv, int64_t N, int64_t batch) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nv * batch; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / nv, i = t - b * nv;
+        out[t] = x[b * N + idx[i]];
+    }
+}
+void launch_gather(double* out, const double* x, const int64_t* idx, int64_t nv, int64_t N, int64_t batch, cudaStream_t stream) {
+    if (nv * batch == 0) return;
+    const int grid = (int)std::min<int64_t>((nv * batch + 255) / 256, 4096);
+    gather_kernel<<<grid, 256, 0, stream>>>(out, x, idx, nv, N, batch);
+}
+
 }  // namespace pmb

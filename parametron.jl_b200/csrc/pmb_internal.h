@@ -257,6 +257,12 @@ struct pmb_ctx {
     int64_t *qp_Pp = nullptr, *qp_Pi = nullptr, *qp_Ap = nullptr, *qp_Ai = nullptr;
     pmb::PackBlockDev* qp_blocks_dev = nullptr;  // collected while planning, lowered to one ST_PROLOGUE step
     int64_t updates = 0;
+    // result path (pmb_set_primal / pmb_value / pmb_objective_value)
+    double* primal = nullptr;            // [batch][N], optimizer variable order
+    bool primal_set = false;
+    double* res_tmp = nullptr;           // [batch][N] scratch (Q x) + [batch] result
+    int64_t* res_idx = nullptr; int64_t res_idx_cap = 0;   // gather table of pmb_value
+    double* res_gather = nullptr; int64_t res_gather_cap = 0;
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraph_t graph = nullptr;
     bool use_graph = false;

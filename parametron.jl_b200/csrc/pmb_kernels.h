@@ -278,6 +278,8 @@ struct ScatterSymArgs {
 };
 void launch_scatter_sym(const ScatterSymArgs& a, int64_t batch, cudaStream_t stream);
 void launch_fill(double* p, int64_t n, double v, cudaStream_t stream);
+// out[b * nv + i] = x[b * N + idx[i]]     (value.(model, x): gather through model_var_to_optimizer, model.jl:166)
+void launch_gather(double* out, const double* x, const int64_t* idx, int64_t nv, int64_t N, int64_t batch, cudaStream_t stream);
 
 // ---------------- term-list export + QP pack (kernels_export.cu) ---------------------------------------------------------
 struct TermEntryDev {      // one term of the per-row template

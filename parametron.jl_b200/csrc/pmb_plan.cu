@@ -1250,6 +1250,81 @@ int pmb_get_stats(pmb_ctx* ctx, pmb_stats* out) {
     API_END(ctx)
 }
 
+// ---- result path: value.(model, x) / objectivevalue(model), model.jl:166-173 -------------------------------------------------------
+int pmb_set_primal(pmb_ctx* ctx, const double* x, int on_device) {
+    API_BEGIN(ctx)
+    if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_set_primal before pmb_initialize");
+    if (!x) fail(PMB_EINVAL, "null primal");
+    const int64_t cnt = ctx->batch * ctx->nvars;
+    if (!ctx->primal) {
+        ctx->primal = dalloc<double>(ctx, std::max<int64_t>(cnt, 1), true);
+        ctx->res_tmp = dalloc<double>(ctx, std::max<int64_t>(cnt, 1) + ctx->batch, true);
+    }
+    CK(cudaMemcpyAsync(ctx->primal, x, (size_t)cnt * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (!on_device) CK(cudaStreamSynchronize(ctx->stream));   // the caller's host buffer may be pageable / reused
+    ctx->primal_set = true;
+    API_END(ctx)
+}
+
+int pmb_value(pmb_ctx* ctx, int64_t nv, const int64_t* var_indices, double* out, int out_on_device) {
+    API_BEGIN(ctx)
+    if (!ctx->primal_set) fail(PMB_EINVAL, "pmb_value before pmb_set_primal (no solution has been handed back)");
+    if (nv < 0 || (nv > 0 && (!var_indices || !out))) fail(PMB_EINVAL, "bad arguments");
+    if (nv == 0) return PMB_OK;
+    std::vector<int64_t> idx((size_t)nv);
+    for (int64_t i = 0; i < nv; ++i) {
+        const int64_t v = var_indices[i];
+        if (v < 1 || v > ctx->nvars) fail(PMB_EINVAL, "variable index %lld out of range 1..%lld", (long long)v, (long long)ctx->nvars);
+        idx[(size_t)i] = ctx->varmap[(size_t)(v - 1)] - 1;     // m.model_var_to_optimizer[x.index]
+    }
+    if (ctx->res_idx_cap < nv) { ctx->res_idx = dalloc<int64_t>(ctx, nv); ctx->res_idx_cap = nv; }
+    CK(cudaMemcpyAsync(ctx->res_idx, idx.data(), (size_t)nv * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // idx is a local
+    double* dst = out;
+    if (!out_on_device) {
+        if (ctx->res_gather_cap < nv * ctx->batch) { ctx->res_gather = dalloc<double>(ctx, nv * ctx->batch); ctx->res_gather_cap = nv * ctx->batch; }
+        dst = ctx->res_gather;
+    }
+    launch_gather(dst, ctx->primal, ctx->res_idx, nv, ctx->nvars, ctx->batch, ctx->stream);
+    CK(cudaGetLastError());
+    if (!out_on_device) {
+        CK(cudaMemcpyAsync(out, dst, (size_t)(nv * ctx->batch) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    API_END(ctx)
+}
+
+int pmb_objective_value(pmb_ctx* ctx, double* out_host) {
+    API_BEGIN(ctx)
+    if (!ctx->primal_set) fail(PMB_EINVAL, "pmb_objective_value before pmb_set_primal (no solution has been handed back)");
+    if (!out_host) fail(PMB_EINVAL, "null out");
+    const int64_t N = ctx->nvars, nb = ctx->batch;
+    double* val = ctx->res_tmp + nb * N;
+    if (ctx->c0) CK(cudaMemcpyAsync(val, ctx->c0, (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    else CK(cudaMemsetAsync(val, 0, (size_t)nb * sizeof(double), ctx->stream));
+    if (ctx->q && N > 0) {   // + q'x
+        DotArgs d{};
+        d.x = ctx->q; d.x_bstride = N; d.y = ctx->primal; d.y_bstride = N; d.n = N; d.out = val; d.out_bstride = 1;
+        d.scale = AlphaDev{1.0, nullptr, 0}; d.accumulate = 1;
+        launch_dot(d, nb, ctx->stream);
+    }
+    if (ctx->obj_kind == PMB_KIND_QUAD && ctx->Q && N > 0) {   // + 1/2 x'(Qx)
+        GemvArgs g{};
+        g.A = ctx->Q; g.lda = N; g.a_bstride = N * N; g.rows = N; g.cols = N; g.trans = 0;
+        g.v = ctx->primal; g.v_bstride = N; g.v_off = 0; g.y = ctx->res_tmp; g.y_bstride = N; g.map = nullptr;
+        g.scale = AlphaDev{1.0, nullptr, 0}; g.accumulate = 0;
+        launch_gemv(g, nb, ctx->stream);
+        DotArgs d{};
+        d.x = ctx->res_tmp; d.x_bstride = N; d.y = ctx->primal; d.y_bstride = N; d.n = N; d.out = val; d.out_bstride = 1;
+        d.scale = AlphaDev{0.5, nullptr, 0}; d.accumulate = 1;
+        launch_dot(d, nb, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_host, val, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
 int pmb_set_gram_mode(pmb_ctx* ctx, int mode, double tol) {
     API_BEGIN(ctx)
     if (ctx->initialized) fail(PMB_EINITIALIZED, "pmb_set_gram_mode after pmb_initialize");

@@ -398,6 +398,30 @@ class Model:
         if self.optimizer is not None:
             self.optimizer(self)
 
+    # -- result path (model.jl:166-173): the optimizer hands its primal solution back in OPTIMIZER variable order
+    def set_primal(self, x, device_ptr=None):
+        """Store the solver's VariablePrimal vector ([batch,] N in optimizer index order); device_ptr: it already lives on the device."""
+        if device_ptr is not None:
+            self._ck(self._lib.pmb_set_primal(self._ctx, C.c_void_p(int(device_ptr)), 1))
+            return
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(self.batch, self.nvars))
+        self._ck(self._lib.pmb_set_primal(self._ctx, C.c_void_p(x.ctypes.data), 0))
+
+    def value(self, x):
+        """value(m, x) / value.(m, xs): VariablePrimal[model_var_to_optimizer[x.index]] (model.jl:166)"""
+        scalar = isinstance(x, Variable)
+        idx = np.array([x.index] if scalar else _flatten_vars(x), dtype=np.int64)
+        out = np.empty((self.batch, len(idx)))
+        self._ck(self._lib.pmb_value(self._ctx, len(idx), C.c_void_p(idx.ctypes.data), C.c_void_p(out.ctypes.data), 0))
+        out = out[0] if self.batch == 1 else out
+        return out[..., 0] if scalar else out
+
+    def objectivevalue(self):
+        """objectivevalue(m) (model.jl:173): the objective of the last update evaluated at the stored solution, on the device"""
+        out = (C.c_double * self.batch)()
+        self._ck(self._lib.pmb_objective_value(self._ctx, out))
+        return float(out[0]) if self.batch == 1 else np.array(out[:])
+
     # -- device-resident handoff (replaces MOI.set, moi_interop.jl:134,171)
     def objective_view(self):
         v = K.ObjectiveView()
