@@ -156,6 +156,23 @@ function block_view(ctx::Ctx, update_pos::Integer)                   # replaces 
     v[]
 end
 
+# precision mode of the Hessian contraction (build phase): 0 = fp64 DMMA only, 1 = certified int8 digit planes on tcgen05 (default)
+set_gram_mode!(ctx::Ctx, mode::Integer, tol::Real = 0.0) =
+    check(ctx, ccall((:pmb_set_gram_mode, lib), Cint, (Ptr{Cvoid}, Cint, Cdouble), ctx.ptr, mode, tol))
+
+# result path, model.jl:166-173.  `x` is the solver's VariablePrimal vector in OPTIMIZER index order (host Vector or device pointer).
+set_primal!(ctx::Ctx, x::Vector{Float64}) = check(ctx, ccall((:pmb_set_primal, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), ctx.ptr, x, 0))
+function value(ctx::Ctx, vars::Vector{Int64}; batch::Integer = 1)     # value.(m, xs): VariablePrimal[m.model_var_to_optimizer[x.index]]
+    out = Matrix{Float64}(undef, length(vars), batch)
+    check(ctx, ccall((:pmb_value, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Cint), ctx.ptr, length(vars), vars, out, 0))
+    out
+end
+function objectivevalue(ctx::Ctx; batch::Integer = 1)                 # objectivevalue(m), model.jl:173
+    out = Vector{Float64}(undef, batch)
+    check(ctx, ccall((:pmb_objective_value, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx.ptr, out))
+    out
+end
+
 # With CUDA.jl a device-aware solver wraps the views without copies, e.g.
 #   v = objective_view(ctx); Q = unsafe_wrap(CuArray, CuPtr{Float64}(UInt(v.Q)), (v.nvars, v.nvars))
 end # module

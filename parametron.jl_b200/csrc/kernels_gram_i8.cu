@@ -34,7 +34,8 @@ namespace pmb {
 
 constexpr int kI8BM = 128;          // tile rows = tcgen05 M (one TMEM lane per row)
 constexpr int kI8KC = 64;           // k (bytes) per pipeline stage: one 64-byte swizzle span, two K=32 MMAs per digit-plane pair
-constexpr int kI8Threads = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kI8EpiWarps = 8;       // two warps per TMEM lane quarter, alternating 16-column chunks
+constexpr int kI8Threads = 64 + 32 * kI8EpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int kI8TmemCols = 512;
 
 template <int NS, int BN>
@@ -134,7 +135,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kI8EpiWarps) : "memory"); }
 
 // shared-memory matrix descriptor of a K-major panel stored as rows of 64 bytes under the 64-byte swizzle (what the TMA box
 // (64 bytes, rows) with CU_TENSOR_MAP_SWIZZLE_64B writes): 8-row groups are 512 bytes apart (SBO), LBO is unused (1), Blackwell
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
 #pragma unroll
         for (int s = 0; s < C::kStages; ++s) { i8::mb_init(&full_bar[s], 1); i8::mb_init(&empty_bar[s], 1); }
         i8::mb_init(&tmem_full_bar, 1);
-        i8::mb_init(&tmem_empty_bar, 4);
+        i8::mb_init(&tmem_empty_bar, kI8EpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) i8::tmem_alloc(&tmem_slot, kI8TmemCols);
@@ -524,9 +525,10 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
             }
         }
     } else {
-        // ===== epilogue: 4 warps, warp w owns TMEM lanes 32 (w % 4) .. +31 = tile rows =====
+        // ===== epilogue: 8 warps, warp w owns TMEM lanes 32 (w % 4) .. +31 = tile rows and every other 16-column chunk =====
         const int q = warp & 3;
-        const int et = tid - 64;   // 0 .. 127
+        const int et = tid - 64;   // 0 .. 32 * kI8EpiWarps - 1
+        const int chalf = (warp - 2) >> 2;   // which of the quarter's two warps: it takes the 16-column chunks of its parity
         uint32_t tile_it = 0;
         for (int64_t u = blockIdx.x; u < a.total_tiles; u += gridDim.x) {
             const I8Unit w = i8_decode<BN>(a, u);
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
             const bool fast = !a.map && !a.accumulate && i0 + kI8BM <= j0 && j0 + BN <= a.n && (a.ldo & 3) == 0 && (a.o_bstride & 3) == 0 &&
                               (((uintptr_t)a.out) & 31) == 0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            for (int c0 = 16 * chalf; c0 < BN; c0 += 16 * (kI8EpiWarps / 4)) {
                 int32_t acc[NS][16];
 #pragma unroll
                 for (int l = 0; l < NS; ++l) i8::tmem_ld16(trow + (uint32_t)(l * BN + c0), acc[l]);

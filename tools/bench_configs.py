@@ -17,12 +17,13 @@ import parametron_b200 as pm  # noqa: E402
 RANK = int(os.environ.get("RANK", "0"))
 LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
 WORLD = int(os.environ.get("WORLD_SIZE", "1"))
-HBM_PEAK = 6538.3   # MEASURED_PEAKS.json
+HBM_PEAK = 6455.6   # MEASURED_PEAKS.json (hbm_gbs)
+I8_PEAK = 2 * 1677.0  # 2 x bf16_tflops (burst) of MEASURED_PEAKS.json: int8 dense rate of tcgen05 = 2 x bf16
 DMMA_PEAK = 37.1    # profiles/r01_probe_dmma.txt
 
 
-def ls_model(n, k, m, batch=1, fixed_matrices=False):
-    model = pm.Model(device=LOCAL, batch=batch)
+def ls_model(n, k, m, batch=1, fixed_matrices=False, gram_mode=None):
+    model = pm.Model(device=LOCAL, batch=batch, gram_mode=gram_mode)
     x = model.variables(n)
     if fixed_matrices:   # MPC style: A, C resident and constant between solves; b, d re-parameterised every solve
         A = pm.Parameter(model, shape=(k, n), device=True)
@@ -86,13 +87,27 @@ def cfg1():
 
 
 def cfg2():
-    m = ls_model(4096, 4096, 1024)
-    st = m.stats()
-    sec = timed_updates(m, 30)
-    kb = kernel_breakdown(m, 10)
-    report("cfg2 n=4096, m=1024 dense", ms_per_update=sec * 1e3, updates_per_s=1 / sec, kernel_us=kb,
-           gram_tflops=st["gram_algorithmic_flops"] / kb["gram_dmma"] / 1e6, gram_frac_of_dmma_peak=st["gram_algorithmic_flops"] / kb["gram_dmma"] / 1e6 / DMMA_PEAK,
-           affine_gbs=st["affine_algorithmic_bytes"] / kb["affine_assemble"] / 1e3, affine_frac_of_hbm_peak=st["affine_algorithmic_bytes"] / kb["affine_assemble"] / 1e3 / HBM_PEAK)
+    for mode, label in ((1, "certified int8 digit planes on tcgen05 (default)"), (0, "fp64 DMMA only (pmb_set_gram_mode 0)")):
+        m = ls_model(4096, 4096, 1024, gram_mode=mode)
+        st = m.stats()
+        sec = timed_updates(m, 30)
+        kb = kernel_breakdown(m, 10)
+        lv = m.gram_level_counts()
+        extra = {}
+        syrk = 4096 * 4096 * 4097
+        if lv[0] + lv[1]:
+            planes = 5 if lv[0] else 6
+            nprod = planes * (planes + 1) // 2
+            extra = dict(gram_planes=planes, gram_int8_tops=nprod * syrk / kb["gram_i8_tcgen05"] / 1e6,
+                         gram_frac_of_int8_peak=nprod * syrk / kb["gram_i8_tcgen05"] / 1e6 / I8_PEAK,
+                         gram_fp64_equivalent_tflops=syrk / (kb["gram_i8_tcgen05"] + kb["gram_i8_slice"]) / 1e6)
+        else:
+            extra = dict(gram_tflops=st["gram_algorithmic_flops"] / kb["gram_dmma"] / 1e6,
+                         gram_frac_of_dmma_peak=st["gram_algorithmic_flops"] / kb["gram_dmma"] / 1e6 / DMMA_PEAK)
+        report(f"cfg2 n=4096, m=1024 dense -- {label}", ms_per_update=sec * 1e3, updates_per_s=1 / sec, kernel_us=kb, gram_levels=lv,
+               affine_gbs=st["affine_algorithmic_bytes"] / kb["affine_assemble"] / 1e3,
+               affine_frac_of_hbm_peak=st["affine_algorithmic_bytes"] / kb["affine_assemble"] / 1e3 / HBM_PEAK, **extra)
+        m.close()
 
 
 def cfg3(total=8192):
