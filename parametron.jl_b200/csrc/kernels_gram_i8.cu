@@ -241,6 +241,8 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
     const bool vec = (a.ldx % 2 == 0) && (((uintptr_t)a.X & 15) == 0) && (a.x_bstride % 2 == 0);
     const bool gvecal = a.gvec && (((uintptr_t)a.gvec & 15) == 0) && (a.g_bstride % 2 == 0);
     const bool cached = a.kp <= (int64_t)4 * T * CIT;
+    const bool k4 = (a.k & 3) == 0;
+    const int64_t plane_stride = a.n * a.kp;
     const int64_t total = a.batch * a.ncols;
     for (int64_t c0 = (int64_t)blockIdx.x * G; c0 < total; c0 += (int64_t)gridDim.x * G) {   // uniform per CTA (block-wide barriers below)
         const int64_t c = c0 + grp;
@@ -258,9 +260,8 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const double av = fabs(v[e]);
-                bad |= !(av <= DBL_MAX);
                 amax = fmax(amax, av);
-                l1 += av;
+                l1 += av;   // Inf / NaN entries surface here (fmax would hide a NaN): tested once per column below
                 ss = fma(v[e], v[e], ss);
             }
             if (g) {
@@ -278,7 +279,9 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
                     if (r0 < a.k) {
                         if (RING) {
                             const double2 p = *(const double2*)(xs + r0), q = *(const double2*)(xs + r0 + 2);   // r0 + 3 < kpe + 2 <= slot + pad
-                            vc[it][0] = p.x; vc[it][1] = r0 + 1 < a.k ? p.y : 0.0; vc[it][2] = r0 + 2 < a.k ? q.x : 0.0; vc[it][3] = r0 + 3 < a.k ? q.y : 0.0;
+                            vc[it][0] = p.x; vc[it][2] = q.x;
+                            if (k4) { vc[it][1] = p.y; vc[it][3] = q.y; }
+                            else { vc[it][1] = r0 + 1 < a.k ? p.y : 0.0; vc[it][2] = r0 + 2 < a.k ? q.x : 0.0; vc[it][3] = r0 + 3 < a.k ? q.y : 0.0; }
                         } else {
                             load4(x, r0, a.k, vec, vc[it]);
                         }
@@ -301,8 +304,8 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             l1 += __shfl_xor_sync(0xffffffffu, l1, o);
             dg += __shfl_xor_sync(0xffffffffu, dg, o);
             gg += __shfl_xor_sync(0xffffffffu, gg, o);
-            bad |= (bool)__shfl_xor_sync(0xffffffffu, (int)bad, o);
         }
+        bad = !(l1 <= DBL_MAX);
         if (T == 256) {
             if (lane == 0) { red[warp][0] = bad ? CUDART_INF : amax; red[warp][1] = ss; red[warp][2] = l1; red[warp][3] = dg; red[warp][4] = gg; }
             __syncthreads();
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
         }
         if (amax > 0.0 && !(amax >= 1e-150 && amax <= 1e150)) bad = true;
         const bool zero = !(amax > 0.0) || bad;
-        const double sigma = zero ? 1.0 : amax / 0.99;
+        const double sigma = zero ? 1.0 : amax * (1.0 / 0.99);
         const double mult = zero ? 0.0 : ldexp(0.99 / amax, 8 * NP - 1);   // x -> fixed point with 47 fractional bits of x / sigma
         int8_t* dst = a.slices + ((inst * NP) * a.n + j) * a.kp;
         uint32_t dsq[NP];
@@ -336,18 +339,21 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             uint32_t lo[4], hi[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const long long X = zero ? 0ll : __double2ll_rn(v[t] * mult);
-                const unsigned long long Y = ((unsigned long long)X + 0x0000008080808080ull) ^ 0x0000008080808080ull;
+                // round-to-nearest-even integer of v * mult (|.| < 2^47) without the slow 64-bit F2I: adding 1.5 * 2^52 leaves the
+                // two's-complement integer in the low mantissa bits; only the low 48 bits are used below
+                const unsigned long long X = (unsigned long long)__double_as_longlong(fma(v[t], mult, 6755399441055744.0));
+                const unsigned long long Y = (X + 0x0000008080808080ull) ^ 0x0000008080808080ull;
                 lo[t] = (uint32_t)Y; hi[t] = (uint32_t)(Y >> 32);
             }
+            int8_t* dp = dst + r0;
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
+            for (int p = 0; p < NP; ++p, dp += plane_stride) {
                 const int bidx = (NP - 1 - p) & 3;
                 const uint32_t* src = (NP - 1 - p) < 4 ? lo : hi;
                 const uint32_t sel = (uint32_t)bidx | ((uint32_t)(4 + bidx) << 4);
                 const uint32_t w = __byte_perm(__byte_perm(src[0], src[1], sel), __byte_perm(src[2], src[3], sel), 0x5410);
                 dsq[p] = (uint32_t)__dp4a((int)w, (int)w, (int)dsq[p]);
-                *(uint32_t*)(dst + (int64_t)p * a.n * a.kp + r0) = w;
+                *(uint32_t*)dp = w;
             }
         };
         if (live) {
@@ -366,9 +372,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             }
         }
 #pragma unroll
-        for (int s = 0; s < NP; ++s)
-#pragma unroll
-            for (int o = 16; o; o >>= 1) dsq[s] += __shfl_xor_sync(0xffffffffu, dsq[s], o);
+        for (int s = 0; s < NP; ++s) dsq[s] = __reduce_add_sync(0xffffffffu, dsq[s]);
         if (T == 256) {
             if (lane == 0) {
 #pragma unroll

@@ -476,9 +476,20 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                     pipe8 = true;
                     c->pipe_param = F.whole_node;
                     c->pipe8 = true;
-                    const int64_t step = 480 * std::max<int64_t>(1, (F.ncols / 8 + 240) / 480);   // ~8 chunks, boundaries on both tile grids
+                    // ~8 chunks of equal width (multiples of 480 = lcm(96, 80) columns keep both tile grids aligned), then a finer tail:
+                    // what is exposed after the last byte of the upload is the last chunk's slice + Gram range + P_x download
+                    const int64_t step = 480 * std::max<int64_t>(1, (F.ncols / 8 + 240) / 480);
                     c->pipe8_bounds.clear();
-                    for (int64_t b0 = 0; b0 < F.ncols; b0 += step) c->pipe8_bounds.push_back(b0);
+                    int64_t b0 = 0;
+                    for (; F.ncols - b0 > 2 * step; b0 += step) c->pipe8_bounds.push_back(b0);
+                    if (const char* e = getenv("PMB_PIPE8_TAIL")) {
+                        const int parts = std::max(1, atoi(e));
+                        const int64_t rem = F.ncols - b0;
+                        for (int q = 0; q < parts; ++q) c->pipe8_bounds.push_back(b0 + (rem * q / parts) / 16 * 16);
+                    } else {
+                        const int64_t rem = F.ncols - b0;
+                        for (int q = 0; q < 4; ++q) c->pipe8_bounds.push_back(b0 + (rem * q / 4) / 16 * 16);
+                    }
                     c->pipe8_bounds.push_back(F.ncols);
                 }
             }
@@ -821,6 +832,7 @@ static void capture_update_graph(pmb_ctx* ctx, bool fallback, cudaGraph_t* graph
                         if (ctx->steps[sj].type == ST_GRAM_I8_MMA && ctx->steps[sj].pipe8) mm = &ctx->steps[sj];
                     if (!mm) fail(PMB_EINVAL, "internal: pipelined slice step without its tcgen05 step");
                     const bool stream_px = ctx->sink_Px && mm->gram.packed_dev == ctx->qp_Px && ctx->qp_P_fused;
+                    int64_t done_prev = 0;   // columns of P_x complete (on both tile grids, 96 and 80 wide) and already sent
                     for (size_t r = 0; r < nranges; ++r) {
                         const int64_t c0 = ctx->pipe8_bounds[r], c1 = ctx->pipe8_bounds[r + 1];
                         CK(cudaStreamWaitEvent(main_s, ctx->ev_chunk[r], 0));
@@ -832,8 +844,12 @@ static void capture_update_graph(pmb_ctx* ctx, bool fallback, cudaGraph_t* graph
                         if (stream_px) {   // columns [c0, c1) of the packed upper triangle are final: they leave while later chunks arrive
                             CK(cudaEventRecord(ctx->ev_gram[r], main_s));
                             CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_gram[r], 0));
-                            const int64_t o0 = c0 * (c0 + 1) / 2, o1 = c1 * (c1 + 1) / 2;
-                            CK(cudaMemcpyAsync(ctx->sink_Px + o0, ctx->qp_Px + o0, (size_t)(o1 - o0) * sizeof(double), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                            // a tile column belongs to the range holding its LAST column: complete are the columns below the last tile boundary
+                            const int64_t done = r + 1 == nranges ? c1 : std::min(c1 / 96 * 96, c1 / 80 * 80);
+                            const int64_t o0 = done_prev * (done_prev + 1) / 2, o1 = done * (done + 1) / 2;
+                            if (o1 > o0)
+                                CK(cudaMemcpyAsync(ctx->sink_Px + o0, ctx->qp_Px + o0, (size_t)(o1 - o0) * sizeof(double), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                            done_prev = std::max(done_prev, done);
                             mark("d2h P_x range " + std::to_string(r), ctx->d2h_stream);
                         }
                     }
