@@ -30,8 +30,8 @@ N_VARS, K_ROWS, M_ROWS = 4096, 4096, 1024
 SEED = 1234
 METRIC = "QP re-parameterizations/sec (update!+coeff-assemble) at n=4096,m=1024"
 GRAM_DRAM_TRAFFIC_BYTES = 410174464 + 167363328    # ncu --set full, one launch of gram_tma_kernel<1,128> at cfg2
-GRAM_I8_DRAM_TRAFFIC_BYTES = 281920000 + 114058240    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r01_n_gram_i8_ncu_full.txt)
-AFFINE_DRAM_TRAFFIC_BYTES = 33626880 + 689664       # ncu --set full, one launch of affine_assemble_tma<0> at cfg2
+GRAM_I8_DRAM_TRAFFIC_BYTES = 275960832 + 116289280    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r01_n_gram_i8_ncu_full.txt)
+AFFINE_DRAM_TRAFFIC_BYTES = 33626880 + 1335808       # ncu --set full, one launch of affine_assemble_tma<0> at cfg2 (profiles/r01_n_affine_tma_ncu_full.txt)
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200: profiles/r01_probe_dmma.txt (mma.sync f64, all SMs)
 
 
@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -175,7 +175,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -270,7 +270,7 @@ def main():
                     "algorithmic_ops": int(nprod * syrk_flops), "avg_launch_ms": i8_ms,
                     "peak_source": f"2 x bf16_tflops (burst) of MEASURED_PEAKS.json ({peak_src}): the int8 dense rate of tcgen05 is twice the bf16 rate "
                                    "(4.5 vs 2.25 POP/s nominal); MEASURED_PEAKS.json has no int8 entry.  ncu's own counter for the same launch: "
-                                   "sm__ops_path_tensor_op_utcimma_src_int8 = 69.9 % of its peak (16384 ops/clk/SM), profiles/r01_n_gram_i8_ncu_full.txt",
+                                   "sm__ops_path_tensor_op_utcimma_src_int8 = 71.9 % of its peak (16384 ops/clk/SM at the 1.69 GHz the SMs hold under this load), profiles/r01_n_gram_i8_ncu_full.txt",
                     "fp64_equivalent_tflops": syrk_flops / ((i8_ms + slice_ms) * 1e-3) / 1e12,
                     "fp64_equivalent_note": f"SYRK-counted fp64 flops / (slice {slice_ms:.3f} ms + tcgen05 {i8_ms:.3f} ms); the fp64 DMMA pipe peaks at "
                                             f"{FP64_DMMA_PEAK_TFLOPS} TFLOP/s (profiles/r01_probe_dmma.txt), the fp64 kernel reached 33 (profiles/r01_m_*)",
@@ -349,10 +349,10 @@ def main():
             "gram_levels": {"int8_5_planes": levels[0], "int8_6_planes": levels[1], "fp64": levels[2]},
             "roofline_affine": {"bound": "hbm", "kernel": "affine_assemble_tma (C, -d): bulk-copy ring", "achieved": aff_gbs, "peak": peaks["hbm_gbs"],
                                 "unit": "GB/s", "frac": (aff_gbs / peaks["hbm_gbs"]) if aff_gbs else None, "traffic": AFFINE_DRAM_TRAFFIC_BYTES,
-                                "traffic_source": "profiles/r01_e_affine_tma_ncu_full.txt: 33.6 MB read; the 33.5 MB written stay in the 126 MB L2",
+                                "traffic_source": "profiles/r01_n_affine_tma_ncu_full.txt: 33.6 MB read; the 33.5 MB written stay in the 126 MB L2",
                                 "algorithmic_bytes": int(st["affine_algorithmic_bytes"]), "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                                 "note": "CUDA-event time of the single launch inside an eager replay of the step (includes ~3 us of event/launch overhead; "
-                                        "ncu gpu__time_duration of the same launch: profiles/r01_e_affine_tma_ncu_full.txt)"},
+                                        "ncu gpu__time_duration of the same launch: 11.5-13.0 us, profiles/r01_n_affine_tma_ncu_full.txt, r01_n_launches_cfg2.csv)"},
             "kernel_ms_per_update": {k: v[0] / max(ksteps, 1) for k, v in kt.items()},
             "kernel_share": kernel_share,
             "cpu_baseline": cpu,
