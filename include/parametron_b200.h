@@ -130,6 +130,10 @@ int pmb_op_sub(pmb_ctx* ctx, pmb_node x, pmb_node y, pmb_node* out);      /* x -
 int pmb_op_mul(pmb_ctx* ctx, pmb_node x, pmb_node y, pmb_node* out);      /* scalar*fn -> mul! :260-274; number*vector -> scale! :284-290 */
 int pmb_op_vcat(pmb_ctx* ctx, int32_t n, const pmb_node* parts, pmb_node* out); /* vcat! :276-278, functions.jl:969-994 */
 int pmb_op_vect(pmb_ctx* ctx, pmb_node x, pmb_node* out);                 /* [x]   :292-298 */
+int pmb_op_convert(pmb_ctx* ctx, pmb_node x, pmb_node* out);              /* convert(Vector, x) -> copyto! :280-282 */
+/* p.field -> GetField :300-302, functions.jl:998-999.  A struct-valued Parameter is a flat record (fields packed in declaration
+ * order, matrices column-major); the field is the ndims/rows/cols sub-array starting at element `offset` of the record. */
+int pmb_op_getfield(pmb_ctx* ctx, pmb_node p, int64_t offset, int ndims, int64_t rows, int64_t cols, pmb_node* out);
 int pmb_node_info(pmb_ctx* ctx, pmb_node n, int32_t* kind, int64_t* rows, int64_t* cols, int32_t* is_constant);
 
 /* ---- model ------------------------------------------------------------------------------------ */

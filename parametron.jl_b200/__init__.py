@@ -4,8 +4,8 @@ The directory name contains a dot, so import it through the root-level shim:  `i
 """
 from . import _capi, macros, shard
 from ._capi import (AlreadyInitialized, DimensionMismatch, PmbError, Unsupported, LIB_PATH)
-from .model import (Expr, Maximize, Minimize, Model, Parameter, Variable, adjoint, bilinear, constraint, dot, objective,
-                    transpose, vcat, vect)
+from .model import (Expr, Maximize, Minimize, Model, Parameter, RecordParameter, Variable, adjoint, bilinear, constraint, convert, dot,
+                    objective, transpose, vcat, vect)
 
 __all__ = ["Model", "Parameter", "Variable", "Expr", "Minimize", "Maximize", "adjoint", "transpose", "dot", "bilinear", "vcat",
-           "vect", "objective", "constraint", "shard", "macros", "PmbError", "DimensionMismatch", "AlreadyInitialized", "Unsupported", "LIB_PATH"]
+           "vect", "convert", "RecordParameter", "objective", "constraint", "shard", "macros", "PmbError", "DimensionMismatch", "AlreadyInitialized", "Unsupported", "LIB_PATH"]

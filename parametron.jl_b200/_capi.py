@@ -76,6 +76,8 @@ SIGNATURES = {
     "pmb_op_mul": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_i32p]),
     "pmb_op_vcat": (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_i32p]),
     "pmb_op_vect": (C.c_int, [C.c_void_p, C.c_int32, c_i32p]),
+    "pmb_op_convert": (C.c_int, [C.c_void_p, C.c_int32, c_i32p]),
+    "pmb_op_getfield": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_int64, C.c_int64, c_i32p]),
     "pmb_node_info": (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_i64p, c_i64p, c_i32p]),
     "pmb_set_objective": (C.c_int, [C.c_void_p, C.c_int, C.c_int32]),
     "pmb_add_constraint": (C.c_int, [C.c_void_p, C.c_int32, C.c_int, c_i32p]),

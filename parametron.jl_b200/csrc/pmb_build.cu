@@ -751,6 +751,36 @@ int pmb_op_vect(pmb_ctx* ctx, pmb_node x, pmb_node* out) {
     API_END(ctx)
 }
 
+int pmb_op_convert(pmb_ctx* ctx, pmb_node x, pmb_node* out) {
+    API_BEGIN(ctx)
+    need_build_phase(ctx, "@expression");
+    if (!out) fail(PMB_EINVAL, "null out");
+    // convert(Vector, x) -> copyto!(dest, x), lazyexpression.jl:280-282: any vector value becomes a Vector{AffineFunction}
+    const int k = node_at(ctx, x).kind;
+    if (k != PMB_KIND_NUM_VECTOR && k != PMB_KIND_VARVEC && k != PMB_KIND_AFFVEC) fail(PMB_EUNSUPPORTED, "convert(Vector, x) needs a vector value");
+    AffForm f = aff_of(ctx, x);
+    *out = push_aff(ctx, PMB_KIND_AFFVEC, std::move(f));
+    API_END(ctx)
+}
+
+int pmb_op_getfield(pmb_ctx* ctx, pmb_node p, int64_t offset, int ndims, int64_t rows, int64_t cols, pmb_node* out) {
+    API_BEGIN(ctx)
+    need_build_phase(ctx, "@expression");
+    if (!out) fail(PMB_EINVAL, "null out");
+    // getproperty(p, :field) -> GetField{field}()(p), lazyexpression.jl:300-302, functions.jl:998-999.  A struct-valued Parameter is a
+    // flat numeric record on the device (fields packed in declaration order, matrices column-major); the field is the sub-array at
+    // element `offset`, copied into its own node by the numeric prologue (one lincomb term, alpha = 1).
+    const Node& pn = node_at(ctx, p);
+    if (pn.kind != PMB_KIND_NUM_VECTOR || pn.bsr_b > 0) fail(PMB_EUNSUPPORTED, "getfield needs a record (flat vector) value");
+    int64_t r = rows, cc = cols;
+    const int kind = kind_of_ndims(ndims, r, cc);
+    const int64_t numel = kind == PMB_KIND_NUM_SCALAR ? 1 : kind == PMB_KIND_NUM_VECTOR ? r : r * cc;
+    if (offset < 0 || offset + numel > pn.rows) fail(PMB_EDIM, "field [%lld, %lld) outside a record of %lld values", (long long)offset,
+                                                     (long long)(offset + numel), (long long)pn.rows);
+    *out = make_lincomb(ctx, kind, r, cc, {LinTermH{Alpha{1.0, -1}, p, offset}});
+    API_END(ctx)
+}
+
 int pmb_node_info(pmb_ctx* ctx, pmb_node n, int32_t* kind, int64_t* rows, int64_t* cols, int32_t* is_constant) {
     API_BEGIN(ctx)
     const Node& nd = node_at(ctx, n);

@@ -127,9 +127,11 @@ class _Lower(ast.NodeVisitor):
 
     def visit_Attribute(self, node):
         v = self.visit(node.value)
+        if isinstance(v, M.RecordParameter) and node.attr in v._fields:   # p.field: the GetField rule, lazyexpression.jl:300-302
+            return v.field(node.attr)
         if node.attr == "T":  # Julia's postfix '
             return M.adjoint(v, model=self.m)
-        raise ArgumentError("getproperty on device expressions has no lowering (lazyexpression.jl:300-302 is host-side)")
+        raise ArgumentError("getproperty: only fields of a struct-valued Parameter (RecordParameter) are lowered (lazyexpression.jl:300-302)")
 
     def _is_sym(self, v):
         return isinstance(v, (M.Expr, M.Variable)) or M._flatten_vars(v) is not None
@@ -170,8 +172,10 @@ class _Lower(ast.NodeVisitor):
     def visit_Call(self, node):
         if not isinstance(node.func, ast.Name):
             raise ArgumentError("Unhandled expression head: call of a non-name")
-        args = [self.visit(a) for a in node.args]
         f = node.func.id
+        if f == "convert" and len(node.args) == 2:   # convert(Vector, x): the type argument is only a tag (lazyexpression.jl:280-282)
+            return M.convert(self.visit(node.args[1]), model=self.m)
+        args = [self.visit(a) for a in node.args]
         if f == "dot" and len(args) == 2:
             return M.dot(args[0], args[1], model=self.m)
         if f in ("adjoint", "transpose") and len(args) == 1:

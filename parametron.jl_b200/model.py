@@ -223,6 +223,47 @@ class Parameter(Expr):
 _rt = None
 
 
+class RecordParameter(Parameter):
+    """A Parameter whose value is a struct (`Parameter(model) do MyWrapper(rand()) end`, test/lazyexpression.jl:355-382).  On the
+    device the fields are packed into one flat vector in declaration order (matrices column-major); `p.field` is the GetField rewrite
+    (lazyexpression.jl:300-302, functions.jl:998-999).  `fields` = ordered {name: shape}; `f()` returns an object (or dict) carrying
+    those fields and is called exactly once per update! like any other Parameter."""
+
+    def __init__(self, model, f, fields):
+        self._fields, off = {}, 0
+        for name, shp in fields.items():
+            shp = tuple(int(v) for v in shp)
+            self._fields[name] = (off, shp)
+            off += int(np.prod(shp)) if shp else 1
+        self._record_f, self.record = f, None
+
+        def flat():
+            rec = self._record_f()
+            self.record = rec
+            parts = []
+            for name, (_, shp) in self._fields.items():
+                a = np.asarray(rec[name] if isinstance(rec, dict) else getattr(rec, name), dtype=np.float64)
+                if a.shape != shp:
+                    raise K.DimensionMismatch(K.EDIM, f"field {name} has shape {a.shape}, declared {shp}")
+                parts.append(a.reshape(-1, order="F"))
+            return np.concatenate(parts) if parts else np.zeros(0)
+        super().__init__(model, f=flat)
+
+    def field(self, name):
+        off, shp = self._fields[name]
+        rows = shp[0] if len(shp) >= 1 else 0
+        cols = shp[1] if len(shp) == 2 else 0
+        out = C.c_int32()
+        m = self.model
+        m._ck(m._lib.pmb_op_getfield(m._ctx, self.node, off, len(shp), rows, cols, out))
+        return Expr(m, out.value)
+
+    def __getattr__(self, name):
+        if name.startswith("_") or "_fields" not in self.__dict__ or name not in self.__dict__["_fields"]:
+            raise AttributeError(name)
+        return self.field(name)
+
+
 def _cudart():
     """libcudart (already loaded by libpmb200.so) for the two scratch allocations of export_block_terms"""
     global _rt
@@ -610,6 +651,14 @@ def vcat(*parts, model=None):
     nodes = (C.c_int32 * len(parts))(*[m._as_node(p) for p in parts])
     out = C.c_int32()
     m._ck(m._lib.pmb_op_vcat(m._ctx, len(parts), nodes, out))
+    return Expr(m, out.value)
+
+
+def convert(x, model=None):
+    """`convert(Vector, x)` (lazyexpression.jl:280-282): any vector value as a Vector{AffineFunction}"""
+    m = model or _model_of(x)
+    out = C.c_int32()
+    m._ck(m._lib.pmb_op_convert(m._ctx, m._as_node(x), out))
     return Expr(m, out.value)
 
 

@@ -570,3 +570,69 @@ def test_two_models_interleaved():
             assert np.array_equal(Cb, A.val) and np.array_equal(db, -b.val)
     for m, _, _ in models:
         m.close()
+
+
+def test_getfield_rule_on_a_struct_valued_parameter():
+    """test/lazyexpression.jl:355-382 (`ex1 = @expression p.x`, `ex2 = @expression p.x + 1`) restated on the device: a struct-valued
+    Parameter is one flat record; `p.field` lowers to GetField (lazyexpression.jl:300-302, functions.jl:998-999).  The fields feed an
+    objective and a constraint, are re-evaluated ONCE per update! with the record, and match the literal oracle."""
+    import parametron_b200 as pm
+    n = 4
+    rng = np.random.default_rng(21)
+
+    class MyWrapper:
+        def __init__(self):
+            self.x = float(rng.random())            # scalar field
+            self.w = rng.random(n)                  # vector field
+            self.M = rng.random((3, n))             # matrix field (column-major on the device)
+
+    m = pm.Model()
+    x = m.variables(n)
+    p = pm.RecordParameter(m, MyWrapper, {"x": (), "w": (n,), "M": (3, n)})
+    ex1 = p.x                                        # @expression p.x
+    ex2 = p.x + 1.0                                  # @expression p.x + 1
+    pm.objective(m, pm.Minimize, ex2 * pm.dot(p.w, x) + ex1)          # (p.x + 1) * (w . x) + p.x
+    pm.constraint(m, p.M * x, "==", np.arange(3.0))
+    m.initialize()
+    for _ in range(3):
+        evals = p.evaluations
+        m.update()
+        assert p.evaluations == evals + 1           # parameter.jl:93-104: once per update!
+        rec = p.record
+        Q, q, c0 = m.objective_arrays()
+        assert_close(q, (rec.x + 1.0) * rec.w, 1e-14, "q"); assert_close([c0], [rec.x], 1e-14, "c0")
+        Cb, db = m.block_arrays(0)
+        assert np.array_equal(Cb, rec.M) and np.array_equal(db, -np.arange(3.0))
+    # the string-macro form lowers `p.x` through the same rule
+    m2 = pm.Model()
+    x2 = m2.variables(n)
+    p2 = pm.RecordParameter(m2, MyWrapper, {"x": (), "w": (n,), "M": (3, n)})
+    pm.macros.objective(m2, pm.Minimize, "(p.x + 1) * (p.w ⋅ x) + p.x", p=p2, x=x2)
+    m2.initialize(); m2.update()
+    _, q2, c2 = m2.objective_arrays()
+    assert_close(q2, (p2.record.x + 1.0) * p2.record.w, 1e-14, "q macro"); assert_close([c2], [p2.record.x], 1e-14, "c0 macro")
+    with pytest.raises(pm.DimensionMismatch):
+        m3 = pm.Model()
+        p3 = pm.RecordParameter(m3, MyWrapper, {"x": (), "w": (n,), "M": (3, n)})
+        out = __import__("ctypes").c_int32()
+        m3._ck(m3._lib.pmb_op_getfield(m3._ctx, p3.node, 10, 1, 100, 0, out))   # field outside the record
+
+
+def test_convert_rule():
+    """test/lazyexpression.jl:265-277: `convert(Vector, A * x)` == A * x as a Vector{AffineFunction} (copyto!, lazyexpression.jl:280-282)."""
+    import parametron_b200 as pm
+    rng = np.random.default_rng(22)
+    Av = rng.integers(1, 4, size=(3, 3)).astype(float)
+    m = pm.Model()
+    x = m.variables(3)
+    A = pm.Parameter(m, f=lambda: Av)
+    e = pm.convert(A * x)
+    pm.constraint(m, e, "==", np.zeros(3))
+    pm.macros.constraint(m, "convert(Vector, x) >= l", x=x, l=np.ones(3))   # a Vector{Variable} converts too
+    m.initialize(); m.update()
+    Cb, db = m.block_arrays(0)
+    views = [m.block_view(i) for i in range(m.num_blocks())]
+    arrs = [m.block_arrays(i) for i in range(m.num_blocks())]
+    assert any(np.array_equal(C_, Av) and np.array_equal(d_, np.zeros(3)) for C_, d_ in arrs)
+    assert any(np.array_equal(C_, np.eye(3)) and np.array_equal(d_, -np.ones(3)) for C_, d_ in arrs)
+    assert len(views) == 2
