@@ -225,3 +225,40 @@ def test_pipelined_upload_slice_gram_download(monkeypatch, tol, expect_repairs):
         assert np.array_equal(sink["A_x"][0], P["C"].val.T.ravel())
         lv = model.gram_level_counts()
         assert (lv[2] == 1) == expect_repairs
+
+
+@pytest.mark.parametrize("mode", [5, 6])
+def test_device_is_bit_identical_to_the_numpy_restatement(mode):
+    """oracle/int8_slices.py restates the device algorithm (scale, rounding, digit planes, exact integer plane products, Horner chain,
+    scaling order) in numpy; tests/test_oracle_int8_slices.py proves the certificate on that restatement.  Integer accumulation is
+    exact, so the device must reproduce it bit for bit (upper triangle; the lower one is its mirror) -- which ties the CPU-side
+    proof of the error bound to the CUDA implementation."""
+    import parametron_b200 as pm
+    from oracle import int8_slices as S
+    n, k, m = 200, 300, 2
+    rng = np.random.default_rng(77 + mode)
+    vals = [rng.standard_normal(s) for s in ((k, n), (k,), (m, n), (m,))]
+    model, params = ls_model(pm, n, k, m, gram_mode=mode)
+    model.initialize()
+    upload_all(params, vals)
+    model.update()
+    Q = model.objective_arrays()[0]
+    Qe, stats = S.gram(vals[0], mode, alpha=2.0)
+    iu = np.triu_indices(n)
+    assert np.array_equal(Q[iu], Qe[iu])
+    assert np.array_equal(Q, Q.T)
+
+
+def test_certificate_verdict_matches_the_numpy_restatement(monkeypatch):
+    import parametron_b200 as pm
+    from oracle import int8_slices as S
+    monkeypatch.setenv("PMB_GRAM_I8_ALWAYS", "1")
+    n, k, m, B = 128, 192, 2, 3
+    rng = np.random.default_rng(5)
+    A = np.stack([rng.random((k, n)), rng.standard_normal((k, n)), rng.standard_normal((k, n)) * 10.0 ** (8.0 * rng.random((k, n)) - 4.0)])
+    model, params = ls_model(pm, n, k, m, batch=B, gram_mode=1)
+    model.initialize()
+    upload_all(params, (A, rng.random((B, k)), rng.random((B, m, n)), rng.random((B, m))))
+    model.update()
+    want = [S.level(S.slice_columns(A[i])[2]) for i in range(B)]
+    assert model.gram_level_counts() == (want.count(5), want.count(6), want.count(64))
