@@ -264,7 +264,7 @@ int pmb_get_stats(pmb_ctx* ctx, pmb_stats* out);
 /* Precision mode of the objective-Hessian contraction (build phase).  The reference accumulates every product in Float64
  * (functions.jl:548-576); the north_star tolerance is 1e-10 relative.  mode 1 (default): contractions large enough to amortise it run
  * as exact integer products of int8 digit planes on the tcgen05 tensor cores whenever a worst-case error bound computed from the
- * operand (tol, default 5e-11, relative to the largest |Q| entry) certifies the result -- per instance, 5 or 6 planes; everything
+ * operand (tol, default 9e-11, relative to the largest |Q| entry) certifies the result -- per instance, 5 or 6 planes; everything
  * else runs on the fp64 DMMA pipe.  mode 0: fp64 only.  modes 5 / 6: force that many planes (experiments, no certificate). */
 int pmb_set_gram_mode(pmb_ctx* ctx, int mode, double tol);
 /* instances of the most recent update whose contraction ran with 5 planes / 6 planes / in fp64: counts[3] */

@@ -52,7 +52,7 @@ def reconstruct(digits, sigma, ns=PLANES):
     return y * sigma[None, :]
 
 
-def level(stats, tol=5e-11):
+def level(stats, tol=9e-11):
     """gram_i8_compute_level (pmb_kernels.h): 5, 6 or 64 (= fp64)"""
     if stats["bad"]:
         return 64
