@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
         const double* xs = (const double*)slice_smem + (int64_t)rs * kpe;
         if (RING) i8::mb_wait(&ring_full[rs], (ring_it / kI8SliceRing) & 1);
         double vc[CIT][4];
-        double amax = 0.0, ss = 0.0, l1 = 0.0, dg = 0.0, gg = 0.0;
+        double amax = 0.0, ss = 0.0, l1 = 0.0, dg = 0.0, dg2 = 0.0, gg = 0.0;
         bool bad = false;
         auto stat4 = [&](const double (&v)[4], int64_t r0) {
 #pragma unroll
@@ -267,8 +267,11 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             if (g) {
                 double gv[4];
                 load4(g, r0, a.k, gvecal, gv);
+                dg = fma(v[0], gv[0], dg); dg2 = fma(v[1], gv[1], dg2); dg = fma(v[2], gv[2], dg); dg2 = fma(v[3], gv[3], dg2);
+                if (j == 0) {   // g.g is needed once per instance: the group that owns column 0 computes it
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { dg = fma(v[e], gv[e], dg); gg = fma(gv[e], gv[e], gg); }
+                    for (int e = 0; e < 4; ++e) gg = fma(gv[e], gv[e], gg);
+                }
             }
         };
         if (live) {
@@ -297,6 +300,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
                 }
             }
         }
+        dg += dg2;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
