@@ -247,7 +247,11 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
     for (int64_t c0 = (int64_t)blockIdx.x * G; c0 < total; c0 += (int64_t)gridDim.x * G) {   // uniform per CTA (block-wide barriers below)
         const int64_t c = c0 + grp;
         const bool live = c < total;
-        const int64_t inst = live ? c / a.ncols : 0, j = live ? a.col0 + (c - inst * a.ncols) : 0;
+        int64_t inst = 0, j = 0;
+        if (live) {   // 64-bit division is ~70 instructions: the planner guarantees batch * n < 2^31
+            const uint32_t q32 = (uint32_t)c / (uint32_t)a.ncols;
+            inst = q32; j = a.col0 + (int64_t)((uint32_t)c - q32 * (uint32_t)a.ncols);
+        }
         const double* x = a.X + inst * a.x_bstride + j * a.ldx;
         const double* g = a.gvec ? a.gvec + inst * a.g_bstride : nullptr;
         const int rs = (int)(ring_it % kI8SliceRing);
@@ -316,21 +320,27 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             if (RING && threadIdx.x == 0) {   // every thread holds its rows in registers: the slot can take the column 3 ahead
                 const int64_t cn = c0 + (int64_t)kI8SliceRing * gridDim.x;
                 if (cn < total) {
-                    const int64_t in2 = cn / a.ncols, j2 = a.col0 + (cn - in2 * a.ncols);
+                    const uint32_t q2 = (uint32_t)cn / (uint32_t)a.ncols;
+                    const int64_t in2 = q2, j2 = a.col0 + (int64_t)((uint32_t)cn - q2 * (uint32_t)a.ncols);
                     i8::mb_expect_tx(&ring_full[rs], (uint32_t)(kpe * 8));
                     i8::bulk_load_1d(i8::s_u32(slice_smem) + (uint32_t)(rs * kpe * 8), a.X + in2 * a.x_bstride + j2 * a.ldx, (uint32_t)(kpe * 8), &ring_full[rs]);
                 }
             }
             ++ring_it;
-            amax = 0.0; ss = 0.0; l1 = 0.0; dg = 0.0; gg = 0.0;
+            amax = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) { amax = fmax(amax, red[w][0]); ss += red[w][1]; l1 += red[w][2]; dg += red[w][3]; gg += red[w][4]; }
+            for (int w = 0; w < 8; ++w) amax = fmax(amax, red[w][0]);
+            if (tig == 0) {   // the column's sums are only consumed by the thread that keeps the running statistics
+                ss = 0.0; l1 = 0.0; dg = 0.0; gg = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { ss += red[w][1]; l1 += red[w][2]; dg += red[w][3]; gg += red[w][4]; }
+            }
             bad = !(amax <= DBL_MAX);
         }
         if (amax > 0.0 && !(amax >= 1e-150 && amax <= 1e150)) bad = true;
         const bool zero = !(amax > 0.0) || bad;
         const double sigma = zero ? 1.0 : amax * (1.0 / 0.99);
-        const double mult = zero ? 0.0 : ldexp(0.99 / amax, 8 * NP - 1);   // x -> fixed point with 47 fractional bits of x / sigma
+        const double mult = zero ? 0.0 : (0.99 / amax) * 140737488355328.0;   // 2^47: x -> fixed point with 47 fractional bits of x / sigma
         int8_t* dst = a.slices + ((inst * NP) * a.n + j) * a.kp;
         uint32_t dsq[NP];
 #pragma unroll
@@ -383,11 +393,13 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
                 for (int s = 0; s < NP; ++s) redu[warp][s] = dsq[s];
             }
             __syncthreads();
+            if (tig == 0) {
 #pragma unroll
-            for (int s = 0; s < NP; ++s) {
-                dsq[s] = 0u;
+                for (int s = 0; s < NP; ++s) {
+                    dsq[s] = 0u;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) dsq[s] += redu[w][s];
+                    for (int w = 0; w < 8; ++w) dsq[s] += redu[w][s];
+                }
             }
             __syncthreads();   // red / redu are rewritten by the next column
         }
@@ -658,7 +670,7 @@ GramI8Plan plan_gram_i8(int64_t k, int64_t n, int64_t batch) {
     GramI8Plan p{};
     if (!encode_fn_i8() || k <= 0 || n <= 0) return p;
     if (k * kGramI8Planes * 16384 >= (int64_t)1 << 31) return p;   // int32 accumulators: (s + t + 1) * k * 128 * 128 must stay below 2^31
-    if (n >= ((int64_t)1 << 31) / 2 || batch >= ((int64_t)1 << 31)) return p;
+    if (n >= ((int64_t)1 << 31) / 2 || batch >= ((int64_t)1 << 31) || batch * n >= ((int64_t)1 << 31)) return p;   // 32-bit column ids in the slice kernel
     p.ok = 1;
     p.kp = (k + 127) / 128 * 128;
     p.slice_bytes = batch * kGramI8Planes * n * p.kp;
