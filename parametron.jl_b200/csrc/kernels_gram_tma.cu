@@ -515,11 +515,12 @@ bool gram_tma_applicable(const double* X, int64_t ld, int64_t bstride, int64_t k
     return encode_fn() != nullptr && ld % 2 == 0 && ((uintptr_t)X & 15) == 0 && !(batch > 1 && (bstride % 2 != 0 || bstride == 0)) && k > 0 && n > 0;
 }
 
-// the fused linear part exists only in the small-problem (64-tile, less than one wave) instantiation
+// the fused linear part exists only in the 64-tile instantiation: latency-bound problems (less than one wave of 128-tiles) and small
+// instances in large batches (n <= 256; cfg3: 9.42 -> 9.09 ms per sweep, the Gram gets 14 % slower but the gemv + dot launch that
+// re-read every A goes away).  For large single problems the fusion costs more MMA-loop throughput than the 34 us gemv it removes.
 bool gram_fused_linear_supported(int64_t k, int64_t n, int64_t batch, int sm_count) {
     const GramSplitPlan pl = plan_gram_split(true, k, n, n, batch, sm_count);
-    const int64_t t128 = ((n + kTBM - 1) / kTBM) * ((n + kTBM - 1) / kTBM + 1) / 2 * batch;
-    return pl.bm == 64 && t128 < sm_count;
+    return pl.bm == 64;
 }
 
 bool launch_gram_syrk_tma(const GramArgs& g, const GramScratch& sc, int64_t batch, int sm_count, cudaStream_t stream) {
