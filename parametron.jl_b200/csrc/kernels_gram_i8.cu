@@ -173,7 +173,8 @@ __device__ __forceinline__ void load4(const double* x, int64_t r0, int64_t k, bo
     }
 }
 
-// A group of T threads (one warp, or the whole CTA for long columns) owns one column of X at a time.  Columns of up to 16 T rows
+// A group of T threads (8 / 16 lanes of a warp for short columns, one warp, or the whole CTA for long columns) owns one column of X at
+// a time.  Columns of up to 16 T rows
 // stay in registers between the statistics pass (largest magnitude, 2-norm, 1-norm, X'g) and the digit pass: X is read ONCE.
 // RING (T = 256, columns of at most 4096 rows, 16-byte aligned): the columns travel global -> shared memory as 1-D bulk copies
 // (cp.async.bulk on an mbarrier, SASS UBLKCP) three columns ahead of the arithmetic, so the HBM latency is off the dependent chain
@@ -305,8 +306,9 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             }
         }
         dg += dg2;
+        constexpr int W = T < 32 ? T : 32;   // lanes that share a column inside one warp (short columns: several columns per warp)
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
+        for (int o = W / 2; o; o >>= 1) {
             amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
             ss += __shfl_xor_sync(0xffffffffu, ss, o);
             l1 += __shfl_xor_sync(0xffffffffu, l1, o);
@@ -385,8 +387,15 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
                 }
             }
         }
+        if (W == 32) {
 #pragma unroll
-        for (int s = 0; s < NP; ++s) dsq[s] = __reduce_add_sync(0xffffffffu, dsq[s]);
+            for (int s = 0; s < NP; ++s) dsq[s] = __reduce_add_sync(0xffffffffu, dsq[s]);
+        } else {
+#pragma unroll
+            for (int s = 0; s < NP; ++s)
+#pragma unroll
+                for (int o = W / 2; o; o >>= 1) dsq[s] += __shfl_xor_sync(0xffffffffu, dsq[s], o);
+        }
         if (T == 256) {
             if (lane == 0) {
 #pragma unroll
@@ -704,6 +713,12 @@ bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t ba
     } else if (sc.plan.kp > 1024) {   // long columns: the whole CTA owns one column (up to 4096 rows cached in registers)
         const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * 4);
         gram_i8_slice_kernel<256, false><<<sgrid, 256, 0, stream>>>(s);
+    } else if (sc.plan.kp <= 128) {   // short columns: 8 / 16 lanes per column, 32 / 16 columns per CTA pass (16 rows per lane, cached)
+        const int sgrid = (int)std::min<int64_t>((cols + 31) / 32, (int64_t)sm_count * 4);
+        gram_i8_slice_kernel<8, false><<<sgrid, 256, 0, stream>>>(s);
+    } else if (sc.plan.kp <= 256) {
+        const int sgrid = (int)std::min<int64_t>((cols + 15) / 16, (int64_t)sm_count * 4);
+        gram_i8_slice_kernel<16, false><<<sgrid, 256, 0, stream>>>(s);
     } else {
         const int sgrid = (int)std::min<int64_t>((cols + 7) / 8, (int64_t)sm_count * 4);
         gram_i8_slice_kernel<32, false><<<sgrid, 256, 0, stream>>>(s);
