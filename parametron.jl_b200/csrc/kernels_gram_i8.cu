@@ -46,6 +46,8 @@ struct I8Cfg {
     static constexpr int kStages = (227 * 1024 - 2048) / kStageBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
     static constexpr int kGrp = 256 / BN;          // column-panel planes covered by one MMA (N = kGrp * BN <= 256)
+    static constexpr int kAccBufs = (2 * NS * BN <= kI8TmemCols) ? 2 : 1;   // narrow tiles: two accumulator sets, the epilogue of a
+                                                                            // tile overlaps the MMAs of the next (short-k problems)
     static_assert(NS * BN <= kI8TmemCols, "accumulators do not fit TMEM");
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "tcgen05 kind::i8, M = 128: N % 16 == 0");
     static_assert(kStages >= 2, "pipeline needs two stages");
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[C::kStages];
     __shared__ __align__(8) uint64_t empty_bar[C::kStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar, tmem_empty_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_slot;
     __shared__ double sfj[BN];       // sigma_j 2^(-4 NS - 3) of the tile's columns
     __shared__ int32_t mapj[BN];     // output index of the tile's columns
@@ -485,8 +487,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < C::kStages; ++s) { i8::mb_init(&full_bar[s], 1); i8::mb_init(&empty_bar[s], 1); }
-        i8::mb_init(&tmem_full_bar, 1);
-        i8::mb_init(&tmem_empty_bar, kI8EpiWarps);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { i8::mb_init(&tmem_full_bar[b], 1); i8::mb_init(&tmem_empty_bar[b], kI8EpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) i8::tmem_alloc(&tmem_slot, kI8TmemCols);
@@ -523,7 +525,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
             for (int64_t u = blockIdx.x; u < a.total_tiles; u += gridDim.x) {
                 const I8Unit w = i8_decode<BN>(a, u);
                 if (!i8_runs<NS>(a, w.inst)) continue;
-                i8::mb_wait(&tmem_empty_bar, (tile_it & 1) ^ 1);   // the epilogue has drained the previous tile
+                const uint32_t ab = tile_it % C::kAccBufs, ause = tile_it / C::kAccBufs;   // accumulator set and how often it was used
+                i8::mb_wait(&tmem_empty_bar[ab], (ause & 1) ^ 1);   // the epilogue has drained this accumulator set
                 i8::tc_fence_after();
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const int s = it % C::kStages;
@@ -543,13 +546,13 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                             for (int sj = 0; sj <= NS - 1 - si; sj += C::kGrp) {
                                 const int gsz = (NS - si - sj) < C::kGrp ? (NS - si - sj) : C::kGrp;
                                 const uint64_t bd = i8::smem_desc_sw64(stage + NS * C::kITile + sj * C::kJTile + kk * 32);
-                                i8::mma_i8(tmem_base + (uint32_t)((si + sj) * BN), ad, bd, i8_idesc(gsz * BN), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
+                                i8::mma_i8(tmem_base + (uint32_t)(ab * NS * BN + (si + sj) * BN), ad, bd, i8_idesc(gsz * BN), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
                             }
                         }
                     }
                     i8::mma_commit(&empty_bar[s]);   // the stage may be refilled once these MMAs have read it
                 }
-                i8::mma_commit(&tmem_full_bar);
+                i8::mma_commit(&tmem_full_bar[ab]);
                 ++tile_it;
             }
         }
@@ -578,13 +581,15 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
             double* out = a.out + w.inst * a.o_bstride;
             double* pk = a.packed_dev ? a.packed_dev + w.inst * a.packed_bstride : nullptr;
             i8::epi_bar();   // sfj / mapj visible
-            i8::mb_wait(&tmem_full_bar, tile_it & 1);
+            const uint32_t ab = tile_it % C::kAccBufs, ause = tile_it / C::kAccBufs;
+            i8::mb_wait(&tmem_full_bar[ab], ause & 1);
             i8::tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-            // interior tile (strictly above the diagonal, no ragged edge), identity map, overwrite: unpredicated stores -- the direct
-            // triangle coalesces across the lanes (consecutive rows), the mirrored one is 16 consecutive doubles per thread (4 x 256-bit)
-            const bool fast = !a.map && !a.accumulate && i0 + kI8BM <= j0 && j0 + BN <= a.n && (a.ldo & 3) == 0 && (a.o_bstride & 3) == 0 &&
-                              (((uintptr_t)a.out) & 31) == 0;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)(NS * BN);
+            // identity map, overwrite, aligned output: a 16-column chunk that lies strictly above the diagonal for this thread's row and
+            // inside the matrix is stored without predicates -- the direct triangle coalesces across the lanes (consecutive rows), the
+            // mirrored one is 16 consecutive doubles per thread (4 x 256-bit stores).  Decided per (row, chunk), so tiles that straddle
+            // the diagonal or the ragged edge (all tiles of a 256 x 256 instance) still take it for most of their chunks.
+            const bool vec_ok = !a.map && !a.accumulate && (a.ldo & 3) == 0 && (a.o_bstride & 3) == 0 && (((uintptr_t)a.out) & 31) == 0;
 #pragma unroll 1
             for (int c0 = 16 * chalf; c0 < BN; c0 += 16 * (kI8EpiWarps / 4)) {
                 int32_t acc[NS][16];
@@ -599,7 +604,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                     for (int l = 1; l < NS; ++l) t = fma(t, 256.0, (double)acc[l][jj]);
                     v[jj] = t * fi * sfj[c0 + jj];
                 }
-                if (fast) {
+                if (vec_ok && row_ok && gi < j0 + c0 && j0 + c0 + 16 <= a.n) {
                     double* p1 = out + gi + (j0 + c0) * a.ldo;
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) p1[(int64_t)jj * a.ldo] = v[jj];
@@ -636,7 +641,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
             }
             i8::tc_fence_before();
             __syncwarp();
-            if (lane == 0) i8::mb_arrive(&tmem_empty_bar);
+            if (lane == 0) i8::mb_arrive(&tmem_empty_bar[ab]);
             i8::epi_bar();   // sfj / mapj are rewritten for the next tile
             ++tile_it;
         }
@@ -689,6 +694,7 @@ GramI8Plan plan_gram_i8(int64_t k, int64_t n, int64_t batch) {
 void configure_gram_i8_kernels() {
     cudaFuncSetAttribute(gram_i8_kernel<5, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 96>::kSmemBytes);
     cudaFuncSetAttribute(gram_i8_kernel<6, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6, 80>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_kernel<5, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 48>::kSmemBytes);
     cudaFuncSetAttribute(gram_i8_slice_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SliceRing * 4096 * 8 + 64);
 }
 
@@ -781,7 +787,13 @@ bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batc
     if (!sc.plan.ok || !sc.slices || g.packed_host || g.gate) return false;
     if (col1 < 0) col1 = g.n;
     bool ok = true;
-    if (sc.force_ns != 6) ok = ok && launch_i8_impl<5, 96>(g, sc, batch, sm_count, stream, col0, col1);
+    // experiment (PMB_I8_NARROW=1): 48-wide tiles keep TWO accumulator sets in TMEM, so the epilogue of a tile overlaps the MMAs of the
+    // next, and multiply plane s against up to five column-panel planes per instruction.  Measured slower than the 96-wide tiles even
+    // for short contractions (1024 x (256 x 256): 0.55 vs 0.40 ms; n = 4096, k = 512: 0.109 vs 0.083 ms): twice the tiles, twice the
+    // row-panel traffic.  Kept for the accumulator double-buffering it exercises.
+    const bool narrow = sc.plan.kp <= 512 && getenv("PMB_I8_NARROW") != nullptr;
+    if (sc.force_ns != 6) ok = ok && (narrow ? launch_i8_impl<5, 48>(g, sc, batch, sm_count, stream, col0, col1)
+                                             : launch_i8_impl<5, 96>(g, sc, batch, sm_count, stream, col0, col1));
     if (sc.force_ns != 5) ok = ok && launch_i8_impl<6, 80>(g, sc, batch, sm_count, stream, col0, col1);
     return ok;
 }
