@@ -30,7 +30,7 @@ N_VARS, K_ROWS, M_ROWS = 4096, 4096, 1024
 SEED = 1234
 METRIC = "QP re-parameterizations/sec (update!+coeff-assemble) at n=4096,m=1024"
 GRAM_DRAM_TRAFFIC_BYTES = 410174464 + 167363328    # ncu --set full, one launch of gram_tma_kernel<1,128> at cfg2
-GRAM_I8_DRAM_TRAFFIC_BYTES = 275519488 + 115255296    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r01_n_gram_i8_ncu_full.txt)
+GRAM_I8_DRAM_TRAFFIC_BYTES = 283136512 + 117279744    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r01_n_gram_i8_ncu_full.txt)
 AFFINE_DRAM_TRAFFIC_BYTES = 33626880 + 1335808       # ncu --set full, one launch of affine_assemble_tma<0> at cfg2 (profiles/r01_n_affine_tma_ncu_full.txt)
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200: profiles/r01_probe_dmma.txt (mma.sync f64, all SMs)
 
@@ -270,7 +270,7 @@ def main():
                     "algorithmic_ops": int(nprod * syrk_flops), "avg_launch_ms": i8_ms,
                     "peak_source": f"2 x bf16_tflops (burst) of MEASURED_PEAKS.json ({peak_src}): the int8 dense rate of tcgen05 is twice the bf16 rate "
                                    "(4.5 vs 2.25 POP/s nominal); MEASURED_PEAKS.json has no int8 entry.  ncu's own counter for the same launch: "
-                                   "sm__ops_path_tensor_op_utcimma_src_int8 = 72.2 % of its peak (16384 ops/clk/SM at the 1.69 GHz the SMs hold under this load), profiles/r01_n_gram_i8_ncu_full.txt",
+                                   "sm__ops_path_tensor_op_utcimma_src_int8 = 71-72 % of its peak (16384 ops/clk/SM at the 1.69 GHz the SMs hold under this load), profiles/r01_n_gram_i8_ncu_full.txt",
                     "fp64_equivalent_tflops": syrk_flops / ((i8_ms + slice_ms) * 1e-3) / 1e12,
                     "fp64_equivalent_note": f"SYRK-counted fp64 flops / (slice {slice_ms:.3f} ms + tcgen05 {i8_ms:.3f} ms); the fp64 DMMA pipe peaks at "
                                             f"{FP64_DMMA_PEAK_TFLOPS} TFLOP/s (profiles/r01_probe_dmma.txt), the fp64 kernel reached 33 (profiles/r01_m_*)",
