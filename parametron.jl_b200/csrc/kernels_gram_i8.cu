@@ -607,16 +607,17 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                 if (vec_ok && row_ok && gi < j0 + c0 && j0 + c0 + 16 <= a.n) {
                     double* p1 = out + gi + (j0 + c0) * a.ldo;
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) p1[(int64_t)jj * a.ldo] = v[jj];
+                    // streaming stores (evict-first): Q is written once and not re-read here, the digit planes (100 MB) should keep the L2
+                    for (int jj = 0; jj < 16; ++jj) __stcs(p1 + (int64_t)jj * a.ldo, v[jj]);
                     double* p2 = out + (j0 + c0) + gi * a.ldo;
 #pragma unroll
                     for (int jj = 0; jj < 16; jj += 4)
-                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p2 + jj), "d"(v[jj]), "d"(v[jj + 1]), "d"(v[jj + 2]), "d"(v[jj + 3]) : "memory");
+                        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p2 + jj), "d"(v[jj]), "d"(v[jj + 1]), "d"(v[jj + 2]), "d"(v[jj + 3]) : "memory");
                     if (pk) {
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) {
                             const int64_t gj = j0 + c0 + jj;
-                            pk[gj * (gj + 1) / 2 + gi] = v[jj];
+                            __stcs(pk + gj * (gj + 1) / 2 + gi, v[jj]);
                         }
                     }
                     continue;
