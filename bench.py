@@ -312,8 +312,10 @@ def main():
         esteps = max(3, min(args.steps, 20))
         ems = timed(e2e_step, esteps) / esteps
         h2d = 8 * (K_ROWS * N_VARS + K_ROWS + M_ROWS * N_VARS + M_ROWS)
+        elv = em.gram_level_counts()
         e2e = {"value": world * 1e3 / ems, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems,
-               "steps": esteps}
+               "steps": esteps, "gram_levels": {"int8_5_planes": elv[0], "int8_6_planes": elv[1], "fp64": elv[2]},
+               "schedule": "chunked upload || per-chunk slice + ranged tcgen05 Gram || streamed P_x download (DESIGN.md section 4, pipe8)"}
         # sanity: the e2e result is the dense meaning of the host inputs (spot checks, fp64)
         i, j = 17, 2049
         ref = 2.0 * float(host["A"][:, i] @ host["A"][:, j])
