@@ -33,28 +33,55 @@
 namespace pmb {
 
 constexpr int kI8BM = 128;          // tile rows = tcgen05 M (one TMEM lane per row)
-constexpr int kI8KC = 64;           // k (bytes) per pipeline stage: one 64-byte swizzle span, two K=32 MMAs per digit-plane pair
+constexpr int kI8KC = 64;           // default k (bytes) per pipeline stage: one 64-byte swizzle span, two K=32 MMAs per digit-plane pair
+                                    // (KC = 32: one 32-byte swizzle span, one MMA; twice the stages for the same bytes in flight)
 constexpr int kI8EpiWarps = 8;       // two warps per TMEM lane quarter, alternating 16-column chunks
 constexpr int kI8Threads = 64 + 32 * kI8EpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int kI8TmemCols = 512;
 
-template <int NS, int BN>
+// CTAS = 1: one CTA per (128 x BN) tile, tcgen05 cta_group::1.  CTAS = 2: a CTA pair (cluster of 2, one TPC) per (256 x BN) tile,
+// cta_group::2 with M = 256: CTA r holds rows 128 r .. 128 r + 127 of the tile (own row panel, own TMEM accumulators) and supplies HALF of
+// every column-panel operand -- for an instruction over two consecutive planes t, t+1 (N = 2 BN) CTA 0 holds plane t and CTA 1 plane t+1 of
+// the tile's BN columns ("pair slot" t/2), for an instruction over a single plane (N = BN; the planes t = NS-1-s with NS-s odd, all even)
+// CTA r holds columns BN/2 r .. of it ("half slot" t/2).  Per k step a CTA then writes 27.5-30.5 KB and the tensor pipe reads 58.5 KB of
+// shared memory instead of 35 + 81 KB: the one-CTA kernel is bound by exactly that traffic (161 B/clk wanted, 128 B/clk available).
+template <int NS, int BN, int CTAS = 1, int KC = kI8KC>
 struct I8Cfg {
-    static constexpr int kITile = kI8BM * kI8KC;   // bytes of one digit plane of the row panel
-    static constexpr int kJTile = BN * kI8KC;
-    static constexpr int kStageBytes = NS * (kITile + kJTile);
-    static constexpr int kStages = (227 * 1024 - 2048) / kStageBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+    static constexpr int kRows = kI8BM * CTAS;     // tile rows
+    static constexpr int kKC = KC;
+    static constexpr int kITile = kI8BM * KC;   // bytes of one digit plane of the (CTA's) row panel
+    static constexpr int kJTile = BN * KC;
+    static constexpr int kNPair = NS / 2, kNHalf = (NS + 1) / 2;                    // CTAS = 2: pair slots and half slots per stage
+    static constexpr int kHalfBytes = BN / 2 * KC;                               // bytes a half slot receives
+    static constexpr int kHalfTile = (kHalfBytes + 16 * KC - 1) / (16 * KC) * (16 * KC);   // its footprint (slots stay aligned to two swizzle periods)
+    // KC = 128 ("wide"): rows of 128 bytes under the 128-byte swizzle.  The TMA engine moves about one box ROW per clock whatever its
+    // length (measured: 64-byte and 32-byte rows take the same time, one box per plane or one per panel as well), so 128-byte rows
+    // double the fill rate.  A whole k step (NS (16 + BN / 8) KB = 140 KB) no longer double-buffers, so the ring is split: kStages = 2
+    // column-panel stages (all NS planes, consecutive: the grouped MMAs span plane boundaries) and kNA row-panel slots of one plane;
+    // the MMA issuer walks the rows s = 0 .. NS-1 of a k step and releases each row-panel slot as soon as its row is done.
+    static constexpr bool kWide = KC == 128;
+    static constexpr int kBStage = NS * kJTile;
+    static constexpr int kStageBytes = kWide ? kBStage : CTAS == 1 ? NS * (kITile + kJTile) : NS * kITile + kNPair * kJTile + kNHalf * kHalfTile;
+    static constexpr int kTxBytes = CTAS == 1 ? kStageBytes : NS * kITile + kNPair * kJTile + kNHalf * kHalfBytes;   // per CTA and stage
+    static constexpr int kStages = kWide ? 2 : (227 * 1024 - 2048) / kStageBytes;
+    static constexpr int kNA = kWide ? (227 * 1024 - 2048 - kStages * kStageBytes) / kITile : 1;
+    static constexpr int kSmemBytes = kStages * kStageBytes + (kWide ? kNA * kITile : 0) + 1024;
     static constexpr int kGrp = 256 / BN;          // column-panel planes covered by one MMA (N = kGrp * BN <= 256)
     static constexpr int kAccBufs = (2 * NS * BN <= kI8TmemCols) ? 2 : 1;   // narrow tiles: two accumulator sets, the epilogue of a
                                                                             // tile overlaps the MMAs of the next (short-k problems)
+    static_assert(CTAS == 1 || CTAS == 2, "one CTA or a CTA pair");
+    static_assert(KC == 128 || KC == 64 || KC == 32, "one swizzle span per stage");
+    static_assert(!kWide || (CTAS == 1 && kNA >= 2 && kNA <= 8), "wide stages: one-CTA kernel");
     static_assert(NS * BN <= kI8TmemCols, "accumulators do not fit TMEM");
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "tcgen05 kind::i8, M = 128: N % 16 == 0");
+    static_assert(CTAS == 1 || (2 * BN <= 256 && BN % 16 == 0), "cta_group::2, M = 256: N % 16 == 0, N <= 256");
     static_assert(kStages >= 2, "pipeline needs two stages");
 };
 
 struct GramI8KernelArgs {
     CUtensorMap tmi, tmj;   // digit planes (kp, n, 6, batch) uint8; boxes (64, 128, 1, 1) and (64, BN, 1, 1), 64-byte swizzle
+    CUtensorMap tmh;        // CTA-pair kernel: box (64, BN / 2, 1, 1)
+    CUtensorMap tmja;       // wide stages: all NS planes of the column panel in ONE box (128, BN, NS, 1)
     int64_t k, kp, n;
     const double* sigma;    // [batch][n]
     const unsigned long long* stats;
@@ -67,6 +94,7 @@ struct GramI8KernelArgs {
     double* packed_dev; int64_t packed_bstride;
     int32_t tj0, tj1;       // tile columns [tj0, tj1) of every instance
     int64_t tiles_per_inst, total_tiles;
+    int32_t dbg;            // timing diagnostics only (PMB_I8_DBG): 1 = no TMA loads, 2 = no MMAs, 4 = only the s = 0 row of MMAs
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------------
@@ -127,6 +155,53 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
 }
+// ---- CTA pair (cta_group::2) flavours ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mb_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// the data lands in THIS CTA's shared memory, the transaction bytes are counted on the leader CTA's mbarrier
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem, uint32_t ncols) {   // one warp of EACH CTA of the pair, same slot offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(slot_in_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 over the pair: issued by ONE thread of the leader CTA; descriptors are offsets valid in both CTAs' shared memory
+__device__ __forceinline__ void mma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
 // 16 consecutive TMEM columns of this thread's lane (lane = 32 * (warp % 4) + laneid)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
     asm volatile(
@@ -142,8 +217,10 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 // shared-memory matrix descriptor of a K-major panel stored as rows of 64 bytes under the 64-byte swizzle (what the TMA box
 // (64 bytes, rows) with CU_TENSOR_MAP_SWIZZLE_64B writes): 8-row groups are 512 bytes apart (SBO), LBO is unused (1), Blackwell
 // descriptor version 1, layout type 4 = SWIZZLE_64B.  A K step of 32 bytes advances the start address by 32.
+template <int KC = 64>
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+    // rows of KC bytes under the KC-byte swizzle: 8-row groups are 8 KC bytes apart; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((8 * KC) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(KC == 128 ? 2 : KC == 64 ? 4 : 6) << 61);
 }
 }  // namespace i8
 
@@ -442,7 +519,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
 struct I8Unit { int64_t inst; int ti, tj; };
 
 // upper tiles, column-major: tile column tj (BN wide) holds the row tiles ti = 0 .. (last column of tj) / 128
-template <int BN>
+template <int BN, int ROWS = kI8BM>
 __device__ __forceinline__ I8Unit i8_decode(const GramI8KernelArgs& a, int64_t u) {
     I8Unit w;
     w.inst = u / a.tiles_per_inst;
@@ -450,7 +527,7 @@ __device__ __forceinline__ I8Unit i8_decode(const GramI8KernelArgs& a, int64_t u
     int tj = a.tj0;
     for (;; ++tj) {
         const int64_t lastcol = ((int64_t)(tj + 1) * BN < a.n ? (int64_t)(tj + 1) * BN : a.n) - 1;
-        const int64_t cnt = lastcol / kI8BM + 1;
+        const int64_t cnt = lastcol / ROWS + 1;
         if (tl < cnt) break;
         tl -= cnt;
     }
@@ -459,8 +536,8 @@ __device__ __forceinline__ I8Unit i8_decode(const GramI8KernelArgs& a, int64_t u
 }
 
 // instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed int8 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24
-__device__ __forceinline__ constexpr uint32_t i8_idesc(int n) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kI8BM >> 4) << 24);
+__device__ __forceinline__ constexpr uint32_t i8_idesc(int n, int m = kI8BM) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // this launch (NS planes) owns the instance?
@@ -469,31 +546,40 @@ __device__ __forceinline__ bool i8_runs(const GramI8KernelArgs& a, int64_t inst)
     return a.force_ns ? a.force_ns == NS : gram_i8_level(a.stats, inst) == NS;
 }
 
-template <int NS, int BN>
+template <int NS, int BN, int CTAS, int KC>
 __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_constant__ GramI8KernelArgs a) {
-    using C = I8Cfg<NS, BN>;
+    using C = I8Cfg<NS, BN, CTAS, KC>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[C::kStages];
     __shared__ __align__(8) uint64_t empty_bar[C::kStages];
     __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t full_a[8], empty_a[8];   // wide stages: row-panel slots
     __shared__ uint32_t tmem_slot;
     __shared__ double sfj[BN];       // sigma_j 2^(-4 NS - 3) of the tile's columns
     __shared__ int32_t mapj[BN];     // output index of the tile's columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ring = (i8::s_u32(smem_raw) + 1023u) & ~1023u;
-    const int nkc = (int)(a.kp / kI8KC);
+    const int nkc = (int)(a.kp / KC);
     if (a.total_tiles == a.tiles_per_inst && !i8_runs<NS>(a, 0)) return;   // one instance and it is not ours: leave before touching TMEM
+    // CTA pair: rank in the cluster; the leader (rank 0) owns the full / tmem_empty barriers and issues the MMAs for both CTAs
+    const uint32_t rank = CTAS == 2 ? i8::cluster_ctarank() : 0u;
+    const int64_t unit0 = CTAS == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+    const int64_t ustride = CTAS == 2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < C::kStages; ++s) { i8::mb_init(&full_bar[s], 1); i8::mb_init(&empty_bar[s], 1); }
+        for (int s = 0; s < C::kStages; ++s) { i8::mb_init(&full_bar[s], CTAS); i8::mb_init(&empty_bar[s], 1); }
 #pragma unroll
-        for (int b = 0; b < 2; ++b) { i8::mb_init(&tmem_full_bar[b], 1); i8::mb_init(&tmem_empty_bar[b], kI8EpiWarps); }
+        for (int s = 0; s < C::kNA; ++s) { i8::mb_init(&full_a[s], 1); i8::mb_init(&empty_a[s], 1); }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { i8::mb_init(&tmem_full_bar[b], 1); i8::mb_init(&tmem_empty_bar[b], kI8EpiWarps * CTAS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) i8::tmem_alloc(&tmem_slot, kI8TmemCols);
+    if (warp == 1) {
+        if constexpr (CTAS == 2) i8::tmem_alloc_pair(&tmem_slot, kI8TmemCols); else i8::tmem_alloc(&tmem_slot, kI8TmemCols);
+    }
     i8::tc_fence_before();
-    __syncthreads();
+    if constexpr (CTAS == 2) i8::cluster_sync_all(); else __syncthreads();   // the peer's barriers are initialised before anything arrives on them
     i8::tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
@@ -501,29 +587,65 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t u = blockIdx.x; u < a.total_tiles; u += gridDim.x) {
-                const I8Unit w = i8_decode<BN>(a, u);
+            [[maybe_unused]] uint32_t ita = 0;
+            for (int64_t u = unit0; u < a.total_tiles; u += ustride) {
+                const I8Unit w = i8_decode<BN, C::kRows>(a, u);
                 if (!i8_runs<NS>(a, w.inst)) continue;
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const int s = it % C::kStages;
                     i8::mb_wait(&empty_bar[s], ((it / C::kStages) & 1) ^ 1);
                     const uint32_t stage = ring + (uint32_t)s * C::kStageBytes;
-                    i8::mb_expect_tx(&full_bar[s], C::kStageBytes);
+                    if constexpr (C::kWide) {
+                        // column panel: all NS planes in one box (they are consecutive in shared memory in box order k, column, plane)
+                        if (a.dbg & 1) i8::mb_arrive(&full_bar[s]);
+                        else {
+                            i8::mb_expect_tx(&full_bar[s], C::kBStage);
+                            i8::tma_load_4d(stage, &a.tmja, kc * KC, w.tj * BN, 0, (int)w.inst, &full_bar[s]);
+                        }
+                        // row panel: one slot per plane, in the order the MMA issuer walks them
+#pragma unroll 1
+                        for (int sl = 0; sl < NS; ++sl, ++ita) {
+                            const int sa = ita % C::kNA;
+                            i8::mb_wait(&empty_a[sa], ((ita / C::kNA) & 1) ^ 1);
+                            if (a.dbg & 1) { i8::mb_arrive(&full_a[sa]); continue; }
+                            i8::mb_expect_tx(&full_a[sa], C::kITile);
+                            i8::tma_load_4d(ring + C::kStages * C::kStageBytes + sa * C::kITile, &a.tmi, kc * KC, w.ti * kI8BM, sl, (int)w.inst, &full_a[sa]);
+                        }
+                    } else if constexpr (CTAS == 2) {
+                        // both CTAs count their bytes on the LEADER's full barrier (2 arrivals + the bytes of both)
+                        const uint32_t fb = i8::mapa_u32(i8::s_u32(&full_bar[s]), 0);
+                        if (a.dbg & 1) { i8::mb_arrive_cluster(fb); continue; }   // timing diagnostics
+                        i8::mb_expect_tx_cluster(fb, C::kTxBytes);
+                        const int row0 = w.ti * C::kRows + (int)rank * kI8BM;
 #pragma unroll
-                    for (int sl = 0; sl < NS; ++sl)
-                        i8::tma_load_4d(stage + sl * C::kITile, &a.tmi, kc * kI8KC, w.ti * kI8BM, sl, (int)w.inst, &full_bar[s]);
+                        for (int sl = 0; sl < NS; ++sl) i8::tma_load_4d_pair(stage + sl * C::kITile, &a.tmi, kc * KC, row0, sl, (int)w.inst, fb);
 #pragma unroll
-                    for (int sl = 0; sl < NS; ++sl)
-                        i8::tma_load_4d(stage + NS * C::kITile + sl * C::kJTile, &a.tmj, kc * kI8KC, w.tj * BN, sl, (int)w.inst, &full_bar[s]);
+                        for (int ps = 0; ps < C::kNPair; ++ps)   // pair slot ps: plane 2 ps + rank, all BN columns
+                            i8::tma_load_4d_pair(stage + NS * C::kITile + ps * C::kJTile, &a.tmj, kc * KC, w.tj * BN, 2 * ps + (int)rank, (int)w.inst, fb);
+#pragma unroll
+                        for (int hs = 0; hs < C::kNHalf; ++hs)   // half slot hs: plane 2 hs, columns BN/2 rank ..
+                            i8::tma_load_4d_pair(stage + NS * C::kITile + C::kNPair * C::kJTile + hs * C::kHalfTile, &a.tmh, kc * KC,
+                                                 w.tj * BN + (int)rank * (BN / 2), 2 * hs, (int)w.inst, fb);
+                    } else {
+                        if (a.dbg & 1) { i8::mb_arrive(&full_bar[s]); continue; }   // timing diagnostics
+                        i8::mb_expect_tx(&full_bar[s], C::kStageBytes);
+#pragma unroll
+                        for (int sl = 0; sl < NS; ++sl)
+                            i8::tma_load_4d(stage + sl * C::kITile, &a.tmi, kc * KC, w.ti * kI8BM, sl, (int)w.inst, &full_bar[s]);
+#pragma unroll
+                        for (int sl = 0; sl < NS; ++sl)
+                            i8::tma_load_4d(stage + NS * C::kITile + sl * C::kJTile, &a.tmj, kc * KC, w.tj * BN, sl, (int)w.inst, &full_bar[s]);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread, all digit-plane pairs with s + t <= NS - 1, level s + t -> TMEM columns [(s+t) BN, +BN) =====
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             uint32_t it = 0, tile_it = 0;
-            for (int64_t u = blockIdx.x; u < a.total_tiles; u += gridDim.x) {
-                const I8Unit w = i8_decode<BN>(a, u);
+            [[maybe_unused]] uint32_t ita = 0;
+            for (int64_t u = unit0; u < a.total_tiles; u += ustride) {
+                const I8Unit w = i8_decode<BN, C::kRows>(a, u);
                 if (!i8_runs<NS>(a, w.inst)) continue;
                 const uint32_t ab = tile_it % C::kAccBufs, ause = tile_it / C::kAccBufs;   // accumulator set and how often it was used
                 i8::mb_wait(&tmem_empty_bar[ab], (ause & 1) ^ 1);   // the epilogue has drained this accumulator set
@@ -533,26 +655,78 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                     i8::mb_wait(&full_bar[s], (it / C::kStages) & 1);
                     i8::tc_fence_after();
                     const uint32_t stage = ring + (uint32_t)s * C::kStageBytes;
+                    if constexpr (C::kWide) {
 #pragma unroll
-                    for (int kk = 0; kk < kI8KC / 32; ++kk) {
+                        for (int si = 0; si < NS; ++si, ++ita) {
+                            const int sa = ita % C::kNA;
+                            i8::mb_wait(&full_a[sa], (ita / C::kNA) & 1);
+                            i8::tc_fence_after();
+                            const uint32_t apanel = ring + C::kStages * C::kStageBytes + sa * C::kITile;
+                            const int W = (NS - si) * BN, nm = (W + 255) / 256, per = ((W + nm - 1) / nm + 15) / 16 * 16;
+                            if (!((a.dbg & 2) || ((a.dbg & 4) && si > 0))) {
+#pragma unroll
+                                for (int kk = 0; kk < KC / 32; ++kk) {
+                                    const uint64_t ad = i8::smem_desc_sw64<KC>(apanel + kk * 32);
+#pragma unroll
+                                    for (int c = 0; c < W; c += per) {
+                                        const int wn = (W - c) < per ? (W - c) : per;
+                                        const uint64_t bd = i8::smem_desc_sw64<KC>(stage + c * KC + kk * 32);
+                                        i8::mma_i8(tmem_base + (uint32_t)(ab * NS * BN + si * BN + c), ad, bd, i8_idesc(wn), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
+                                    }
+                                }
+                            }
+                            i8::mma_commit(&empty_a[sa]);   // this row-panel slot may be refilled
+                        }
+                        i8::mma_commit(&empty_bar[s]);
+                    } else {
+#pragma unroll
+                    for (int kk = 0; kk < KC / 32; ++kk) {
+                        if constexpr (CTAS == 2) {
+                            // CTA pair: plane s of the 256-row panel against planes (t, t+1) of the column panel (N = 2 BN, one plane from
+                            // each CTA) for t = 0, 2, ..; a left-over single plane t = NS-1-s (N = BN, half of its columns from each CTA)
+                            // always lands on the last level
+#pragma unroll
+                            for (int si = 0; si < NS; ++si) {
+                                if ((a.dbg & 2) || ((a.dbg & 4) && si > 0)) continue;
+                                const uint64_t ad = i8::smem_desc_sw64<KC>(stage + si * C::kITile + kk * 32);
+                                const uint32_t first = (kc > 0 || kk > 0 || si > 0) ? 1u : 0u;
+#pragma unroll
+                                for (int t0 = 0; t0 + 1 < NS - si; t0 += 2) {
+                                    const uint64_t bd = i8::smem_desc_sw64<KC>(stage + NS * C::kITile + (t0 / 2) * C::kJTile + kk * 32);
+                                    i8::mma_i8_pair(tmem_base + (uint32_t)(ab * NS * BN + (si + t0) * BN), ad, bd, i8_idesc(2 * BN, 256), first);
+                                }
+                                if ((NS - si) & 1) {
+                                    const uint64_t bd = i8::smem_desc_sw64<KC>(stage + NS * C::kITile + C::kNPair * C::kJTile + ((NS - 1 - si) / 2) * C::kHalfTile + kk * 32);
+                                    i8::mma_i8_pair(tmem_base + (uint32_t)(ab * NS * BN + (NS - 1) * BN), ad, bd, i8_idesc(BN, 256), first);
+                                }
+                            }
+                        } else {
                         // plane s of the row panel against GRP consecutive planes t .. t+g-1 of the column panel in ONE instruction
                         // (N = g BN): the planes are contiguous in shared memory and the levels s+t .. s+t+g-1 are adjacent TMEM column
                         // blocks, so the row panel is read from shared memory 9 times per k step instead of 15 (21 for 6 planes).
                         // Every level is first written by the s = 0 instructions (accumulate off at the first k step).
 #pragma unroll
                         for (int si = 0; si < NS; ++si) {
-                            const uint64_t ad = i8::smem_desc_sw64(stage + si * C::kITile + kk * 32);
+                            if ((a.dbg & 2) || ((a.dbg & 4) && si > 0)) continue;
+                            const uint64_t ad = i8::smem_desc_sw64<KC>(stage + si * C::kITile + kk * 32);
+                            // the (NS - si) BN columns of this row are cut into the fewest instructions of N <= 256 (N % 16 == 0; a cut need
+                            // not fall on a plane boundary: 5 planes of 96 = 240 + 240), so the row panel is read 8 times per k step for
+                            // 5 planes (9 for 6)
+                            const int W = (NS - si) * BN, nm = (W + 255) / 256;
+                            const int per = ((W + nm - 1) / nm + 15) / 16 * 16;
 #pragma unroll
-                            for (int sj = 0; sj <= NS - 1 - si; sj += C::kGrp) {
-                                const int gsz = (NS - si - sj) < C::kGrp ? (NS - si - sj) : C::kGrp;
-                                const uint64_t bd = i8::smem_desc_sw64(stage + NS * C::kITile + sj * C::kJTile + kk * 32);
-                                i8::mma_i8(tmem_base + (uint32_t)(ab * NS * BN + (si + sj) * BN), ad, bd, i8_idesc(gsz * BN), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
+                            for (int c = 0; c < W; c += per) {
+                                const int wn = (W - c) < per ? (W - c) : per;
+                                const uint64_t bd = i8::smem_desc_sw64<KC>(stage + NS * C::kITile + c * KC + kk * 32);
+                                i8::mma_i8(tmem_base + (uint32_t)(ab * NS * BN + si * BN + c), ad, bd, i8_idesc(wn), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
                             }
                         }
+                        }
                     }
-                    i8::mma_commit(&empty_bar[s]);   // the stage may be refilled once these MMAs have read it
+                    if constexpr (CTAS == 2) i8::mma_commit_pair(&empty_bar[s]); else i8::mma_commit(&empty_bar[s]);   // the stage may be refilled once these MMAs have read it
+                    }
                 }
-                i8::mma_commit(&tmem_full_bar[ab]);
+                if constexpr (CTAS == 2) i8::mma_commit_pair(&tmem_full_bar[ab]); else i8::mma_commit(&tmem_full_bar[ab]);
                 ++tile_it;
             }
         }
@@ -562,10 +736,10 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
         const int et = tid - 64;   // 0 .. 32 * kI8EpiWarps - 1
         const int chalf = (warp - 2) >> 2;   // which of the quarter's two warps: it takes the 16-column chunks of its parity
         uint32_t tile_it = 0;
-        for (int64_t u = blockIdx.x; u < a.total_tiles; u += gridDim.x) {
-            const I8Unit w = i8_decode<BN>(a, u);
+        for (int64_t u = unit0; u < a.total_tiles; u += ustride) {
+            const I8Unit w = i8_decode<BN, C::kRows>(a, u);
             if (!i8_runs<NS>(a, w.inst)) continue;
-            const int64_t i0 = (int64_t)w.ti * kI8BM, j0 = (int64_t)w.tj * BN;
+            const int64_t i0 = (int64_t)w.ti * C::kRows + (int64_t)rank * kI8BM, j0 = (int64_t)w.tj * BN;
             const double* sg = a.sigma + w.inst * a.n;
             if (et < BN) {
                 const int64_t gj = j0 + et;
@@ -590,34 +764,50 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
             // mirrored one is 16 consecutive doubles per thread (4 x 256-bit stores).  Decided per (row, chunk), so tiles that straddle
             // the diagonal or the ragged edge (all tiles of a 256 x 256 instance) still take it for most of their chunks.
             const bool vec_ok = !a.map && !a.accumulate && (a.ldo & 3) == 0 && (a.o_bstride & 3) == 0 && (((uintptr_t)a.out) & 31) == 0;
-#pragma unroll 1
-            for (int c0 = 16 * chalf; c0 < BN; c0 += 16 * (kI8EpiWarps / 4)) {
-                int32_t acc[NS][16];
+            // phase 1: TMEM -> registers (Horner chain, scaling) for all of this thread's chunks, then hand the accumulators back: the
+            // MMAs of the CTA's next tile run while phase 2 stores to global memory
+            constexpr int NCH = (BN / 16 + 1) / 2;
+            double v[NCH][16];
 #pragma unroll
-                for (int l = 0; l < NS; ++l) i8::tmem_ld16(trow + (uint32_t)(l * BN + c0), acc[l]);
-                i8::tmem_ld_wait();
-                double v[16];
+            for (int ci = 0; ci < NCH; ++ci) {
+                const int c0 = 16 * chalf + 32 * ci;
+                if (c0 < BN) {
+                    int32_t acc[NS][16];
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                    double t = (double)acc[0][jj];
+                    for (int l = 0; l < NS; ++l) i8::tmem_ld16(trow + (uint32_t)(l * BN + c0), acc[l]);
+                    i8::tmem_ld_wait();
 #pragma unroll
-                    for (int l = 1; l < NS; ++l) t = fma(t, 256.0, (double)acc[l][jj]);
-                    v[jj] = t * fi * sfj[c0 + jj];
+                    for (int jj = 0; jj < 16; ++jj) {
+                        double t = (double)acc[0][jj];
+#pragma unroll
+                        for (int l = 1; l < NS; ++l) t = fma(t, 256.0, (double)acc[l][jj]);
+                        v[ci][jj] = t * fi * sfj[c0 + jj];
+                    }
                 }
+            }
+            i8::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CTAS == 2) i8::mb_arrive_cluster(i8::mapa_u32(i8::s_u32(&tmem_empty_bar[ab]), 0)); else i8::mb_arrive(&tmem_empty_bar[ab]);
+            }
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) {
+                const int c0 = 16 * chalf + 32 * ci;
+                if (c0 >= BN) continue;
                 if (vec_ok && row_ok && gi < j0 + c0 && j0 + c0 + 16 <= a.n) {
                     double* p1 = out + gi + (j0 + c0) * a.ldo;
 #pragma unroll
                     // streaming stores (evict-first): Q is written once and not re-read here, the digit planes (100 MB) should keep the L2
-                    for (int jj = 0; jj < 16; ++jj) __stcs(p1 + (int64_t)jj * a.ldo, v[jj]);
+                    for (int jj = 0; jj < 16; ++jj) __stcs(p1 + (int64_t)jj * a.ldo, v[ci][jj]);
                     double* p2 = out + (j0 + c0) + gi * a.ldo;
 #pragma unroll
                     for (int jj = 0; jj < 16; jj += 4)
-                        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p2 + jj), "d"(v[jj]), "d"(v[jj + 1]), "d"(v[jj + 2]), "d"(v[jj + 3]) : "memory");
+                        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p2 + jj), "d"(v[ci][jj]), "d"(v[ci][jj + 1]), "d"(v[ci][jj + 2]), "d"(v[ci][jj + 3]) : "memory");
                     if (pk) {
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) {
                             const int64_t gj = j0 + c0 + jj;
-                            __stcs(pk + gj * (gj + 1) / 2 + gi, v[jj]);
+                            __stcs(pk + gj * (gj + 1) / 2 + gi, v[ci][jj]);
                         }
                     }
                     continue;
@@ -628,30 +818,27 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                     if (row_ok && gj < a.n && gi <= gj) {   // every unordered pair of columns exactly once
                         const int64_t on = mapj[c0 + jj];
                         double* p1 = out + om + on * a.ldo;
-                        if (a.accumulate) *p1 += v[jj]; else *p1 = v[jj];
+                        if (a.accumulate) *p1 += v[ci][jj]; else *p1 = v[ci][jj];
                         if (gi != gj) {
                             double* p2 = out + on + om * a.ldo;
-                            if (a.accumulate) *p2 += v[jj]; else *p2 = v[jj];
+                            if (a.accumulate) *p2 += v[ci][jj]; else *p2 = v[ci][jj];
                         }
                         if (pk) {
                             const int64_t lo = om < on ? om : on, hi = om < on ? on : om;
-                            pk[hi * (hi + 1) / 2 + lo] = v[jj];
+                            pk[hi * (hi + 1) / 2 + lo] = v[ci][jj];
                         }
                     }
                 }
             }
-            i8::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) i8::mb_arrive(&tmem_empty_bar[ab]);
             i8::epi_bar();   // sfj / mapj are rewritten for the next tile
             ++tile_it;
         }
     }
     i8::tc_fence_before();
-    __syncthreads();
+    if constexpr (CTAS == 2) i8::cluster_sync_all(); else __syncthreads();   // nobody leaves (or frees TMEM) while the peer can still signal into this CTA
     if (warp == 1) {
         i8::tc_fence_after();
-        i8::tmem_dealloc(tmem_base, kI8TmemCols);
+        if constexpr (CTAS == 2) i8::tmem_dealloc_pair(tmem_base, kI8TmemCols); else i8::tmem_dealloc(tmem_base, kI8TmemCols);
     }
 }
 
@@ -669,15 +856,15 @@ static EncodeTiledFnI8 encode_fn_i8() {
     return fn;
 }
 
-static bool make_plane_map(CUtensorMap* tm, const int8_t* base, int64_t kp, int64_t n, int64_t batch, int box_rows) {
+static bool make_plane_map(CUtensorMap* tm, const int8_t* base, int64_t kp, int64_t n, int64_t batch, int box_rows, int kc = kI8KC, int box_planes = 1) {
     EncodeTiledFnI8 enc = encode_fn_i8();
     if (!enc) return false;
     cuuint64_t dims[4] = {(cuuint64_t)kp, (cuuint64_t)n, (cuuint64_t)kGramI8Planes, (cuuint64_t)batch};
     cuuint64_t strides[3] = {(cuuint64_t)kp, (cuuint64_t)kp * n, (cuuint64_t)kp * n * kGramI8Planes};
-    cuuint32_t box[4] = {(cuuint32_t)kI8KC, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)box_rows, (cuuint32_t)box_planes, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     kc == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : kc == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -693,9 +880,13 @@ GramI8Plan plan_gram_i8(int64_t k, int64_t n, int64_t batch) {
 }
 
 void configure_gram_i8_kernels() {
-    cudaFuncSetAttribute(gram_i8_kernel<5, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 96>::kSmemBytes);
-    cudaFuncSetAttribute(gram_i8_kernel<6, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6, 80>::kSmemBytes);
-    cudaFuncSetAttribute(gram_i8_kernel<5, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 48>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_kernel<5, 96, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 96, 1, 64>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_kernel<6, 80, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6, 80, 1, 64>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_kernel<5, 48, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 48, 1, 64>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_kernel<5, 96, 2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 96, 2, 64>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_kernel<6, 80, 2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6, 80, 2, 64>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_kernel<5, 96, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 96, 1, 128>::kSmemBytes);
+    cudaFuncSetAttribute(gram_i8_kernel<6, 80, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6, 80, 1, 128>::kSmemBytes);
     cudaFuncSetAttribute(gram_i8_slice_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SliceRing * 4096 * 8 + 64);
 }
 
@@ -733,11 +924,14 @@ bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t ba
     return true;
 }
 
-template <int NS, int BN>
+template <int NS, int BN, int CTAS = 1, int KC = kI8KC>
 static bool launch_i8_impl(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0, int64_t col1) {
+    using C = I8Cfg<NS, BN, CTAS, KC>;
     GramI8KernelArgs a{};
-    if (!make_plane_map(&a.tmi, sc.slices, sc.plan.kp, g.n, batch, kI8BM)) return false;
-    if (!make_plane_map(&a.tmj, sc.slices, sc.plan.kp, g.n, batch, BN)) return false;
+    if (!make_plane_map(&a.tmi, sc.slices, sc.plan.kp, g.n, batch, kI8BM, KC)) return false;
+    if (!make_plane_map(&a.tmj, sc.slices, sc.plan.kp, g.n, batch, BN, KC)) return false;
+    if (!make_plane_map(&a.tmh, sc.slices, sc.plan.kp, g.n, batch, BN / 2, KC)) return false;
+    if (!make_plane_map(&a.tmja, sc.slices, sc.plan.kp, g.n, batch, BN, KC, NS)) return false;
     a.k = g.k; a.kp = sc.plan.kp; a.n = g.n; a.sigma = sc.sigma; a.stats = sc.stats; a.tol = sc.tol; a.force_ns = sc.force_ns;
     a.out = g.H; a.ldo = g.ldh; a.o_bstride = g.h_bstride; a.map = g.map; a.scale = g.scale; a.accumulate = g.accumulate;
     a.packed_dev = g.accumulate ? nullptr : g.packed_dev; a.packed_bstride = g.packed_bstride;
@@ -749,13 +943,27 @@ static bool launch_i8_impl(const GramArgs& g, const GramI8Scratch& sc, int64_t b
     a.tj1 = a.tj0;
     while (a.tj1 < ntj && lastcol(a.tj1) < col1) ++a.tj1;
     int64_t tpi = 0;
-    for (int tj = a.tj0; tj < a.tj1; ++tj) tpi += lastcol(tj) / kI8BM + 1;
+    for (int tj = a.tj0; tj < a.tj1; ++tj) tpi += lastcol(tj) / C::kRows + 1;
     a.tiles_per_inst = tpi;
     a.total_tiles = tpi * batch;
+    if (const char* e = getenv("PMB_I8_DBG")) a.dbg = atoi(e);
     if (a.total_tiles == 0) return true;
-    const int grid = (int)std::min<int64_t>(a.total_tiles, sm_count);
-    gram_i8_kernel<NS, BN><<<grid, kI8Threads, I8Cfg<NS, BN>::kSmemBytes, stream>>>(a);
-    return true;
+    if constexpr (CTAS == 2) {   // one cluster of two CTAs (a TPC) per tile
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * std::min<int64_t>(a.total_tiles, sm_count / 2)));
+        cfg.blockDim = dim3(kI8Threads);
+        cfg.dynamicSmemBytes = C::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, gram_i8_kernel<NS, BN, 2, KC>, a) == cudaSuccess;
+    } else {
+        const int grid = (int)std::min<int64_t>(a.total_tiles, sm_count);
+        gram_i8_kernel<NS, BN, 1, KC><<<grid, kI8Threads, C::kSmemBytes, stream>>>(a);
+        return true;
+    }
 }
 
 __global__ void gram_i8_count_levels_kernel(const unsigned long long* stats, double tol, int force_ns, int64_t batch, unsigned long long* counts) {
@@ -793,9 +1001,26 @@ bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batc
     // for short contractions (1024 x (256 x 256): 0.55 vs 0.40 ms; n = 4096, k = 512: 0.109 vs 0.083 ms): twice the tiles, twice the
     // row-panel traffic.  Kept for the accumulator double-buffering it exercises.
     const bool narrow = sc.plan.kp <= 512 && getenv("PMB_I8_NARROW") != nullptr;
-    if (sc.force_ns != 6) ok = ok && (narrow ? launch_i8_impl<5, 48>(g, sc, batch, sm_count, stream, col0, col1)
-                                             : launch_i8_impl<5, 96>(g, sc, batch, sm_count, stream, col0, col1));
-    if (sc.force_ns != 5) ok = ok && launch_i8_impl<6, 80>(g, sc, batch, sm_count, stream, col0, col1);
+    // Defaults, measured on B200 at n = k = 4096 (tools/probe/i8_wide.sh, i8_pair.sh; profiles/r01_o_gram_i8_variants.txt):
+    //   5 planes: 64-byte stages, 3-stage ring (0.336 ms; 128-byte split ring 0.344 ms; CTA pair 0.49-0.51 ms)
+    //   6 planes: 128-byte split ring (0.469 ms; 64-byte stages fit only 2 stages of 78 KB: 0.498 ms; CTA pair 0.62-0.65 ms)
+    // PMB_I8_KC = 64 | 128 and PMB_I8_PAIR = 1 override for experiments.
+    static const int kc_env = getenv("PMB_I8_KC") ? atoi(getenv("PMB_I8_KC")) : 0;
+    static const bool pair = getenv("PMB_I8_PAIR") != nullptr && atoi(getenv("PMB_I8_PAIR")) != 0;
+    if (pair) {
+        if (sc.force_ns != 6) ok = ok && launch_i8_impl<5, 96, 2, 64>(g, sc, batch, sm_count, stream, col0, col1);
+        if (sc.force_ns != 5) ok = ok && launch_i8_impl<6, 80, 2, 64>(g, sc, batch, sm_count, stream, col0, col1);
+        return ok;
+    }
+    if (!narrow) {
+        if (sc.force_ns != 6) ok = ok && (kc_env == 128 ? launch_i8_impl<5, 96, 1, 128>(g, sc, batch, sm_count, stream, col0, col1)
+                                                        : launch_i8_impl<5, 96, 1, 64>(g, sc, batch, sm_count, stream, col0, col1));
+        if (sc.force_ns != 5) ok = ok && (kc_env == 64 ? launch_i8_impl<6, 80, 1, 64>(g, sc, batch, sm_count, stream, col0, col1)
+                                                       : launch_i8_impl<6, 80, 1, 128>(g, sc, batch, sm_count, stream, col0, col1));
+        return ok;
+    }
+    if (sc.force_ns != 6) ok = ok && launch_i8_impl<5, 48, 1, 64>(g, sc, batch, sm_count, stream, col0, col1);
+    if (sc.force_ns != 5) ok = ok && launch_i8_impl<6, 80, 1, 128>(g, sc, batch, sm_count, stream, col0, col1);
     return ok;
 }
 

@@ -262,3 +262,44 @@ def test_certificate_verdict_matches_the_numpy_restatement(monkeypatch):
     model.update()
     want = [S.level(S.slice_columns(A[i])[2]) for i in range(B)]
     assert model.gram_level_counts() == (want.count(5), want.count(6), want.count(64))
+
+
+_VARIANT_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+import parametron_b200 as pm
+from oracle import int8_slices as S
+out = {}
+for mode, (n, k) in ((5, (520, 1000)), (6, (300, 500)), (5, (130, 260)), (6, (777, 130))):
+    rng = np.random.default_rng(1000 * mode + n)
+    A = rng.standard_normal((k, n))
+    model = pm.Model(batch=1, gram_mode=mode)
+    x = model.variables(n)
+    Ap = pm.Parameter(model, shape=(k, n), device=True)
+    r = Ap * x
+    pm.objective(model, pm.Minimize, pm.dot(r, r))
+    model.initialize()
+    Ap.upload(A)
+    model.update()
+    Q = model.objective_arrays()[0]
+    Qe, _ = S.gram(A, mode, alpha=2.0)
+    iu = np.triu_indices(n)
+    assert np.array_equal(Q[iu], Qe[iu]), (mode, n, k)
+    assert np.array_equal(Q, Q.T)
+    assert model.gram_level_counts() == ((1, 0, 0) if mode == 5 else (0, 1, 0))
+print("VARIANT OK")
+"""
+
+
+@pytest.mark.parametrize("env", [{"PMB_I8_PAIR": "1"}, {"PMB_I8_KC": "128"}, {"PMB_I8_KC": "64"}])
+def test_kernel_variants_are_bit_identical_to_the_numpy_restatement(env):
+    """The tcgen05 Gram kernel has three pipelines (64-byte stages, the 128-byte split ring, the CTA pair with cta_group::2 / M = 256);
+    the launcher picks per plane count (kernels_gram_i8.cu: launch_gram_i8_mma) and PMB_I8_KC / PMB_I8_PAIR force one.  Integer
+    accumulation is exact, so every variant must reproduce oracle/int8_slices.py bit for bit on ragged shapes, 5 and 6 planes.
+    The switches are read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, PMB_GRAM_I8_ALWAYS="1", **env)
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, root], env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "VARIANT OK" in r.stdout, r.stdout + r.stderr
