@@ -94,7 +94,8 @@ struct GramI8KernelArgs {
     double* packed_dev; int64_t packed_bstride;
     int32_t tj0, tj1;       // tile columns [tj0, tj1) of every instance
     int64_t tiles_per_inst, total_tiles;
-    int32_t dbg;            // timing diagnostics only (PMB_I8_DBG): 1 = no TMA loads, 2 = no MMAs, 4 = only the s = 0 row of MMAs
+    int32_t dbg;            // timing diagnostics only (PMB_I8_DBG): 1 = no TMA loads, 2 = no MMAs, 4 = only the s = 0 row of MMAs,
+                            // 8 = no epilogue work, 16 = the s = 0 row three times (same MAC count, N = 240 instructions only)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------------
@@ -705,6 +706,16 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                         // (N = g BN): the planes are contiguous in shared memory and the levels s+t .. s+t+g-1 are adjacent TMEM column
                         // blocks, so the row panel is read from shared memory 9 times per k step instead of 15 (21 for 6 planes).
                         // Every level is first written by the s = 0 instructions (accumulate off at the first k step).
+                        if (a.dbg & 16) {
+                            for (int rep3 = 0; rep3 < 3; ++rep3) {
+                                const uint64_t ad = i8::smem_desc_sw64<KC>(stage + rep3 * C::kITile + kk * 32);
+#pragma unroll
+                                for (int c = 0; c < NS * BN; c += NS * BN / 2) {
+                                    const uint64_t bd = i8::smem_desc_sw64<KC>(stage + NS * C::kITile + c * KC + kk * 32);
+                                    i8::mma_i8(tmem_base + (uint32_t)(ab * NS * BN + c), ad, bd, i8_idesc(NS * BN / 2), (kc > 0 || kk > 0 || rep3 > 0) ? 1u : 0u);
+                                }
+                            }
+                        } else
 #pragma unroll
                         for (int si = 0; si < NS; ++si) {
                             if ((a.dbg & 2) || ((a.dbg & 4) && si > 0)) continue;
@@ -764,14 +775,17 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
             // mirrored one is 16 consecutive doubles per thread (4 x 256-bit stores).  Decided per (row, chunk), so tiles that straddle
             // the diagonal or the ragged edge (all tiles of a 256 x 256 instance) still take it for most of their chunks.
             const bool vec_ok = !a.map && !a.accumulate && (a.ldo & 3) == 0 && (a.o_bstride & 3) == 0 && (((uintptr_t)a.out) & 31) == 0;
-            // phase 1: TMEM -> registers (Horner chain, scaling) for all of this thread's chunks, then hand the accumulators back: the
-            // MMAs of the CTA's next tile run while phase 2 stores to global memory
+            // phase 1: TMEM -> registers (Horner chain) for all of this thread's chunks, then hand the accumulators back: the MMAs of the
+            // CTA's next tile run while phase 2 scales and stores (cfg2: 0.351 -> 0.337 ms).  An exact 64-bit integer combination of the
+            // levels (three IMAD.WIDE + one conversion per entry instead of the fp64 chain) was measured and is no faster: what the tile
+            // boundary costs (~5 us, tools/probe/i8_dbg.sh bit 8) is the latency chain commit -> tmem_full -> tcgen05.ld -> tmem_empty,
+            // not fp64 throughput
             constexpr int NCH = (BN / 16 + 1) / 2;
             double v[NCH][16];
 #pragma unroll
             for (int ci = 0; ci < NCH; ++ci) {
                 const int c0 = 16 * chalf + 32 * ci;
-                if (c0 < BN) {
+                if (c0 < BN && !(a.dbg & 8)) {
                     int32_t acc[NS][16];
 #pragma unroll
                     for (int l = 0; l < NS; ++l) i8::tmem_ld16(trow + (uint32_t)(l * BN + c0), acc[l]);
@@ -781,7 +795,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                         double t = (double)acc[0][jj];
 #pragma unroll
                         for (int l = 1; l < NS; ++l) t = fma(t, 256.0, (double)acc[l][jj]);
-                        v[ci][jj] = t * fi * sfj[c0 + jj];
+                        v[ci][jj] = t;
                     }
                 }
             }
@@ -793,7 +807,11 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
 #pragma unroll
             for (int ci = 0; ci < NCH; ++ci) {
                 const int c0 = 16 * chalf + 32 * ci;
-                if (c0 >= BN) continue;
+                if (c0 >= BN || (a.dbg & 8)) continue;
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    v[ci][jj] = v[ci][jj] * fi * sfj[c0 + jj];
+                }
                 if (vec_ok && row_ok && gi < j0 + c0 && j0 + c0 + 16 <= a.n) {
                     double* p1 = out + gi + (j0 + c0) * a.ldo;
 #pragma unroll
