@@ -196,7 +196,19 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on STDOUT when the communicator comes up (NCCL_DEBUG=VERSION in this image); the contract is
+        # ONE JSON line on stdout, so file descriptor 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     # the library enqueues on torch's current stream so that torch.cuda.Event sees its work; the legacy default stream has
     # handle 0 (= "create your own" in pmb_ctx_create), so make a real stream current for the whole run
     tstream = torch.cuda.Stream()
