@@ -267,6 +267,24 @@ def main():
     aff_ms = kt["affine_assemble"][0] / max(kt["affine_assemble"][1], 1)
     peaks, peak_src = measured_peaks()
     syrk_flops = K_ROWS * N_VARS * (N_VARS + 1)
+
+    def library_int8_gemm_tops(n=8192, reps=10):
+        """dense int8 GEMM rate of this GPU through the library path (torch._int_mm -> cuBLASLt), best of `reps`, timed alone with CUDA
+        events: a MEASURED int8 figure next to the 2 x bf16 denominator (MEASURED_PEAKS.json has no int8 entry)"""
+        try:
+            a8 = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda")
+            b8 = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda")
+            for _ in range(3):
+                torch._int_mm(a8, b8)
+            torch.cuda.synchronize()
+            best = float("inf")
+            for _ in range(reps):
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(); torch._int_mm(a8, b8); t1.record(); torch.cuda.synchronize()
+                best = min(best, t0.elapsed_time(t1))
+            return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        except Exception:
+            return None
     if levels[0] + levels[1] > 0:
         # dominant kernel: gram_i8_kernel<planes, BN> (tcgen05 kind::i8).  Algorithmic work = planes (planes + 1) / 2 exact int8 digit-plane
         # products of the SYRK-counted contraction (k N (N + 1) ops each; redundant lower halves of diagonal tiles not counted)
@@ -274,6 +292,7 @@ def main():
         nprod = planes * (planes + 1) // 2
         i8_tops = nprod * syrk_flops / (i8_ms * 1e-3) / 1e12
         i8_peak = 2.0 * peaks.get("bf16_tflops", 1590.0)   # burst figure: the kernel is timed alone (CUDA events around the one launch)
+        lib_i8 = library_int8_gemm_tops() if rank == 0 else None
         roofline = {"bound": "tensor", "kernel": f"gram_i8_kernel<{planes},{96 if planes == 5 else 80}> (Q = 2A'A as {nprod} exact int8 digit-plane products: "
                                                  "TMA ring + tcgen05.mma kind::i8, int32 accumulators in TMEM)",
                     "achieved": i8_tops, "peak": i8_peak, "unit": "TOP/s", "frac": i8_tops / i8_peak, "traffic": GRAM_I8_DRAM_TRAFFIC_BYTES,
@@ -283,6 +302,9 @@ def main():
                     "peak_source": f"2 x bf16_tflops (burst) of MEASURED_PEAKS.json ({peak_src}): the int8 dense rate of tcgen05 is twice the bf16 rate "
                                    "(4.5 vs 2.25 POP/s nominal); MEASURED_PEAKS.json has no int8 entry.  ncu's own counter for the same launch: "
                                    "sm__ops_path_tensor_op_utcimma_src_int8 = 71-72 % of its peak (16384 ops/clk/SM at the 1.69 GHz the SMs hold under this load), profiles/r01_o_gram_i8_ncu_full.txt",
+                    "library_int8_gemm_tops_measured": lib_i8, "frac_vs_library_int8_gemm": (i8_tops / lib_i8) if lib_i8 else None,
+                    "library_int8_gemm_note": "torch._int_mm (cuBLASLt) 8192^3, best of 10, measured in this run after the timed region; "
+                                              "tools/probe/int8_peak.py, profiles/r01_o_int8_library_peak.json",
                     "fp64_equivalent_tflops": syrk_flops / ((i8_ms + slice_ms) * 1e-3) / 1e12,
                     "fp64_equivalent_note": f"SYRK-counted fp64 flops / (slice {slice_ms:.3f} ms + tcgen05 {i8_ms:.3f} ms); the fp64 DMMA pipe peaks at "
                                             f"{FP64_DMMA_PEAK_TFLOPS} TFLOP/s (profiles/r01_probe_dmma.txt), the fp64 kernel reached 33 (profiles/r01_m_*)",
