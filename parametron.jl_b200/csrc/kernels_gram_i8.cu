@@ -7,13 +7,17 @@
 //   1. slice kernel: every column j of X is scaled by 1 / sigma_j (sigma_j = largest magnitude / 0.99), rounded to a 47-bit signed
 //      fixed-point integer and cut into 6 balanced base-256 digits d_0..d_5 in [-128, 127] (int8 planes, K-major like X).  The same
 //      pass records, per instance, max sigma_j, max ||x_j||^2, max ||x_j / sigma_j||_1 and the largest 2-norm of every digit plane.
-//   2. Gram kernel <NS planes, BN>: for an output tile (128 columns i) x (BN columns j) all digit-plane products with s + t <= NS-1
-//      are issued as tcgen05.mma kind::i8 (M=128, N=BN, K=32) from TMA-loaded, 64-byte-swizzled shared-memory panels; planes with
-//      equal s + t share an int32 accumulator in TMEM (NS accumulators x BN columns <= 512 TMEM columns).  Integer accumulation is
-//      exact, so the result does not depend on tiling, k order or the number of SMs.
-//   3. epilogue: the NS int32 accumulators are combined by a Horner chain in fp64 (one rounding at 2^-53), scaled by
-//      sigma_i sigma_j 2^(-8 NS - 6) and by the caller's alpha, scattered through the variable map and written to both triangles
-//      (and, when asked, to the packed upper triangle P_x).
+//   2. Gram kernel <NS planes, BN, CTAS, KC>: for an output tile (128 columns i) x (BN columns j) all digit-plane products with
+//      s + t <= NS-1 are issued as tcgen05.mma kind::i8 (M = 128, K = 32) from TMA-loaded, swizzled shared-memory panels; planes with
+//      equal s + t share an int32 accumulator in TMEM (NS accumulators x BN columns <= 512 TMEM columns), and one instruction covers
+//      up to 256 consecutive accumulator columns (several planes / levels).  Integer accumulation is exact, so the result does not
+//      depend on tiling, k order, pipeline variant or the number of SMs.  Three pipelines share the kernel body (I8Cfg):
+//        KC = 64,  CTAS = 1: 3-stage ring of whole k steps (default for 5 planes)
+//        KC = 128, CTAS = 1: 128-byte rows, split ring: 2 column-panel stages + 6 row-panel slots (default for 6 planes)
+//        KC = 64,  CTAS = 2: CTA pair, tcgen05 cta_group::2 with M = 256 (measured slower; kept as an experiment, PMB_I8_PAIR=1)
+//   3. epilogue: phase 1 pulls the NS int32 accumulators of the thread's 48 entries out of TMEM (Horner chain in fp64, one rounding at
+//      2^-53) and hands TMEM back, so the next tile's MMAs start; phase 2 scales by sigma_i sigma_j 2^(-8 NS - 6) and the caller's
+//      alpha, scatters through the variable map and writes both triangles (and, when asked, the packed upper triangle P_x).
 //
 // What is dropped are the digit products with s + t >= NS and the representation error of the planes used.  gram_i8_level()
 // (pmb_kernels.h, shared with the fp64 kernel) bounds both with the recorded norms and picks, per instance, the smallest NS in {5, 6}
