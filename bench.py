@@ -30,7 +30,7 @@ N_VARS, K_ROWS, M_ROWS = 4096, 4096, 1024
 SEED = 1234
 METRIC = "QP re-parameterizations/sec (update!+coeff-assemble) at n=4096,m=1024"
 GRAM_DRAM_TRAFFIC_BYTES = 410174464 + 167363328    # ncu --set full, one launch of gram_tma_kernel<1,128> at cfg2
-GRAM_I8_DRAM_TRAFFIC_BYTES = 288979200 + 117453056    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r01_o_gram_i8_ncu_full.txt)
+GRAM_I8_DRAM_TRAFFIC_BYTES = 277568000 + 116847616    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r01_o_gram_i8_ncu_full.txt)
 AFFINE_DRAM_TRAFFIC_BYTES = 33626880 + 1335808       # ncu --set full, one launch of affine_assemble_tma<0> at cfg2 (profiles/r01_n_affine_tma_ncu_full.txt)
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200: profiles/r01_probe_dmma.txt (mma.sync f64, all SMs)
 
