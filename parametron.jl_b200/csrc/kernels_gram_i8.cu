@@ -247,6 +247,10 @@ struct GramI8SliceArgs {
     AlphaDev qscale, cscale;
 };
 
+// max of two doubles as one compare + select (fmax() expands to 8 instructions for its NaN rules: DSETP.MAX, FSEL, SEL, a predicated
+// LOP3 and moves).  A NaN operand loses every comparison, which is fine here: non-finite columns are detected through the 1-norm
+__device__ __forceinline__ double dmax(double a, double b) { return b > a ? b : a; }
+
 __device__ __forceinline__ void load4(const double* x, int64_t r0, int64_t k, bool vec, double (&v)[4]) {
     if (vec && r0 + 3 < k) {
         const double2 p = __ldg((const double2*)(x + r0)), q = __ldg((const double2*)(x + r0 + 2));
@@ -264,10 +268,14 @@ __device__ __forceinline__ void load4(const double* x, int64_t r0, int64_t k, bo
 // (cp.async.bulk on an mbarrier, SASS UBLKCP) three columns ahead of the arithmetic, so the HBM latency is off the dependent chain
 // load -> reduce -> digits -> store of a column.
 constexpr int kI8SliceRing = 3;
-template <int T, bool RING>
+// FULL (ring only): k == kp is a multiple of 1024 and the offset vector, if any, is 16-byte aligned -- every row of every cached iteration
+// that runs exists, so the bounds tests, masked loads and their reconvergence points (about a fifth of the instructions of this issue-bound
+// kernel) are compiled out
+template <int T, bool RING, bool FULL = false>
 __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8SliceArgs a) {
     constexpr int NP = kGramI8Planes, G = 256 / T, CIT = 4;   // CIT cached iterations of 4 rows per thread
     static_assert(!RING || T == 256, "the ring feeds one column per CTA");
+    static_assert(!FULL || RING, "the full-column fast path belongs to the ring kernel");
     extern __shared__ __align__(128) unsigned char slice_smem[];
     __shared__ __align__(8) uint64_t ring_full[kI8SliceRing];
     __shared__ double red[8][5];
@@ -325,8 +333,9 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tig = threadIdx.x % T, grp = threadIdx.x / T;
     const bool vec = (a.ldx % 2 == 0) && (((uintptr_t)a.X & 15) == 0) && (a.x_bstride % 2 == 0);
     const bool gvecal = a.gvec && (((uintptr_t)a.gvec & 15) == 0) && (a.g_bstride % 2 == 0);
-    const bool cached = a.kp <= (int64_t)4 * T * CIT;
-    const bool k4 = (a.k & 3) == 0;
+    const bool cached = FULL || a.kp <= (int64_t)4 * T * CIT;
+    const bool k4 = FULL || (a.k & 3) == 0;
+    const int nit = (int)(a.k / (4 * T));   // FULL: k is a multiple of 4 T = 1024 rows, whole cached iterations
     const int64_t plane_stride = a.n * a.kp;
     const int64_t total = a.batch * a.ncols;
     for (int64_t c0 = (int64_t)blockIdx.x * G; c0 < total; c0 += (int64_t)gridDim.x * G) {   // uniform per CTA (block-wide barriers below)
@@ -349,12 +358,16 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const double av = fabs(v[e]);
-                amax = fmax(amax, av);
+                amax = dmax(amax, av);
                 l1 += av;   // Inf / NaN entries surface here (fmax would hide a NaN): tested once per column below
                 ss = fma(v[e], v[e], ss);
             }
             if (g) {
                 double gv[4];
+                if (FULL) {
+                    const double2 p = __ldg((const double2*)(g + r0)), q = __ldg((const double2*)(g + r0 + 2));
+                    gv[0] = p.x; gv[1] = p.y; gv[2] = q.x; gv[3] = q.y;
+                } else
                 load4(g, r0, a.k, gvecal, gv);
                 dg = fma(v[0], gv[0], dg); dg2 = fma(v[1], gv[1], dg2); dg = fma(v[2], gv[2], dg); dg2 = fma(v[3], gv[3], dg2);
                 if (j == 0) {   // g.g is needed once per instance: the group that owns column 0 computes it
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
 #pragma unroll
                 for (int it = 0; it < CIT; ++it) {
                     const int64_t r0 = ((int64_t)it * T + tig) * 4;
-                    if (r0 < a.k) {
+                    if (FULL ? it < nit : r0 < a.k) {
                         if (RING) {
                             const double2 p = *(const double2*)(xs + r0), q = *(const double2*)(xs + r0 + 2);   // r0 + 3 < kpe + 2 <= slot + pad
                             vc[it][0] = p.x; vc[it][2] = q.x;
@@ -393,7 +406,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
         constexpr int W = T < 32 ? T : 32;   // lanes that share a column inside one warp (short columns: several columns per warp)
 #pragma unroll
         for (int o = W / 2; o; o >>= 1) {
-            amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            amax = dmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
             ss += __shfl_xor_sync(0xffffffffu, ss, o);
             l1 += __shfl_xor_sync(0xffffffffu, l1, o);
             dg += __shfl_xor_sync(0xffffffffu, dg, o);
@@ -415,7 +428,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
             ++ring_it;
             amax = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) amax = fmax(amax, red[w][0]);
+            for (int w = 0; w < 8; ++w) amax = dmax(amax, red[w][0]);
             if (tig == 0) {   // the column's sums are only consumed by the thread that keeps the running statistics
                 ss = 0.0; l1 = 0.0; dg = 0.0; gg = 0.0;
 #pragma unroll
@@ -428,6 +441,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
         const double sigma = zero ? 1.0 : amax * (1.0 / 0.99);
         const double mult = zero ? 0.0 : (0.99 / amax) * 140737488355328.0;   // 2^47: x -> fixed point with 47 fractional bits of x / sigma
         int8_t* dst = a.slices + ((inst * NP) * a.n + j) * a.kp;
+        asm volatile("" : "+l"(dst));   // keep the column's base in registers: the compiler otherwise rebuilds the 64-bit product per 4-row group
         uint32_t dsq[NP];
 #pragma unroll
         for (int s = 0; s < NP; ++s) dsq[s] = 0u;
@@ -461,7 +475,7 @@ __global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8Slice
 #pragma unroll
                 for (int it = 0; it < CIT; ++it) {
                     const int64_t r0 = ((int64_t)it * T + tig) * 4;
-                    if (r0 < a.kp) digits4(vc[it], r0);
+                    if (FULL ? it < nit : r0 < a.kp) digits4(vc[it], r0);
                 }
             } else {
                 for (int64_t r0 = (int64_t)tig * 4; r0 < a.kp; r0 += 4 * T) {
@@ -910,6 +924,7 @@ void configure_gram_i8_kernels() {
     cudaFuncSetAttribute(gram_i8_kernel<5, 96, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<5, 96, 1, 128>::kSmemBytes);
     cudaFuncSetAttribute(gram_i8_kernel<6, 80, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<6, 80, 1, 128>::kSmemBytes);
     cudaFuncSetAttribute(gram_i8_slice_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SliceRing * 4096 * 8 + 64);
+    cudaFuncSetAttribute(gram_i8_slice_kernel<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SliceRing * 4096 * 8 + 64);
 }
 
 bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0, int64_t col1) {
@@ -929,7 +944,9 @@ bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t ba
     if (sc.plan.kp > 1024 && sc.plan.kp <= 4096 && aligned && !getenv("PMB_I8_NO_RING")) {   // bulk-copy ring, 2 CTAs per SM
         const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * 2);
         const size_t smem = (size_t)kI8SliceRing * (size_t)((g.k + 1) / 2 * 2) * 8 + 64;
-        gram_i8_slice_kernel<256, true><<<sgrid, 256, smem, stream>>>(s);
+        const bool galigned = !g.gvec || ((((uintptr_t)g.gvec) & 15) == 0 && g.g_bstride % 2 == 0);
+        if (sc.plan.kp == g.k && g.k % 1024 == 0 && galigned && !getenv("PMB_I8_SLICE_GENERIC")) gram_i8_slice_kernel<256, true, true><<<sgrid, 256, smem, stream>>>(s);
+        else gram_i8_slice_kernel<256, true><<<sgrid, 256, smem, stream>>>(s);
     } else if (sc.plan.kp > 1024) {   // long columns: the whole CTA owns one column (up to 4096 rows cached in registers)
         const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * 4);
         gram_i8_slice_kernel<256, false><<<sgrid, 256, 0, stream>>>(s);
