@@ -1,10 +1,10 @@
 #!/bin/bash
-# CTA-pair (cta_group::2) and 32-byte-stage variants of the int8 Gram kernel: correctness on small shapes under a short timeout
+# CTA-pair (cta_group::2) and 128-byte split-ring variants of the int8 Gram kernel against the default: correctness on small shapes under a short timeout
 # (a hang costs 30 s), then timing; last, the timing diagnostics (PMB_I8_DBG, wrong results by construction) of every variant
 mkdir -p gpurun_out
 P=tools/probe/i8_probe
 {
-for cfg in "0 64" "0 32" "1 64" "1 32"; do
+for cfg in "0 64" "1 64" "0 128"; do
   set -- $cfg
   export PMB_I8_PAIR=$1 PMB_I8_KC=$2
   echo "=== PMB_I8_PAIR=$1 PMB_I8_KC=$2"
