@@ -30,6 +30,7 @@ N_VARS, K_ROWS, M_ROWS = 4096, 4096, 1024
 SEED = 1234
 METRIC = "QP re-parameterizations/sec (update!+coeff-assemble) at n=4096,m=1024"
 GRAM_DRAM_TRAFFIC_BYTES = 410174464 + 167363328    # ncu --set full, one launch of gram_tma_kernel<1,128> at cfg2
+AFFINE_BATCHED_DRAM_TRAFFIC_BYTES = 537068800 + 487929344   # ncu --set full, the 16-instance launch (profiles/r01_o_affine_tma_batched_ncu_full.txt)
 GRAM_I8_DRAM_TRAFFIC_BYTES = 277568000 + 116847616    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r01_o_gram_i8_ncu_full.txt)
 AFFINE_DRAM_TRAFFIC_BYTES = 33626880 + 1335808       # ncu --set full, one launch of affine_assemble_tma<0> at cfg2 (profiles/r01_n_affine_tma_ncu_full.txt)
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200: profiles/r01_probe_dmma.txt (mma.sync f64, all SMs)
@@ -414,7 +415,11 @@ def main():
                                                          f"{aff_batched['instances_per_launch']} instances of cfg2's constraint block per launch",
                                "achieved": aff_batched["achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                "frac": aff_batched["achieved_gbs"] / peaks["hbm_gbs"], "algorithmic_bytes": aff_batched["algorithmic_bytes"],
-                               "avg_launch_ms": aff_batched["avg_launch_ms"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+                               "avg_launch_ms": aff_batched["avg_launch_ms"], "traffic": AFFINE_BATCHED_DRAM_TRAFFIC_BYTES,
+                               "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 16-instance launch, "
+                                                 "profiles/r01_o_affine_tma_batched_ncu_full.txt (537 MB read + 488 MB written; the rest of the "
+                                                 "537 MB written is still in L2 when the kernel ends)",
+                               "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                                "single_instance_launch_in_step": single}
         else:
             roofline_affine = dict({"bound": "hbm", "kernel": "affine_assemble_tma (C, -d): bulk-copy ring", "peak": peaks["hbm_gbs"], "unit": "GB/s",
