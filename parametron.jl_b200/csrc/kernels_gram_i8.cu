@@ -969,8 +969,8 @@ static bool launch_i8_impl(const GramArgs& g, const GramI8Scratch& sc, int64_t b
     GramI8KernelArgs a{};
     if (!make_plane_map(&a.tmi, sc.slices, sc.plan.kp, g.n, batch, kI8BM, KC)) return false;
     if (!make_plane_map(&a.tmj, sc.slices, sc.plan.kp, g.n, batch, BN, KC)) return false;
-    if (!make_plane_map(&a.tmh, sc.slices, sc.plan.kp, g.n, batch, BN / 2, KC)) return false;
-    if (!make_plane_map(&a.tmja, sc.slices, sc.plan.kp, g.n, batch, BN, KC, NS)) return false;
+    if constexpr (CTAS == 2) { if (!make_plane_map(&a.tmh, sc.slices, sc.plan.kp, g.n, batch, BN / 2, KC)) return false; }
+    if constexpr (C::kWide) { if (!make_plane_map(&a.tmja, sc.slices, sc.plan.kp, g.n, batch, BN, KC, NS)) return false; }
     a.k = g.k; a.kp = sc.plan.kp; a.n = g.n; a.sigma = sc.sigma; a.stats = sc.stats; a.tol = sc.tol; a.force_ns = sc.force_ns;
     a.out = g.H; a.ldo = g.ldh; a.o_bstride = g.h_bstride; a.map = g.map; a.scale = g.scale; a.accumulate = g.accumulate;
     a.packed_dev = g.accumulate ? nullptr : g.packed_dev; a.packed_bstride = g.packed_bstride;
