@@ -74,7 +74,7 @@ enum {
     PMB_PARAM_HOST = 1,    /* caller-owned HOST buffer (+ optional host callback run once per update, then one
                               H2D copy) (ref: in-place Parameter(f, val, model), parameter.jl:57,101) */
     PMB_PARAM_UNIFORM = 2  /* built-in device generator: scale * U[0,1) from Philox4x32-10 keyed by
-                              (seed, instance, update counter) (ref: Parameter(rand!, zeros(n,n), model), README.md:36-43) */
+                              (seed, GLOBAL instance id = pmb_set_instance_offset + local instance, update counter) (ref: Parameter(rand!, zeros(n,n), model), README.md:36-43) */
 };
 
 typedef void (*pmb_host_callback)(double* val, int64_t rows, int64_t cols, int64_t batch, void* user);
@@ -83,6 +83,12 @@ typedef void (*pmb_host_callback)(double* val, int64_t rows, int64_t cols, int64
 /* ref: Model(optimizer) model.jl:10-30.  `stream` is a cudaStream_t (NULL = the library creates its own). */
 int pmb_ctx_create(int device, void* stream, int64_t batch, pmb_ctx** out);
 int pmb_ctx_destroy(pmb_ctx* ctx);
+/* Instance-shard data parallelism: this context owns the contiguous shard [first, first + batch) of a larger
+ * batch of independent instances of the model (ref: the same update! loop, model.jl:132-143, run once per instance).  `first` is the
+ * GLOBAL id of local instance 0: the built-in generators (PMB_PARAM_UNIFORM) key Philox by the global id, so the shard reproduces
+ * bit for bit the matching slice of the unsharded batch.  Build phase only; default 0. */
+int pmb_set_instance_offset(pmb_ctx* ctx, int64_t first);
+int pmb_get_instance_offset(const pmb_ctx* ctx, int64_t* first);
 const char* pmb_last_error(const pmb_ctx* ctx);
 const char* pmb_version(void);
 

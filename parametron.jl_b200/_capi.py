@@ -51,6 +51,8 @@ HOST_CALLBACK = C.CFUNCTYPE(None, c_f64p, C.c_int64, C.c_int64, C.c_int64, C.c_v
 SIGNATURES = {
     "pmb_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "pmb_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "pmb_set_instance_offset": (C.c_int, [C.c_void_p, C.c_int64]),
+    "pmb_get_instance_offset": (C.c_int, [C.c_void_p, c_i64p]),
     "pmb_last_error": (C.c_char_p, [C.c_void_p]),
     "pmb_version": (C.c_char_p, []),
     "pmb_add_variables": (C.c_int, [C.c_void_p, C.c_int64, c_i64p]),

@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libpmb200.so")
-SOURCES = ["kernels_affine.cu", "kernels_affine_tma.cu", "kernels_gram.cu", "kernels_gram_tma.cu", "kernels_gram_i8.cu", "kernels_misc.cu", "kernels_export.cu", "pmb_export.cu", "pmb_build.cu", "pmb_plan.cu"]
-HEADERS = ["pmb_kernels.h", "pmb_internal.h", "pmb_host.h", os.path.join("..", "..", "include", "parametron_b200.h")]
+SOURCES = ["kernels_affine.cu", "kernels_affine_tma.cu", "kernels_gram.cu", "kernels_gram_tma.cu", "kernels_gram_i8.cu", "kernels_gram_i8_fused.cu", "kernels_misc.cu", "kernels_export.cu", "pmb_export.cu", "pmb_build.cu", "pmb_plan.cu"]
+HEADERS = ["pmb_kernels.h", "pmb_internal.h", "pmb_host.h", "pmb_i8_ptx.h", os.path.join("..", "..", "include", "parametron_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
          "-Xptxas", "-v", "--use_fast_math=false"]
@@ -44,11 +44,13 @@ def build(force=False, verbose=False):
             if verbose:
                 sys.stderr.write(r.stderr)
     if force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
+        tmp = LIB + ".tmp"   # link beside the target and rename: a snapshot of the tree never sees a half-written library
+        cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+        os.replace(tmp, LIB)
     return LIB
 
 

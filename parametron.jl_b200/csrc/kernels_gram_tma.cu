@@ -54,6 +54,7 @@ struct GramTmaKernelArgs {
     const unsigned long long* cert_stats;  // see GramArgs::cert_stats: instances certified for the int8 path are skipped here
     double cert_tol;
     int32_t cert_force;
+    const unsigned long long* cert_none;   // number of instances the int8 launch left uncertified (null: unknown); 0 -> nothing to do here
     int32_t* counters;    // [total_tiles - full_tiles] arrival counters, zero between launches
     double* workspace;    // [(total_tiles - full_tiles) * nslices][64][256] partial accumulators
     int64_t total_units;
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
     const uint32_t gring = ring + (uint32_t)kTStages * 2 * kTBM * kTKT * 8;  // 128-byte slots: 16 entries of gvec per stage
     constexpr bool fuse_q = SYRK && FUSEQ;  // compiled out of the large-problem instantiations: it costs MMA-loop scheduling freedom
 
+    if (SYRK && a.cert_stats && (a.cert_force || (a.cert_none && __ldcg(a.cert_none) == 0ull))) return;   // every instance was certified: leave at once
     if (SYRK && a.total_tiles == a.tiles_per_inst && skip_certified(a, 0)) return;   // one instance, owned by the int8 path: nothing to do
     if (tid == 0) {
 #pragma unroll
@@ -497,7 +499,7 @@ static bool launch_tma_impl(bool syrk, const double* X, int64_t ldx, int64_t xbs
         a.gvec = fused->gvec; a.g_bstride = fused->g_bstride; a.qout = fused->qout; a.q_bstride = fused->q_bstride; a.c0out = fused->c0out;
         a.qscale = fused->qscale; a.cscale = fused->cscale; a.qworkspace = sc.qworkspace;
     }
-    if (fused) { a.cert_stats = fused->cert_stats; a.cert_tol = fused->cert_tol; a.cert_force = fused->cert_force; }
+    if (fused) { a.cert_stats = fused->cert_stats; a.cert_tol = fused->cert_tol; a.cert_force = fused->cert_force; a.cert_none = fused->cert_none; }
     a.total_units = a.full_tiles + (a.total_tiles - a.full_tiles) * a.nslices;
     const int grid = (int)(a.total_units < sm_count ? a.total_units : sm_count);
     if (bm == 64) {

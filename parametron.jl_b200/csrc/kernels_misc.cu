@@ -45,7 +45,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 // One launch replaces  tick + one Philox launch per Parameter + a memset node  (launch latency dominates the small configs).
 // All blocks read the update counter, use counter + 1 as this update's id, and the block that finishes LAST (atomic ticket)
 // publishes the incremented counter -- every other block has read it by then.
-__global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int njobs, int total_blocks, int64_t batch,
+__global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int njobs, int total_blocks, int64_t batch, int64_t inst_offset,
                                                        unsigned long long* counter, unsigned int* ticket) {
     const uint32_t upd = (uint32_t)(*counter + 1ULL);
     // which job does this block belong to?
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int 
         for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
             double* o = job.out + inst * job.numel;
             for (int64_t p = (int64_t)b * 256 + threadIdx.x; p < pairs; p += (int64_t)job.nblocks * 256) {
-                uint32_t c[4] = {(uint32_t)p, (uint32_t)((uint64_t)p >> 32), (uint32_t)inst, upd};
+                uint32_t c[4] = {(uint32_t)p, (uint32_t)((uint64_t)p >> 32), (uint32_t)(inst + inst_offset), upd};
                 philox4x32_10(c, (uint32_t)job.seed, (uint32_t)(job.seed >> 32));
                 double d0 = (double)((((uint64_t)c[1] << 32) | c[0]) >> 11) * (1.0 / 9007199254740992.0) * job.scale;
                 double d1 = (double)((((uint64_t)c[3] << 32) | c[2]) >> 11) * (1.0 / 9007199254740992.0) * job.scale;
@@ -84,13 +84,13 @@ __global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int 
         }
     }
 }
-void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, unsigned long long* counter, unsigned int* ticket,
-                     cudaStream_t stream) {
+void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, int64_t inst_offset, unsigned long long* counter,
+                     unsigned int* ticket, cudaStream_t stream) {
     if (njobs == 0 || total_blocks == 0) return;
     // at most 64 instance rows: the per-job block counts were sized for min(batch, 64) rows, and the end-of-kernel ticket is one
     // atomic per block (hundreds of thousands of blocks would serialise on it)
     int64_t by = batch < 64 ? batch : 64;
-    prologue_kernel<<<dim3((unsigned)total_blocks, (unsigned)by), 256, 0, stream>>>(jobs_dev, njobs, total_blocks, batch, counter, ticket);
+    prologue_kernel<<<dim3((unsigned)total_blocks, (unsigned)by), 256, 0, stream>>>(jobs_dev, njobs, total_blocks, batch, inst_offset, counter, ticket);
 }
 
 // ---------------- numeric prologue ---------------------------------------------------------------

@@ -520,6 +520,20 @@ int pmb_param_set_uniform(pmb_ctx* ctx, pmb_node p, uint64_t seed, double scale)
     API_END(ctx)
 }
 
+int pmb_set_instance_offset(pmb_ctx* ctx, int64_t first) {
+    API_BEGIN(ctx)
+    need_build_phase(ctx, "pmb_set_instance_offset");
+    if (first < 0 || first + ctx->batch > ((int64_t)1 << 32)) fail(PMB_EINVAL, "instance offset %lld out of range (global instance ids are 32-bit)", (long long)first);
+    ctx->inst_offset = first;
+    API_END(ctx)
+}
+
+int pmb_get_instance_offset(const pmb_ctx* ctx, int64_t* first) {
+    if (!ctx || !first) return PMB_EINVAL;
+    *first = ctx->inst_offset;
+    return PMB_OK;
+}
+
 int pmb_const_numeric(pmb_ctx* ctx, int ndims, int64_t rows, int64_t cols, const double* host_values, pmb_node* out) {
     API_BEGIN(ctx)
     need_build_phase(ctx, "constant");

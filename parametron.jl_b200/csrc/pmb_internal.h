@@ -132,7 +132,7 @@ enum KernelClass { KC_AFFINE = 0, KC_GRAM, KC_GEMM, KC_PHILOX, KC_H2D, KC_REDUCE
 
 enum StepType {
     ST_MEMSET, ST_LINCOMB, ST_TRANSPOSE, ST_GEMV, ST_DOT, ST_SPROD, ST_AFFINE, ST_GRAM, ST_GEMM,
-    ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM, ST_PROLOGUE, ST_GEMV_DOT, ST_PACK_P, ST_PACK_A, ST_GRAM_I8_SLICE, ST_GRAM_I8_MMA
+    ST_SCATTER_VEC, ST_BILINEAR, ST_COO, ST_SCATTER_SYM, ST_PROLOGUE, ST_GEMV_DOT, ST_PACK_P, ST_PACK_A, ST_GRAM_I8_SLICE, ST_GRAM_I8_MMA, ST_GRAM_I8_FUSED
 };
 
 struct Step {
@@ -198,6 +198,7 @@ struct pmb_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t batch = 1;
+    int64_t inst_offset = 0;   // global id of local instance 0 (instance-shard: pmb_set_instance_offset)
     int64_t nvars = 0;
     bool initialized = false;
     std::string err;

@@ -112,6 +112,7 @@ struct GramArgs {
     const unsigned long long* cert_stats;
     double cert_tol;
     int32_t cert_force;    // experiments: the int8 path was forced for every instance
+    const unsigned long long* cert_none;   // fused small-instance route: device counter of the instances it left uncertified (0: the fp64 launch exits at once)
 };
 void launch_gram_syrk(const GramArgs& a, int64_t batch, int sm_count, cudaStream_t stream);
 // general TN product  M (n x p, ld) = X' * Y  (scratch for dot(f, h) with f != h and for A * Vector{AffineFunction})
@@ -196,6 +197,7 @@ struct GramI8Scratch {
     unsigned long long* stats;   // [batch][kGramI8StatsStride]
     double tol;                  // certification tolerance (relative to max |H|)
     int32_t force_ns;            // experiments: 5 / 6 = run that many planes whatever the certificate says, 0 = adaptive
+    int32_t fused;               // the fused small-instance kernel (kernels_gram_i8_fused.cu) runs instead of slice + Gram launches: no planes in HBM
 };
 // memset(stats) + slice kernel (gram_i8_slice) and the two tcgen05 Gram launches, 5 and 6 planes, of which at most one does work per
 // instance (gram_i8_mma).  false: not applicable (the caller runs the fp64 kernel alone).
@@ -211,6 +213,13 @@ void launch_gram_i8_count_levels(const GramI8Scratch& sc, int64_t batch, unsigne
 // predicted seconds of the two ways to compute one SYRK step; the planner picks the int8 path when it is the faster one
 bool gram_i8_pays_off(int64_t k, int64_t n, int64_t batch, int sm_count);
 void configure_gram_i8_kernels();
+// K3: fused small-instance route (n <= 256, k <= 256, even k, 16-byte aligned operands): slicing, the 15 digit-plane products and the
+// epilogue of one instance per CTA pair in ONE launch; statistics / verdict land in sc.stats (stride kGramI8StatsStride, followed by the
+// count of uncertified instances).  The fp64 launch that follows computes H of the uncertified instances only.
+bool gram_i8_fused_applicable(const GramArgs& g, int64_t batch);
+bool gram_i8_fused_pays_off(int64_t k, int64_t n, int64_t batch, int sm_count);
+bool launch_gram_i8_fused(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream);
+void configure_gram_i8_fused_kernel();
 
 // ---------------- small kernels ---------------------------------------------------------------
 // fused prologue of one update: all built-in Parameter generators (kind 0: Philox uniform fill, per instance) + zero fills
@@ -223,8 +232,8 @@ struct FillJob {
     int32_t kind;
     int32_t nblocks;   // blocks of 256 threads assigned to this job
 };
-void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, unsigned long long* counter, unsigned int* ticket,
-                     cudaStream_t stream);
+void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, int64_t inst_offset, unsigned long long* counter,
+                     unsigned int* ticket, cudaStream_t stream);   // inst_offset: global id of local instance 0 (Philox key)
 // out[i] = cst[i] + sum_t alpha_t * src_t[off_t + i]
 struct LinCombTermDev { const double* src; int64_t src_bstride; int64_t src_off; AlphaDev alpha; };
 void launch_lincomb(double* out, int64_t out_bstride, int64_t n, const LinCombTermDev* terms, int nterms,

@@ -325,6 +325,7 @@ struct DenseSide {
     double cx = 1.0;
     double cg = 1.0;            // the offsets are cg * g[...]
     int whole_node = -1;        // X is exactly this (whole) matrix node, read in place
+    bool ident = false;         // map[i] == i for every column: kernels take the null (identity) map and their vectorised store paths
 };
 
 static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps, int64_t nb) {
@@ -350,6 +351,8 @@ static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps,
         s.X = sn.dptr + m.src_col_off * sn.rows; s.ldx = sn.rows; s.xbs = sn.bstride; s.ncols = m.cols; s.cx = m.a.c;
         if (m.src_col_off == 0 && m.cols == sn.cols && sn.bsr_b == 0) s.whole_node = m.mat;
         s.map = upload(c, map);
+        s.ident = true;
+        for (size_t i = 0; i < map.size(); ++i) s.ident = s.ident && map[i] == (int32_t)i;
         if (has_off && g_direct) {
             const Node& gn = c->nodes[f.offs[0].vec];
             s.g = gn.dptr + f.offs[0].src_off; s.gbs = gn.bstride; s.cg = f.offs[0].a.c;
@@ -377,6 +380,8 @@ static DenseSide densify(pmb_ctx* c, const AffForm& f, std::vector<Step>& steps,
         steps.push_back(affine_step(lower_aff(c, f, X, f.rows * nt, gg, f.rows, true, &touched), nb));
         s.X = X; s.ldx = f.rows; s.xbs = f.rows * nt; s.ncols = nt; s.cx = 1.0;
         s.map = upload(c, touched);
+        s.ident = true;
+        for (size_t i = 0; i < touched.size(); ++i) s.ident = s.ident && touched[i] == (int32_t)i;
     }
     s.g = g; s.gbs = f.rows;
     return s;
@@ -430,11 +435,27 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
             s.type = ST_GRAM; s.cls = KC_GRAM; s.batch = nb;
             GramArgs ga{};
             ga.X = F.X; ga.ldx = F.ldx; ga.x_bstride = F.xbs; ga.k = F.k; ga.n = F.ncols;
-            ga.H = T.Q; ga.ldh = N; ga.h_bstride = N * N; ga.map = F.map;
+            ga.H = T.Q; ga.ldh = N; ga.h_bstride = N * N; ga.map = F.ident ? nullptr : F.map;
             ga.scale = scaled(a, 2.0 * F.cx * F.cx); ga.accumulate = overwrite ? 0 : 1;
             // certified int8-slice path on tcgen05 (kernels_gram_i8.cu): large contractions only, fp64 kernel keeps the uncertified instances
             GramI8Scratch i8{};
-            if (c->gram_mode != 0 && c->use_tma && gram_tma_applicable(F.X, F.ldx, F.xbs, F.k, F.ncols, nb) &&
+            // fused small-instance route (kernels_gram_i8_fused.cu): batches of instances with n, k <= 256 -- slicing, digit-plane products and
+            // epilogue of one instance per CTA pair in one launch, no digit planes in HBM; q and c0 ride along
+            GramArgs fz = ga;
+            if (F.g) {
+                fz.gvec = F.g; fz.g_bstride = F.gbs; fz.qout = T.q; fz.q_bstride = N; fz.c0out = T.c0;
+                fz.qscale = scaled(a, 2.0 * F.cx * F.cg); fz.cscale = scaled(a, F.cg * F.cg);
+            }
+            if ((c->gram_mode == 1 || c->gram_mode == 5) && c->use_tma && !getenv("PMB_NO_FUSED_I8") && gram_tma_applicable(F.X, F.ldx, F.xbs, F.k, F.ncols, nb) &&
+                gram_i8_fused_applicable(fz, nb) && (c->gram_mode == 5 || gram_i8_fused_pays_off(F.k, F.ncols, nb, c->sm_count))) {
+                i8.stats = dalloc<unsigned long long>(c, nb * kGramI8StatsStride + 2, true);
+                i8.tol = c->gram_tol;
+                i8.force_ns = c->gram_mode == 5 ? 5 : 0;
+                i8.fused = 1;
+                ga.cert_stats = i8.stats; ga.cert_tol = i8.tol; ga.cert_force = i8.force_ns != 0; ga.cert_none = i8.stats + nb * kGramI8StatsStride;
+                fz.cert_stats = ga.cert_stats; fz.cert_tol = ga.cert_tol; fz.cert_force = ga.cert_force; fz.cert_none = ga.cert_none;
+            }
+            if (!i8.fused && c->gram_mode != 0 && c->use_tma && gram_tma_applicable(F.X, F.ldx, F.xbs, F.k, F.ncols, nb) &&
                 (c->gram_mode >= 5 || gram_i8_pays_off(F.k, F.ncols, nb, c->sm_count))) {
                 i8.plan = plan_gram_i8(F.k, F.ncols, nb);
                 if (i8.plan.ok) {
@@ -494,6 +515,12 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                 }
             }
             s.pipe8 = pipe8;
+            if (i8.fused) {   // one fused launch (H of the certified instances, q and c0 of all), then the fp64 launch for what it left
+                Step fs;
+                fs.type = ST_GRAM_I8_FUSED; fs.cls = KC_GRAM_I8; fs.batch = nb; fs.gram = fz; fs.i8 = i8;
+                st.push_back(fs);
+                s.i8 = i8;
+            }
             if (i8.slices) {  // slice pass, then the 5- and 6-plane tcgen05 launches; the fp64 launch after them skips what they certified
                 Step sl;
                 sl.type = ST_GRAM_I8_SLICE; sl.cls = KC_GRAM_SLICE; sl.batch = nb; sl.gram = ga; sl.i8 = i8; sl.pipe8 = pipe8;
@@ -511,7 +538,7 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
             c->gram_flops += F.k * F.ncols * (F.ncols + 1) + 2 * F.k * F.ncols + 2 * F.k;
             // small (latency-bound) problems only: one launch fewer.  For large problems the extra work in the MMA loop costs more
             // than the separate gemv+dot launch (measured at cfg2: Gram 2.09 -> 2.39 ms against a 34 us gemv).
-            const bool fuse_lin = !i8.slices && F.g && c->use_tma && !getenv("PMB_NO_FUSED_Q") && F.k % 2 == 0 && aligned16(F.g) && (nb == 1 || F.gbs % 2 == 0) &&
+            const bool fuse_lin = !i8.slices && !i8.fused && F.g && c->use_tma && !getenv("PMB_NO_FUSED_Q") && F.k % 2 == 0 && aligned16(F.g) && (nb == 1 || F.gbs % 2 == 0) &&
                                   gram_tma_applicable(F.X, F.ldx, F.xbs, F.k, F.ncols, nb) &&
                                   gram_fused_linear_supported(F.k, F.ncols, nb, c->sm_count);
             if (fuse_lin) {
@@ -519,12 +546,12 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                 Step& gs = st.back();
                 gs.gram.gvec = F.g; gs.gram.g_bstride = F.gbs; gs.gram.qout = T.q; gs.gram.q_bstride = N; gs.gram.c0out = T.c0;
                 gs.gram.qscale = scaled(a, 2.0 * F.cx * F.cg); gs.gram.cscale = scaled(a, F.cg * F.cg);
-            } else if (F.g && !i8.slices) {
+            } else if (F.g && !i8.slices && !i8.fused) {
                 Step v;
                 v.type = ST_GEMV; v.cls = KC_REDUCE; v.batch = nb;
                 GemvArgs g{};
                 g.A = F.X; g.lda = F.ldx; g.a_bstride = F.xbs; g.rows = F.k; g.cols = F.ncols; g.trans = 1;
-                g.v = F.g; g.v_bstride = F.gbs; g.v_off = 0; g.y = T.q; g.y_bstride = N; g.map = F.map;
+                g.v = F.g; g.v_bstride = F.gbs; g.v_off = 0; g.y = T.q; g.y_bstride = N; g.map = F.ident ? nullptr : F.map;
                 g.scale = scaled(a, 2.0 * F.cx * F.cg); g.accumulate = 1;
                 v.gemv = g;
                 DotArgs d{};
@@ -650,7 +677,7 @@ static int count_refs(pmb_ctx* c, int id) {
 static void run_step(pmb_ctx* c, const Step& s) {
     cudaStream_t st = c->stream;
     switch (s.type) {
-        case ST_PROLOGUE: launch_prologue(s.jobs, s.njobs, s.job_blocks, s.batch, c->d_counter, c->d_ticket, st); break;
+        case ST_PROLOGUE: launch_prologue(s.jobs, s.njobs, s.job_blocks, s.batch, c->inst_offset, c->d_counter, c->d_ticket, st); break;
         case ST_GEMV_DOT: launch_gemv_t_dot(s.gemv, s.dot, s.batch, st); break;
         case ST_PACK_P: launch_pack_upper(s.src, s.n, s.src_bstride, s.out, s.out_bstride, s.batch, st); break;
         case ST_PACK_A:
@@ -671,8 +698,12 @@ static void run_step(pmb_ctx* c, const Step& s) {
             if (c->fb_mode) break;   // fp64 replay
             if (!launch_gram_i8_mma(s.gram, s.i8, s.batch, c->sm_count, st)) fail(PMB_ECUDA, "int8-slice Gram: tcgen05 launch refused");
             break;
+        case ST_GRAM_I8_FUSED:
+            if (c->fb_mode) break;
+            if (!launch_gram_i8_fused(s.gram, s.i8, s.batch, c->sm_count, st)) fail(PMB_ECUDA, "fused int8 Gram: launch refused");
+            break;
         case ST_GRAM:
-            if (s.i8.slices) {  // companion of the int8 steps: must be the TMA kernel, it is the one that skips certified instances
+            if (s.i8.slices || s.i8.fused) {  // companion of the int8 steps: must be the TMA kernel, it is the one that skips certified instances
                 GramArgs ga = s.gram;
                 if (c->fb_mode) { ga.cert_stats = nullptr; ga.cert_force = 0; }   // fp64 replay: compute every instance
                 if (!launch_gram_syrk_tma(ga, s.gscratch, s.batch, c->sm_count, st)) fail(PMB_ECUDA, "fp64 Gram (TMA) launch refused");
@@ -952,6 +983,7 @@ int pmb_ctx_create(int device, void* stream, int64_t batch, pmb_ctx** out) {
     configure_affine_tma_kernels();
     configure_gram_tma_kernels();
     configure_gram_i8_kernels();
+    configure_gram_i8_fused_kernel();
     if (const char* gm = getenv("PMB_GRAM_MODE")) c->gram_mode = atoi(gm);
     const char* ng = getenv("PMB_NO_GRAPH");
     c->use_graph = !(ng && ng[0] == '1');
@@ -1360,7 +1392,7 @@ int pmb_gram_level_counts(pmb_ctx* ctx, int64_t* counts) {
     int64_t fp64_only = 0;
     for (auto& s : ctx->steps) {
         if (s.type != ST_GRAM) continue;
-        if (s.i8.slices) launch_gram_i8_count_levels(s.i8, s.batch, ctx->gram_counts, ctx->stream);
+        if (s.i8.slices || s.i8.fused) launch_gram_i8_count_levels(s.i8, s.batch, ctx->gram_counts, ctx->stream);
         else fp64_only += s.batch;
     }
     unsigned long long h[3];

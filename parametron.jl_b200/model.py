@@ -294,7 +294,7 @@ class Model:
     """src/model.jl:1-30.  `optimizer` is an optional callable invoked by solve() with the model after update() -- the
     external solve itself is out of scope and untouched (north_star); results stay on the device."""
 
-    def __init__(self, optimizer=None, device=0, batch=1, stream=None, gram_mode=None, gram_tol=0.0):
+    def __init__(self, optimizer=None, device=0, batch=1, stream=None, gram_mode=None, gram_tol=0.0, instance_offset=0):
         self._lib = K.load()
         self._ctx = C.c_void_p()
         code = self._lib.pmb_ctx_create(int(device), C.c_void_p(stream) if stream else None, int(batch), C.byref(self._ctx))
@@ -303,6 +303,10 @@ class Model:
                                    "there is no CPU fallback")
         if gram_mode is not None:  # 0: fp64 DMMA only, 1: certified int8 digit planes on tcgen05 (default), 5 / 6: forced planes
             self._ck(self._lib.pmb_set_gram_mode(self._ctx, int(gram_mode), float(gram_tol)))
+        # instance-shard: this model owns global instances [instance_offset, instance_offset + batch) of a larger batch
+        self.instance_offset = int(instance_offset)
+        if self.instance_offset:
+            self._ck(self._lib.pmb_set_instance_offset(self._ctx, self.instance_offset))
         self.optimizer = optimizer
         self.device = int(device)
         self.batch = int(batch)

@@ -22,8 +22,8 @@ I8_PEAK = 2 * 1677.0  # 2 x bf16_tflops (burst) of MEASURED_PEAKS.json: int8 den
 DMMA_PEAK = 37.1    # profiles/r01_probe_dmma.txt
 
 
-def ls_model(n, k, m, batch=1, fixed_matrices=False, gram_mode=None):
-    model = pm.Model(device=LOCAL, batch=batch, gram_mode=gram_mode)
+def ls_model(n, k, m, batch=1, fixed_matrices=False, gram_mode=None, instance_offset=0):
+    model = pm.Model(device=LOCAL, batch=batch, gram_mode=gram_mode, instance_offset=instance_offset)
     x = model.variables(n)
     if fixed_matrices:   # MPC style: A, C resident and constant between solves; b, d re-parameterised every solve
         A = pm.Parameter(model, shape=(k, n), device=True)
@@ -111,17 +111,24 @@ def cfg2():
 
 
 def cfg3(total=8192):
-    batch = total // WORLD
-    m = ls_model(256, 256, 64, batch=batch)
+    first, batch = pm.shard.instance_shard(total, RANK, WORLD)
+    m = ls_model(256, 256, 64, batch=batch, instance_offset=first)
     st = m.stats()
     sec = allreduce_max(timed_updates(m, 10))
     kb = kernel_breakdown(m, 5)
+    lv = m.gram_level_counts()
+    extra = {}
+    if kb.get("gram_i8_tcgen05"):   # fused small-instance kernel: HBM-bound by design (reads A once, writes Q once)
+        gbytes = (8 * 256 * 256 + 8 * 256 * 256) * batch
+        extra = dict(gram_fused_gbs_per_gpu=gbytes / kb["gram_i8_tcgen05"] / 1e3, gram_fused_frac_of_hbm_peak=gbytes / kb["gram_i8_tcgen05"] / 1e3 / HBM_PEAK,
+                     gram_fp64_equivalent_tflops=st["gram_algorithmic_flops"] * batch / kb["gram_i8_tcgen05"] / 1e6)
+    if kb.get("gram_dmma", 0) > 50:
+        extra.update(gram_tflops_per_gpu=st["gram_algorithmic_flops"] * batch / kb["gram_dmma"] / 1e6,
+                     gram_frac_of_dmma_peak=st["gram_algorithmic_flops"] * batch / kb["gram_dmma"] / 1e6 / DMMA_PEAK)
     report(f"cfg3 batch={total} x (n=256, m=64), {WORLD} GPU(s), {batch} instances per GPU", ms_per_update=sec * 1e3,
-           instance_updates_per_s=total / sec, kernel_us_rank0=kb,
+           instance_updates_per_s=total / sec, kernel_us_rank0=kb, gram_levels=lv,
            affine_gbs_per_gpu=st["affine_algorithmic_bytes"] * batch / kb["affine_assemble"] / 1e3,
-           affine_frac_of_hbm_peak=st["affine_algorithmic_bytes"] * batch / kb["affine_assemble"] / 1e3 / HBM_PEAK,
-           gram_tflops_per_gpu=st["gram_algorithmic_flops"] * batch / kb["gram_dmma"] / 1e6,
-           gram_frac_of_dmma_peak=st["gram_algorithmic_flops"] * batch / kb["gram_dmma"] / 1e6 / DMMA_PEAK)
+           affine_frac_of_hbm_peak=st["affine_algorithmic_bytes"] * batch / kb["affine_assemble"] / 1e3 / HBM_PEAK, **extra)
 
 
 def cfg4():
