@@ -266,8 +266,11 @@ struct pmb_ctx {
     double* res_gather = nullptr; int64_t res_gather_cap = 0;
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraph_t graph = nullptr;
+    cudaGraph_t graph_timing = nullptr;            // pmb_enable_kernel_timing: the steps serialised with event-record nodes around each launch
+    cudaGraphExec_t graph_exec_timing = nullptr;
     bool use_graph = false;
     bool use_tma = true;
+    bool trace = false;                  // PMB_TRACE was set when the context was created (timeline of the pipelined schedule)
     // Gram precision mode (pmb_set_gram_mode): 0 = fp64 DMMA only, 1 = certified int8 slices where they pay off (default),
     // 5 / 6 = force that many digit planes on every SYRK step (experiments: no certificate, no fp64 fallback)
     int gram_mode = 1;

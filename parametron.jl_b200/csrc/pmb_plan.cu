@@ -448,7 +448,7 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
             }
             if ((c->gram_mode == 1 || c->gram_mode == 5) && c->use_tma && !getenv("PMB_NO_FUSED_I8") && gram_tma_applicable(F.X, F.ldx, F.xbs, F.k, F.ncols, nb) &&
                 gram_i8_fused_applicable(fz, nb) && (c->gram_mode == 5 || gram_i8_fused_pays_off(F.k, F.ncols, nb, c->sm_count))) {
-                i8.stats = dalloc<unsigned long long>(c, nb * kGramI8StatsStride + 2, true);
+                i8.stats = dalloc<unsigned long long>(c, nb * kGramI8StatsStride + 2 + 1024, true);
                 i8.tol = c->gram_tol;
                 i8.force_ns = c->gram_mode == 5 ? 5 : 0;
                 i8.fused = 1;
@@ -744,7 +744,7 @@ static void collect_timing(pmb_ctx* c) {
 // aid (env PMB_TRACE=1, see pmb_update) that prints when each chunk landed, was multiplied and left.
 static void capture_update_graph(pmb_ctx* ctx, bool fallback, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out, bool eager = false) {
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
-    const bool trace = eager && getenv("PMB_TRACE");
+    const bool trace = eager && ctx->trace;
     auto mark = [&](const std::string& label, cudaStream_t on) {
         if (!trace) return;
         cudaEvent_t e;
@@ -985,6 +985,7 @@ int pmb_ctx_create(int device, void* stream, int64_t batch, pmb_ctx** out) {
     configure_gram_i8_kernels();
     configure_gram_i8_fused_kernel();
     if (const char* gm = getenv("PMB_GRAM_MODE")) c->gram_mode = atoi(gm);
+    c->trace = getenv("PMB_TRACE") != nullptr;   // read once: pmb_update is the hot call
     const char* ng = getenv("PMB_NO_GRAPH");
     c->use_graph = !(ng && ng[0] == '1');
     const char* nt = getenv("PMB_NO_TMA");
@@ -1001,6 +1002,8 @@ int pmb_ctx_destroy(pmb_ctx* c) {
     if (c->graph) cudaGraphDestroy(c->graph);
     if (c->graph_exec_fb) cudaGraphExecDestroy(c->graph_exec_fb);
     if (c->graph_fb) cudaGraphDestroy(c->graph_fb);
+    if (c->graph_exec_timing) cudaGraphExecDestroy(c->graph_exec_timing);
+    if (c->graph_timing) cudaGraphDestroy(c->graph_timing);
     for (auto e : c->ev_chunk) cudaEventDestroy(e);
     for (auto e : c->ev_gram) cudaEventDestroy(e);
     if (c->ev_d2h_done) cudaEventDestroy(c->ev_d2h_done);
@@ -1147,13 +1150,19 @@ int pmb_update(pmb_ctx* ctx) {
         CK(cudaMemcpyAsync(ctx->pipe_gate, ctx->pipe_ones, sizeof(int32_t) * (size_t)ctx->pipe_chunks, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->timing) {
         collect_timing(ctx);
-        for (size_t i = 0; i < ctx->steps.size(); ++i) {
-            CK(cudaEventRecord(ctx->ev[2 * i], ctx->stream));
-            run_step(ctx, ctx->steps[i]);
-            CK(cudaEventRecord(ctx->ev[2 * i + 1], ctx->stream));
+        if (ctx->graph_exec_timing) {
+            // the steps of one update, serialised on the context stream, with an event-record NODE on either side of every launch: the
+            // time stamps are taken by the device between back-to-back graph nodes, so no host launch gap lands inside an event pair
+            CK(cudaGraphLaunch(ctx->graph_exec_timing, ctx->stream));
+        } else {
+            for (size_t i = 0; i < ctx->steps.size(); ++i) {
+                CK(cudaEventRecord(ctx->ev[2 * i], ctx->stream));
+                run_step(ctx, ctx->steps[i]);
+                CK(cudaEventRecord(ctx->ev[2 * i + 1], ctx->stream));
+            }
         }
         ctx->ev_pending = true;
-    } else if (ctx->graph_exec && (ctx->pipe8_live || getenv("PMB_TRACE"))) {
+    } else if (ctx->graph_exec && (ctx->pipe8_live || ctx->trace)) {
         // The pipelined int8 schedule (chunked upload || per-chunk slice + Gram || streamed P_x download) is issued directly on its four
         // streams: replayed as ONE CUDA graph the copy nodes of the two directions were serialised by the graph scheduler (measured
         // 5.0 ms against 3.9 ms for the identical schedule issued eagerly; the ~60 API calls are hidden behind 3.5 ms of PCIe time).
@@ -1412,6 +1421,25 @@ int pmb_enable_kernel_timing(pmb_ctx* ctx, int enable) {
     }
     if (enable && !ctx->timing) {
         for (int i = 0; i < KC_COUNT; ++i) { ctx->cls_ms[i] = 0; ctx->cls_launches[i] = 0; }
+    }
+    if (enable && !ctx->graph_exec_timing && ctx->use_graph && !ctx->steps.empty()) {
+        // capture the timing graph once: every step in plan order on the context stream, bracketed by external event-record nodes
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            for (size_t i = 0; i < ctx->steps.size(); ++i) {
+                CK(cudaEventRecordWithFlags(ctx->ev[2 * i], ctx->stream, cudaEventRecordExternal));
+                run_step(ctx, ctx->steps[i]);
+                CK(cudaEventRecordWithFlags(ctx->ev[2 * i + 1], ctx->stream, cudaEventRecordExternal));
+            }
+        } catch (...) {
+            cudaStreamEndCapture(ctx->stream, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        CK(cudaStreamEndCapture(ctx->stream, &g));
+        ctx->graph_timing = g;
+        if (cudaGraphInstantiate(&ctx->graph_exec_timing, g, 0) != cudaSuccess) { (void)cudaGetLastError(); ctx->graph_exec_timing = nullptr; }
     }
     ctx->timing = enable != 0;
     API_END(ctx)

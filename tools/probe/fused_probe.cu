@@ -27,7 +27,7 @@ int main(int argc, char** argv) {
     for (auto& v : g) v = -(rand() / (double)RAND_MAX);
     double *dX, *dg, *dH, *dq, *dc0; unsigned long long* dstats;
     CKP(cudaMalloc(&dX, X.size() * 8)); CKP(cudaMalloc(&dg, g.size() * 8)); CKP(cudaMalloc(&dH, (size_t)(batch * n * n) * 8));
-    CKP(cudaMalloc(&dq, (size_t)(batch * n) * 8)); CKP(cudaMalloc(&dc0, (size_t)batch * 8)); CKP(cudaMalloc(&dstats, (size_t)(batch * 16 + 2) * 8));
+    CKP(cudaMalloc(&dq, (size_t)(batch * n) * 8)); CKP(cudaMalloc(&dc0, (size_t)batch * 8)); CKP(cudaMalloc(&dstats, (size_t)(batch * 16 + 2 + 1024) * 8)); CKP(cudaMemset(dstats, 0, (size_t)(batch * 16 + 2 + 1024) * 8));
     CKP(cudaMemcpy(dX, X.data(), X.size() * 8, cudaMemcpyHostToDevice)); CKP(cudaMemcpy(dg, g.data(), g.size() * 8, cudaMemcpyHostToDevice));
     CKP(cudaMemset(dH, 0xff, (size_t)(batch * n * n) * 8));
     pmb::GramArgs ga{};
@@ -50,10 +50,21 @@ int main(int argc, char** argv) {
         if (se != cudaSuccess) return 1;
     }
     std::vector<double> H((size_t)(batch * n * n)), q((size_t)(batch * n)), c0((size_t)batch);
-    std::vector<unsigned long long> stats((size_t)(batch * 16 + 2));
+    std::vector<unsigned long long> stats((size_t)(batch * 16 + 2 + 1024));
     CKP(cudaMemcpy(H.data(), dH, H.size() * 8, cudaMemcpyDeviceToHost)); CKP(cudaMemcpy(q.data(), dq, q.size() * 8, cudaMemcpyDeviceToHost));
     CKP(cudaMemcpy(c0.data(), dc0, c0.size() * 8, cudaMemcpyDeviceToHost)); CKP(cudaMemcpy(stats.data(), dstats, stats.size() * 8, cudaMemcpyDeviceToHost));
     printf("uncertified: %llu; verdict[0] = %llu\n", stats[(size_t)batch * 16], stats[15]);
+    if (getenv("PMB_FUSED_DBG") && (atoi(getenv("PMB_FUSED_DBG")) & 32)) {
+        const unsigned long long* tl = stats.data() + batch * 16 + 2;
+        unsigned long long t0 = ~0ull;
+        for (int r = 0; r < 4; ++r) for (int e = 0; e < 127; ++e) if (tl[r * 256 + 2 * e + 1] && tl[r * 256 + 2 * e + 1] < t0) t0 = tl[r * 256 + 2 * e + 1];
+        const char* names[4] = {"worker0", "worker8", "mma", "producer"};
+        for (int r = 0; r < 4; ++r) {
+            printf("timeline %s:", names[r]);
+            for (int e = 0; e < 127; ++e) { if (!tl[r * 256 + 2 * e + 1]) break; printf(" [%llu]%llu", tl[r * 256 + 2 * e], tl[r * 256 + 2 * e + 1] - t0); }
+            printf("\n");
+        }
+    }
     double worst = 0, worstq = 0, worstc = 0; int64_t bad_inst = -1;
     const int64_t check[] = {0, 1, batch / 2, batch - 1};
     for (int64_t inst : check) {
