@@ -220,10 +220,13 @@ __global__ void __launch_bounds__(kTThreads, 1) gram_tma_kernel(const __grid_con
                     // wait until the column chunk holding this tile's right-most panel has been uploaded (ti <= tj: the left
                     // panel is in the same or an earlier chunk); the flag is written by the copy engine after the data
                     const int32_t* flag = a.gate + ((int64_t)(w.tj + 1) * BM - 1 < a.n ? ((int64_t)(w.tj + 1) * BM - 1) : (a.n - 1)) / a.gate_cols;
+                    // The flag is written by a copy node of a sibling branch of the same graph: CUDA does not promise that it runs concurrently
+                    // with this kernel, so the wait is BOUNDED (~4 s); a stalled upload aborts the kernel loudly instead of hanging the update
                     int v;
+                    unsigned int spins = 0;
                     do {
                         asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-                        if (!v) __nanosleep(200);
+                        if (!v) { __nanosleep(400); if (++spins > 10000000u) __trap(); }
                     } while (!v);
                     asm volatile("fence.proxy.async;" ::: "memory");  // order the generic-proxy flag read before the async-proxy TMA reads
                 }

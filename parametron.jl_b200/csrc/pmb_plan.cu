@@ -469,7 +469,10 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
             }
             // upload/compute overlap: the operand is a pinned HOST Parameter nothing else reads -> gate the kernel on chunk arrival
             if (!i8.slices && is_objective && overwrite && c->h2d_in_graph && nb == 1 && F.whole_node >= 0 && c->pipe_param < 0 && c->use_tma &&
-                !getenv("PMB_NO_PIPE")) {
+                getenv("PMB_PIPE_GATED") && !getenv("PMB_NO_PIPE")) {
+                // OPT-IN (PMB_PIPE_GATED=1): the persistent kernel polls flags written by copy nodes of a sibling graph branch, which only works
+                // while the runtime runs the two concurrently (it does on this driver; a profiler, sanitizer or MPS time-slicing may serialise
+                // them -- the poll is bounded and traps).  Default: the operand is uploaded first (the int8 route has its own event-gated pipeline)
                 const Node& pn = c->nodes[(size_t)F.whole_node];
                 const int64_t tile_cols = (F.ncols + 127) / 128;
                 if (pn.nop == NOP_PARAM && pn.pmode == PMB_PARAM_HOST && tile_cols >= 8 && count_refs(c, F.whole_node) == 1 &&
@@ -887,8 +890,12 @@ static void capture_update_graph(pmb_ctx* ctx, bool fallback, cudaGraph_t* graph
                     if (stream_px) { CK(cudaEventRecord(ctx->ev_d2h_done, ctx->d2h_stream)); px_streamed = true; }
                     launch_gram_i8_flag(s.i8, 1, ctx->repair_flag_dev, main_s);
                     CK(cudaMemcpyAsync(ctx->repair_flag_host, ctx->repair_flag_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, main_s));
+                    continue;
                 }
-                continue;   // the tcgen05 step ran per chunk above; the fp64 companion is replaced by the host-side repair
+                if (s.type == ST_GRAM_I8_MMA) continue;   // ran per chunk above
+                // the fp64 companion stays IN the stream: it leaves at once when the certificate accepted the operand, and otherwise computes
+                // Q (and the packed P_x) on the fp64 pipe -- device-resident results are valid in stream order whatever the verdict; only the
+                // host copy of P_x, streamed out per range before the verdict was final, is refreshed by sync_and_repair() below
             }
             ctx->stream = main_s;
             run_step(ctx, s);
@@ -943,7 +950,6 @@ void build_update_graph(pmb_ctx* ctx) {
             CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         }
         capture_update_graph(ctx, false, &ctx->graph, &ctx->graph_exec);
-        if (ctx->pipe8_live) capture_update_graph(ctx, true, &ctx->graph_fb, &ctx->graph_exec_fb);
     }
 }
 
@@ -1185,17 +1191,24 @@ int pmb_update(pmb_ctx* ctx) {
     API_END(ctx)
 }
 
-int pmb_synchronize(pmb_ctx* ctx) {
-    API_BEGIN(ctx)
+// Synchronise the context stream; on the pipelined int8 schedule the packed P_x left for the host sink range by range BEFORE the certificate's
+// verdict was final: when the verdict ended at fp64 (the in-stream fp64 launch has then recomputed Q and P_x on the device) the host copy is
+// refreshed here.  Every entry point that hands results to the host goes through this helper.
+static void sync_and_repair(pmb_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
-    // pipelined int8 graph: it carries no fp64 launch.  If the certificate refused the operand, replay the update as a plain fp64 graph
-    // (same host Parameter buffers; the caller is blocked here, results are only promised after this call returns).
-    if (ctx->pipe8_live && ctx->repair_flag_host && *ctx->repair_flag_host && ctx->graph_exec_fb) {
+    if (ctx->pipe8_live && ctx->repair_flag_host && *ctx->repair_flag_host) {
         *ctx->repair_flag_host = 0;
-        CK(cudaGraphLaunch(ctx->graph_exec_fb, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->sink_Px && ctx->qp_Px && ctx->qp_nnzP > 0) {
+            CK(cudaMemcpyAsync(ctx->sink_Px, ctx->qp_Px, (size_t)(ctx->batch * ctx->qp_nnzP) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
         ctx->repairs += 1;
     }
+}
+
+int pmb_synchronize(pmb_ctx* ctx) {
+    API_BEGIN(ctx)
+    sync_and_repair(ctx);
     API_END(ctx)
 }
 
@@ -1318,7 +1331,7 @@ int pmb_set_primal(pmb_ctx* ctx, const double* x, int on_device) {
         ctx->res_tmp = dalloc<double>(ctx, std::max<int64_t>(cnt, 1) + ctx->batch, true);
     }
     CK(cudaMemcpyAsync(ctx->primal, x, (size_t)cnt * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-    if (!on_device) CK(cudaStreamSynchronize(ctx->stream));   // the caller's host buffer may be pageable / reused
+    if (!on_device) sync_and_repair(ctx);   // the caller's host buffer may be pageable / reused
     ctx->primal_set = true;
     API_END(ctx)
 }
@@ -1346,7 +1359,7 @@ int pmb_value(pmb_ctx* ctx, int64_t nv, const int64_t* var_indices, double* out,
     CK(cudaGetLastError());
     if (!out_on_device) {
         CK(cudaMemcpyAsync(out, dst, (size_t)(nv * ctx->batch) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        sync_and_repair(ctx);
     }
     API_END(ctx)
 }
@@ -1378,7 +1391,7 @@ int pmb_objective_value(pmb_ctx* ctx, double* out_host) {
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_host, val, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    sync_and_repair(ctx);
     API_END(ctx)
 }
 
@@ -1406,7 +1419,7 @@ int pmb_gram_level_counts(pmb_ctx* ctx, int64_t* counts) {
     }
     unsigned long long h[3];
     CK(cudaMemcpyAsync(h, ctx->gram_counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    sync_and_repair(ctx);
     counts[0] = (int64_t)h[0]; counts[1] = (int64_t)h[1]; counts[2] = (int64_t)h[2] + fp64_only;
     API_END(ctx)
 }
