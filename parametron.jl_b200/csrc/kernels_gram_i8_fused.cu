@@ -43,12 +43,13 @@ constexpr int kKBlock = 128;                 // bytes of k per swizzle span
 constexpr int kPanel = kCols * kKBlock;      // 16 KB: one plane, one k-block
 constexpr int kPlaneBytes = 2 * kPanel;      // k <= 256
 constexpr int kPlanesBytes = kNS * kPlaneBytes;          // 160 KB
-constexpr int kStageCols = 8;                // one column per worker warp
+constexpr int kStageCols = 8;                // one column per warp of the worker group that owns the stage
 constexpr int kStages = 3;
 constexpr int kStageBytes = kStageCols * 256 * 8;        // 16 KB
-constexpr int kWorkers = 8;
-constexpr int kThreads = 64 + 32 * kWorkers;
-constexpr int kSmemBytes = 1024 + kPlanesBytes + kStages * kStageBytes + 2 * 2048 /* g */ + kWorkers * 768 /* reduction scratch */;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter
+constexpr int kSlicers = 8;                  // one column of a stage each
+constexpr int kThreads = 32 * (kEpiWarps + kSlicers + 4);   // + producer warp + MMA warp + two idle warps (setmaxnreg works on groups of four)
+constexpr int kSmemBytes = 1024 + kPlanesBytes + kStages * kStageBytes + 2 * 2048 /* g */;
 constexpr int kTmemCols = 512;
 
 __device__ __forceinline__ void mb_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -72,8 +73,38 @@ __device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
 __device__ __forceinline__ void mb_arrive_cluster_relaxed(uint32_t bar_cluster_addr) {   // no data is published with this arrival: no fence
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {   // 8 consecutive TMEM columns of this thread's lane
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// whole-warp flavours: every lane executes them with warp-uniform operands (so the descriptors live in uniform registers), ONE elected lane issues
+__device__ __forceinline__ void mma_i8_pair_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@q tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+        "}\n" ::"r"(i8::s_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kWorkers) : "memory"); }
+__device__ __forceinline__ void slicer_bar() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kSlicers) : "memory"); }
 __device__ __forceinline__ double2 lds_v2(uint32_t addr) {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
@@ -98,6 +129,7 @@ struct GramI8FusedArgs {
     double tol;
     int32_t force;                 // experiments (pmb_set_gram_mode 5): no certificate
     int32_t npairs;
+    unsigned long long* tl;        // timeline of CTA 0 (PMB_FUSED_DBG & 32): [role][256] clock64 stamps, role 0 worker 0, 1 worker 8, 2 MMA issuer, 3 producer
     int32_t dbg;                   // timing diagnostics only (PMB_FUSED_DBG; results wrong by construction): 1 = no MMAs, 2 = no digit / plane work,
                                    // 4 = no epilogue arithmetic or stores, 8 = no global stores, 16 = only one of the 15 products per half
 };
@@ -120,6 +152,22 @@ __device__ __forceinline__ int fused_level(unsigned long long s0, unsigned long 
     return (1.01 * sig * sig * by <= tol * ss) ? 5 : kGramI8Fp64;
 }
 
+// generic store of four consecutive entries of one output row (ragged edge, index map, accumulation): kept OUT of line -- the unrolled
+// epilogue must stay small enough for the instruction cache (five warps per scheduler run three different code regions)
+__device__ __noinline__ void fused_store_generic(double* outp, int64_t ldo, const int32_t* map, int accumulate, int64_t om, int gc, int nn, double v0,
+                                                 double v1, double v2, double v3) {
+    const double v[4] = {v0, v1, v2, v3};
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const int gj = gc + j;
+        if (gj < nn) {
+            const int64_t on = map ? (int64_t)map[gj] : (int64_t)gj;
+            double* p1 = outp + on + om * ldo;   // the MIRRORED entry, like the vector path: every (row, column) is written exactly once
+            if (accumulate) *p1 += v[j]; else *p1 = v[j];
+        }
+    }
+}
+
 // exact int64 -> fp64 with ONE rounding (to nearest even), without the slow I2F.F64 of the XU pipe: both halves become doubles
 // exactly through the 2^52 mantissa trick, one fma combines them.  |t| < 2^62.
 __device__ __forceinline__ double i64_to_f64(long long t) {
@@ -130,12 +178,33 @@ __device__ __forceinline__ double i64_to_f64(long long t) {
     return fma(dh, 4294967296.0, dl);
 }
 
+#ifndef FZ_TIMELINE
+#define TL_STAMP(role, tag) do { } while (0)
+#else
+#define TL_STAMP(role, tag)                                                                                         \
+    do {                                                                                                            \
+        if (tl_on && tl_n < 127) { a.tl[(role) * 256 + 2 * tl_n] = (unsigned long long)(tag); a.tl[(role) * 256 + 2 * tl_n + 1] = (unsigned long long)clock64(); ++tl_n; } \
+    } while (0)
+#endif
+
+// Warp roles (20 warps = 5 per scheduler: 2 epilogue + 2 slicers + 1 of the last group; launched with 96 registers each, setmaxnreg moves
+// registers to the epilogue warps -- per scheduler 2 x 144 + 2 x 72 + 48 = 480 = 5 x 96):
+//   warps 0-7   epilogue: TMEM -> exact integer combination of the five levels -> one rounding -> scale -> store (64 columns per thread)   144 registers
+//   warps 8-15  slicers: one column per warp and stage -> statistics, digits, operand panels, q and c0                                 72 registers
+//   warp 16     lane 0 = producer: bulk copies (UBLKCP) of the CTA's columns, 8 per stage, 3 stages ahead                                48 registers
+//   warp 17     MMA issuer of the leader CTA (whole warp, warp-uniform descriptors, one elected lane issues); owns the TMEM allocation; warps 18, 19 idle
+// The slicers start instance i+1 as soon as the products of instance i have read the panels, while the epilogue warps are still converting
+// and storing instance i: slicing and epilogue overlap, the tensor pipe idles only while the panels are rewritten.
+// Level order per output half: 4, then {2, 3}, then {0, 1}.  The epilogue carries w = ((a2 256 + a3) 256 + a4) between the units as a 42-bit
+// integer -- 32 low bits per column plus three 10-bit high parts per register (86 registers for 64 columns) -- and finishes each entry as
+// t = (a0 256 + a1) 2^24 + w the moment levels 0 and 1 arrive: exact (|t| < 2^55), one rounding to fp64.
 __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const GramI8FusedArgs a) {
     using namespace fz;
     using fz::mb_arrive_cluster_relaxed;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t stage_full[kStages], stage_empty[kStages];
     __shared__ __align__(8) uint64_t conv_done, planes_free;
+    __shared__ __align__(8) uint64_t g_full[2], g_empty[2];       // the offset vector of instance parity p has landed in / been read from gbuf[p]
     __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) unsigned long long cstat[8];          // this CTA's running maxima: sigma, ss, l1 / sigma, dsq[0..4]
@@ -144,7 +213,7 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = i8::cluster_ctarank();
     const uint32_t base = (i8::s_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t planes = base, staging = base + kPlanesBytes, gbuf = staging + kStages * kStageBytes, red = gbuf + 2 * 2048;
+    const uint32_t planes = base, staging = base + kPlanesBytes, gbuf = staging + kStages * kStageBytes;
     const int64_t n = a.n, k = a.k;
     const int nloc = (int)max((int64_t)0, min((int64_t)kCols, n - (int64_t)kCols * rank));   // live columns of this CTA
     const int nst = (nloc + kStageCols - 1) / kStageCols;
@@ -153,63 +222,77 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
     const int nh = n > 64 ? 2 : 1;                   // output halves with live columns
     const uint32_t colbytes = (uint32_t)(k * 8);
     const int64_t pair0 = blockIdx.x >> 1;
+    [[maybe_unused]] const bool tl_on = (a.dbg & 32) && a.tl && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 16 || warp == 17);
+    [[maybe_unused]] int tl_n = 0;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) { i8::mb_init(&stage_full[s], 1); i8::mb_init(&stage_empty[s], kWorkers); }
+        for (int s = 0; s < kStages; ++s) { i8::mb_init(&stage_full[s], 1); i8::mb_init(&stage_empty[s], kSlicers); }
         i8::mb_init(&conv_done, 2);
         i8::mb_init(&planes_free, 1);
+        i8::mb_init(&g_full[0], 1); i8::mb_init(&g_full[1], 1); i8::mb_init(&g_empty[0], 1); i8::mb_init(&g_empty[1], 1);
 #pragma unroll
-        for (int b = 0; b < 2; ++b) { i8::mb_init(&tmem_full[b], 1); i8::mb_init(&tmem_empty[b], 2 * kWorkers); }
+        for (int b = 0; b < 2; ++b) { i8::mb_init(&tmem_full[b], 1); i8::mb_init(&tmem_empty[b], 2 * kEpiWarps); }
 #pragma unroll
         for (int s = 0; s < 8; ++s) cstat[s] = 0ull;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // staging columns are 256 rows apart whatever k is: rows k .. 255 (and the tail of the offset vector) are zeroed ONCE, the bulk copies
-    // never touch them, so the workers read whole columns without bounds tests (zero rows add nothing to any statistic or digit)
+    // never touch them, so the slicers read whole columns without bounds tests (zero rows add nothing to any statistic or digit)
     if (k < 256) {
         for (uint32_t o = (uint32_t)tid * 8u; o < (uint32_t)(kStages * kStageBytes + 2 * 2048); o += (uint32_t)kThreads * 8u)
             asm volatile("st.shared.u64 [%0], %1;" ::"r"(staging + o), "l"(0ull) : "memory");
         fence_proxy_async_smem();
     }
-    if (warp == 1) i8::tmem_alloc_pair(&tmem_slot, kTmemCols);
+    if (warp == kEpiWarps + kSlicers + 1) i8::tmem_alloc_pair(&tmem_slot, kTmemCols);
     i8::tc_fence_before();
     i8::cluster_sync_all();
     i8::tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp == 0) {
-        // ===== producer: bulk copies of this CTA's columns, 8 per stage =====
-        if (lane == 0) {
-            uint32_t slot = 0, ph = 0, ii = 0;
-            const bool contiguous = k == 256 && a.ldx == 256;
-            for (int64_t inst = pair0; inst < a.batch; inst += a.npairs, ++ii) {
-                const double* xi = a.X + inst * a.x_bstride + (int64_t)kCols * rank * a.ldx;
-                for (int st = 0; st < nst; ++st) {
-                    i8::mb_wait(&stage_empty[slot], ph ^ 1u);
-                    const int c0 = st * kStageCols, nc = min(kStageCols, nloc - c0);
-                    const bool with_g = st == 0 && a.gvec != nullptr;
-                    i8::mb_expect_tx(&stage_full[slot], (uint32_t)nc * colbytes + (with_g ? colbytes : 0u));
-                    const uint32_t dst = staging + slot * kStageBytes;
-                    if (contiguous) {
-                        i8::bulk_load_1d(dst, xi + (int64_t)c0 * 256, (uint32_t)nc * 2048u, &stage_full[slot]);
-                    } else {
-                        for (int c = 0; c < nc; ++c) i8::bulk_load_1d(dst + (uint32_t)c * 2048u, xi + (int64_t)(c0 + c) * a.ldx, colbytes, &stage_full[slot]);
+    if (warp >= kEpiWarps + kSlicers) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        if (warp == kEpiWarps + kSlicers) {
+            if (lane == 0) {
+                // ===== producer: bulk copies of this CTA's columns, 8 per stage =====
+                uint32_t slot = 0, ph = 0, ii = 0;
+                const bool contiguous = k == 256 && a.ldx == 256;
+                for (int64_t inst = pair0; inst < a.batch; inst += a.npairs, ++ii) {
+                    const double* xi = a.X + inst * a.x_bstride + (int64_t)kCols * rank * a.ldx;
+                    if (a.gvec && nloc > 0) {   // gbuf[ii & 1] was last read while instance ii - 2 was sliced
+                        i8::mb_wait(&g_empty[ii & 1u], ((ii >> 1) & 1u) ^ 1u);
+                        i8::mb_expect_tx(&g_full[ii & 1u], colbytes);
+                        i8::bulk_load_1d(gbuf + (ii & 1u) * 2048u, a.gvec + inst * a.g_bstride, colbytes, &g_full[ii & 1u]);
                     }
-                    if (with_g) i8::bulk_load_1d(gbuf + (ii & 1u) * 2048u, a.gvec + inst * a.g_bstride, colbytes, &stage_full[slot]);
-                    if (++slot == kStages) { slot = 0; ph ^= 1u; }
+                    for (int st = 0; st < nst; ++st) {
+                        i8::mb_wait(&stage_empty[slot], ph ^ 1u);
+                        if (st == 0 || st == nst - 1) TL_STAMP(3, 1000 * ii + st);
+                        const int c0 = st * kStageCols, nc = min(kStageCols, nloc - c0);
+                        i8::mb_expect_tx(&stage_full[slot], (uint32_t)nc * colbytes);
+                        const uint32_t dst = staging + slot * kStageBytes;
+                        if (contiguous) {
+                            i8::bulk_load_1d(dst, xi + (int64_t)c0 * 256, (uint32_t)nc * 2048u, &stage_full[slot]);
+                        } else {
+                            for (int c = 0; c < nc; ++c) i8::bulk_load_1d(dst + (uint32_t)c * 2048u, xi + (int64_t)(c0 + c) * a.ldx, colbytes, &stage_full[slot]);
+                        }
+                        if (++slot == kStages) { slot = 0; ph ^= 1u; }
+                    }
                 }
             }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (leader CTA): per instance 2 halves x 3 units of digit-plane products into alternating 256-column TMEM buffers =====
-        if (lane == 0 && rank == 0) {
+        } else if (warp == kEpiWarps + kSlicers + 1 && rank == 0) {
+            // ===== MMA issuer (leader CTA, whole warp): per instance 2 halves x 3 units of digit-plane products into alternating 256-column
+            // TMEM buffers.  Descriptors: the high word is constant (128-byte rows, 1024 bytes between 8-row groups, SWIZZLE_128B), the low
+            // word is 1 << 16 | address >> 4 -- one add per instruction =====
             uint32_t ii = 0, uc = 0;
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             const uint32_t free_remote = i8::mapa_u32(i8::s_u32(&planes_free), 1);
+            const uint64_t dproto = i8::smem_desc_sw64<128>(0);
+            const uint64_t dhi = dproto & 0xFFFFFFFF00000000ull;
+            const uint32_t dlo0 = (uint32_t)dproto | ((planes & 0x3FFFFu) >> 4);
             for (int64_t inst = pair0; inst < a.batch; inst += a.npairs, ++ii) {
                 const uint32_t par = ii & 1u;
                 i8::mb_wait(&conv_done, par);
+                TL_STAMP(2, 1000 * ii + 1);
                 int lv = 5;
                 if (!a.force) {
                     unsigned long long m[8];
@@ -218,8 +301,8 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                     lv = fused_level(m[0], m[1], m[2], m + 3, a.tol);
                 }
                 if (lv != 5) {   // not certified: the fp64 kernel owns the instance; the operand panels are free at once
-                    i8::mb_arrive(&planes_free);
-                    i8::mb_arrive_cluster(free_remote);
+                    if (lane == 0) { i8::mb_arrive(&planes_free); i8::mb_arrive_cluster(free_remote); }
+                    __syncwarp();
                     continue;
                 }
                 i8::tc_fence_after();
@@ -229,67 +312,72 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                         const uint32_t buf = uc & 1u;
                         i8::mb_wait(&tmem_empty[buf], ((uc >> 1) & 1u) ^ 1u);
                         i8::tc_fence_after();
-                        // unit 0: levels 0, 1;  unit 1: levels 2, 3;  unit 2: level 4.  Level l = all (s, t) with s + t = l.
+                        TL_STAMP(2, 1000 * ii + 10 + 3 * h + u);
+                        uint32_t dlo = dlo0;
+                        asm volatile("" : "+r"(dlo));   // opaque: descriptors are formed next to their instruction, not hoisted (register budget: 48)
+                        // unit 0: level 4;  unit 1: levels 2, 3;  unit 2: levels 0, 1.  Level l = all (s, t) with s + t = l.
 #pragma unroll
                         for (int lsub = 0; lsub < 2; ++lsub) {
-                            const int l = 2 * u + lsub;
-                            if (l >= kNS) break;
+                            const int l = u == 0 ? 4 : (u == 1 ? 2 + lsub : lsub);
+                            if (u == 0 && lsub == 1) break;
                             const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)lsub * 128u;
+#pragma unroll
                             for (int s = 0; s <= l; ++s) {
                                 const int t = l - s;
-                                const uint32_t ap = planes + (uint32_t)s * kPlaneBytes, bp = planes + (uint32_t)t * kPlaneBytes + (uint32_t)h * (64u * kKBlock);
+#ifdef FZ_DEBUG
                                 if ((a.dbg & 1) || ((a.dbg & 16) && l > 0)) continue;
-                                for (int ks = 0; ks < nks; ++ks) {
-                                    const uint32_t off = (uint32_t)(ks >> 2) * kPanel + (uint32_t)(ks & 3) * 32u;
-                                    i8::mma_i8_pair(dcol, i8::smem_desc_sw64<128>(ap + off), i8::smem_desc_sw64<128>(bp + off), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+#endif
+                                const uint32_t alo = dlo + (uint32_t)(s * kPlaneBytes >> 4), blo = dlo + (uint32_t)(t * kPlaneBytes >> 4) + (uint32_t)h * (64u * kKBlock >> 4);
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks) {
+                                    if (ks < nks) {
+                                        const uint32_t off = (uint32_t)((ks >> 2) * kPanel + (ks & 3) * 32) >> 4;
+                                        mma_i8_pair_elect(dcol, dhi | (uint64_t)(alo + off), dhi | (uint64_t)(blo + off), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                                    }
                                 }
                             }
                         }
-                        i8::mma_commit_pair(&tmem_full[buf]);
+                        mma_commit_pair_elect(&tmem_full[buf]);
                     }
                 }
-                i8::mma_commit_pair(&planes_free);   // every product of this instance has read its operands
+                mma_commit_pair_elect(&planes_free);   // every product of this instance has read its operands
+                TL_STAMP(2, 1000 * ii + 99);
             }
         }
-    } else {
-        // ===== workers =====
-        const int wid = warp - 2;
-        const int q = warp & 3;                   // TMEM lane quarter this warp may read
-        const int chalf = wid >> 2;               // which 64 of a unit's 128 output columns (= which CTA supplied them)
+    } else if (warp >= kEpiWarps) {
+        // ===== slicers =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        const int wig = warp - kEpiWarps;         // this warp's column inside a stage
         const uint32_t peer = rank ^ 1u;
         const uint32_t conv_remote = i8::mapa_u32(i8::s_u32(&conv_done), peer);
-        const uint32_t empty_remote0 = i8::mapa_u32(i8::s_u32(&tmem_empty[0]), 0), empty_remote1 = i8::mapa_u32(i8::s_u32(&tmem_empty[1]), 0);
-        const bool vec_ok = !a.map && !a.accumulate && (a.ldo & 3) == 0 && (a.o_bstride & 3) == 0 && (((uintptr_t)a.out) & 31) == 0;
         // staging reads: rows 4 lane .. 4 lane + 3 of each k-block as two 16-byte loads with the halves SWAPPED for lanes 4-7 of every 8, so a
         // quarter warp touches all 32 banks; the swap is undone for free by the selectors of the byte permutes that assemble the plane words
         const bool swp = (lane & 4) != 0;
         const uint32_t lane_off = (uint32_t)lane * 32u + (swp ? 16u : 0u);
         const uint32_t selA = swp ? 0x1054u : 0x5410u, selB = swp ? 0x3276u : 0x7632u;
         const uint32_t word_off = (((uint32_t)(lane >> 2)) << 4) | ((uint32_t)(lane & 3) * 4u);   // this lane's 4 bytes inside a 128-byte row, before the swizzle
-        const uint32_t red_w = red + (uint32_t)wid * 768u;                                          // [3][32] doubles of reduction scratch
-        uint32_t slot = 0, ph = 0, ii = 0, uc = 0;
+        const bool restore = k < 96;              // the reduction scratch (first 768 bytes of the warp's own column slot) reaches into the zeroed tail rows
+        uint32_t slot = 0, ph = 0, ii = 0;
         for (int64_t inst = pair0; inst < a.batch; inst += a.npairs, ++ii) {
             const uint32_t par = ii & 1u;
-            // ---------- (a) slice this CTA's columns into the operand panels ----------
+            TL_STAMP(1, 1000 * ii + 0);
             if (ii > 0) i8::mb_wait(&planes_free, (ii - 1u) & 1u);   // the previous instance's products have read the panels
-            double gv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) gv[e] = 0.0;
+            TL_STAMP(1, 1000 * ii + 1);
             double w_sig = 0.0, w_ss = 0.0, w_l1 = 0.0;   // running maxima: sigma (uniform), ||x||^2 (lane 0), ||x / sigma||_1 (lane 8)
             uint32_t w_dsq[kNS];
             bool w_bad = false;
 #pragma unroll
             for (int s = 0; s < kNS; ++s) w_dsq[s] = 0u;
             const double qs = a.gvec ? (a.qscale.ptr ? a.qscale.c * a.qscale.ptr[inst * a.qscale.bstride] : a.qscale.c) : 0.0;
+            if (a.gvec && nloc > 0) i8::mb_wait(&g_full[par], (ii >> 1) & 1u);   // the offset vector of this instance (same, swapped, element order as the columns)
+            const uint32_t gb = gbuf + par * 2048u + lane_off;
             for (int st = 0; st < nst; ++st) {
                 i8::mb_wait(&stage_full[slot], ph);
-                const uint32_t cb = staging + slot * kStageBytes + (uint32_t)wid * 2048u + lane_off;
-                if (st == 0 && a.gvec) {   // the offset vector arrived with this stage; same (swapped) element order as the columns
-                    const uint32_t gb = gbuf + par * 2048u + lane_off;
-                    const double2 g0 = lds_v2(gb), g1 = lds_v2(gb ^ 16u), g2 = lds_v2(gb + 1024u), g3 = lds_v2((gb + 1024u) ^ 16u);
-                    gv[0] = g0.x; gv[1] = g0.y; gv[2] = g1.x; gv[3] = g1.y; gv[4] = g2.x; gv[5] = g2.y; gv[6] = g3.x; gv[7] = g3.y;
-                }
-                const int lc = st * kStageCols + wid;   // local column of this warp
+                const uint32_t myslot = slot;
+                if (++slot == kStages) { slot = 0; ph ^= 1u; }
+                const uint32_t colbase = staging + myslot * kStageBytes + (uint32_t)wig * 2048u;
+                const uint32_t cb = colbase + lane_off;
+                const int lc = st * kStageCols + wig;   // local column of this warp
                 const bool live = lc < nloc;            // warp-uniform
                 double v[8];
                 {
@@ -297,18 +385,45 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                     v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
                 }
                 __syncwarp();
-                if (lane == 0) i8::mb_arrive(&stage_empty[slot]);   // the column sits in registers: the slot can take the stage 3 ahead
-                if (++slot == kStages) { slot = 0; ph ^= 1u; }
-                if (!live || (a.dbg & 2)) continue;
+#ifdef FZ_DEBUG
+                if (a.dbg & 2) { if (lane == 0) i8::mb_arrive(&stage_empty[myslot]); continue; }
+#endif
+                if (!live) { if (lane == 0) i8::mb_arrive(&stage_empty[myslot]); continue; }
                 double am = 0.0, ss = 0.0, l1 = 0.0, dg = 0.0;
+                {
+                    double gv[8];
+                    if (a.gvec) {
+                        const double2 g0 = lds_v2(gb), g1 = lds_v2(gb ^ 16u), g2 = lds_v2(gb + 1024u), g3 = lds_v2((gb + 1024u) ^ 16u);
+                        gv[0] = g0.x; gv[1] = g0.y; gv[2] = g1.x; gv[3] = g1.y; gv[4] = g2.x; gv[5] = g2.y; gv[6] = g3.x; gv[7] = g3.y;
+                    } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const double av = fabs(v[e]);
-                    am = dmax(am, av);
-                    l1 += av;
-                    ss = fma(v[e], v[e], ss);
-                    dg = fma(v[e], gv[e], dg);
+                        for (int e = 0; e < 8; ++e) gv[e] = 0.0;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const double av = fabs(v[e]);
+                        am = dmax(am, av);
+                        l1 += av;
+                        ss = fma(v[e], v[e], ss);
+                        dg = fma(v[e], gv[e], dg);
+                    }
+                    if (a.gvec && rank == 0 && lc == 0) {   // c0 += cscale g.g, once per instance
+                        double gg = 0.0;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) gg = fma(gv[e], gv[e], gg);
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, o);
+                        if (lane == 0) {
+                            const double cs = a.cscale.ptr ? a.cscale.c * a.cscale.ptr[inst * a.cscale.bstride] : a.cscale.c;
+                            atomicAdd(a.c0out + inst, cs * gg);
+                        }
+                    }
                 }
+                // per-lane partial sums -> scratch (the head of this warp's own column slot: the column sits in registers); lanes 0-23 add four
+                // partials each, three butterfly steps finish the three sums: ||x||^2 in lane 0, ||x||_1 in lane 8, x.g in lane 16
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(colbase + (uint32_t)lane * 8u), "d"(ss) : "memory");
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(colbase + 256u + (uint32_t)lane * 8u), "d"(l1) : "memory");
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(colbase + 512u + (uint32_t)lane * 8u), "d"(dg) : "memory");
                 // largest magnitude of the column in every lane: two integer warp reductions on the bit pattern (monotonic for values >= 0)
                 const uint32_t hmax = __reduce_max_sync(0xffffffffu, (uint32_t)__double2hiint(am));
                 const uint32_t lmax = __reduce_max_sync(0xffffffffu, (uint32_t)__double2hiint(am) == hmax ? (uint32_t)__double2loint(am) : 0u);
@@ -319,17 +434,21 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                 const double inv = zero ? 0.0 : 0.99 / amax;
                 const double sigma = zero ? 1.0 : amax * (1.0 / 0.99);
                 const double mult = inv * 140737488355328.0;   // 2^47
-                // per-lane partial sums -> scratch; lanes 0-23 add four partials each, three butterfly steps finish the three sums:
-                // ||x||^2 in lane 0, ||x||_1 in lane 8, x.g in lane 16
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(red_w + (uint32_t)lane * 8u), "d"(ss) : "memory");
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(red_w + 256u + (uint32_t)lane * 8u), "d"(l1) : "memory");
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(red_w + 512u + (uint32_t)lane * 8u), "d"(dg) : "memory");
                 __syncwarp();
                 double tot = 0.0;
                 if (lane < 24) {
-                    const double2 r0 = lds_v2(red_w + (uint32_t)lane * 32u), r1 = lds_v2(red_w + (uint32_t)lane * 32u + 16u);
+                    const double2 r0 = lds_v2(colbase + (uint32_t)lane * 32u), r1 = lds_v2(colbase + (uint32_t)lane * 32u + 16u);
                     tot = (r0.x + r0.y) + (r1.x + r1.y);
                 }
+                __syncwarp();
+                if (restore) {
+                    asm volatile("st.shared.u64 [%0], %1;" ::"r"(colbase + (uint32_t)lane * 8u), "l"(0ull) : "memory");
+                    asm volatile("st.shared.u64 [%0], %1;" ::"r"(colbase + 256u + (uint32_t)lane * 8u), "l"(0ull) : "memory");
+                    asm volatile("st.shared.u64 [%0], %1;" ::"r"(colbase + 512u + (uint32_t)lane * 8u), "l"(0ull) : "memory");
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                }
+                if (lane == 0) i8::mb_arrive(&stage_empty[myslot]);   // column and scratch are done with the slot: it can take the stage 3 ahead
                 tot += __shfl_xor_sync(0xffffffffu, tot, 1);
                 tot += __shfl_xor_sync(0xffffffffu, tot, 2);
                 tot += __shfl_xor_sync(0xffffffffu, tot, 4);
@@ -382,18 +501,6 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
 #pragma unroll
                     for (int s2 = 0; s2 < kNS; ++s2) w_dsq[s2] = w_dsq[s2] > dsq[s2] ? w_dsq[s2] : dsq[s2];
                 }
-                if (a.gvec && rank == 0 && lc == 0) {   // c0 += cscale g.g, once per instance
-                    double gg = 0.0;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) gg = fma(gv[e], gv[e], gg);
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, o);
-                    if (lane == 0) {
-                        const double cs = a.cscale.ptr ? a.cscale.c * a.cscale.ptr[inst * a.cscale.bstride] : a.cscale.c;
-                        atomicAdd(a.c0out + inst, cs * gg);
-                    }
-                }
-                __syncwarp();   // the reduction scratch is rewritten by the next column
             }
             if (lane == 0) {
                 if (w_bad) atomicMax(&cstat[0], (unsigned long long)__double_as_longlong(CUDART_INF));
@@ -406,9 +513,11 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
             } else if (lane == 8 && !w_bad && w_l1 > 0.0) {
                 atomicMax(&cstat[2], (unsigned long long)__double_as_longlong(w_l1));
             }
+            TL_STAMP(1, 1000 * ii + 2);
             fence_proxy_async_smem();   // the panel writes (generic proxy) become visible to the tensor core (async proxy)
-            worker_bar();
-            if (wid == 0 && lane == 0) {   // publish this CTA's statistics in both CTAs, then count the CTA in on both conv_done barriers
+            slicer_bar();
+            if (wig == 0 && lane == 0) {   // publish this CTA's statistics in both CTAs, then count the CTA in on both conv_done barriers
+                if (a.gvec && nloc > 0) i8::mb_arrive(&g_empty[par]);   // every slicer of this CTA is done with the offset vector
 #pragma unroll
                 for (int s2 = 0; s2 < 8; ++s2) {
                     const unsigned long long vv = cstat[s2];
@@ -418,135 +527,159 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                 }
                 i8::mb_arrive_cluster(i8::mapa_u32(i8::s_u32(&conv_done), rank));
                 i8::mb_arrive_cluster(conv_remote);
+                TL_STAMP(1, 1000 * ii + 3);
+                if (rank == 0) {   // the record the fp64 companion launch and pmb_gram_level_counts read
+                    i8::mb_wait(&conv_done, par);
+                    unsigned long long m[8];
+#pragma unroll
+                    for (int s2 = 0; s2 < 8; ++s2) m[s2] = xstat[par][0][s2] > xstat[par][1][s2] ? xstat[par][0][s2] : xstat[par][1][s2];
+                    const int lv = a.force ? 5 : fused_level(m[0], m[1], m[2], m + 3, a.tol);
+                    unsigned long long* sp = a.stats + inst * kGramI8StatsStride;
+#pragma unroll
+                    for (int s2 = 0; s2 < 8; ++s2) sp[s2] = m[s2];
+                    sp[8] = 0ull; sp[14] = (unsigned long long)n; sp[15] = (unsigned long long)lv;
+                    if (lv != 5) atomicAdd(a.stats + a.batch * kGramI8StatsStride, 1ull);
+                }
             }
-            // ---------- verdict ----------
+        }
+    } else {
+        // ===== epilogue =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+        const int q = warp & 3;                   // TMEM lane quarter this warp may read
+        const int chalf = warp >> 2;              // which 64 of a unit's 128 output columns (= which CTA supplied them)
+        const uint32_t empty_remote0 = i8::mapa_u32(i8::s_u32(&tmem_empty[0]), 0), empty_remote1 = i8::mapa_u32(i8::s_u32(&tmem_empty[1]), 0);
+        const bool vec_ok = !a.map && !a.accumulate && (a.ldo & 3) == 0 && (a.o_bstride & 3) == 0 && (((uintptr_t)a.out) & 31) == 0;
+        const int nn = (int)n;
+        const int row0 = kCols * (int)rank + q * 32;   // first row of this warp
+        const int gi = row0 + lane;
+        const bool row_ok = gi < nn;
+        uint32_t ii = 0, uc = 0;
+        for (int64_t inst = pair0; inst < a.batch; inst += a.npairs, ++ii) {
+            const uint32_t par = ii & 1u;
+            TL_STAMP(0, 1000 * ii + 0);
             i8::mb_wait(&conv_done, par);
+            TL_STAMP(0, 1000 * ii + 4);
             int lv = 5;
-            unsigned long long m[8];
+            if (!a.force) {
+                unsigned long long m[8];
 #pragma unroll
-            for (int s2 = 0; s2 < 8; ++s2) m[s2] = xstat[par][0][s2] > xstat[par][1][s2] ? xstat[par][0][s2] : xstat[par][1][s2];
-            if (!a.force) lv = fused_level(m[0], m[1], m[2], m + 3, a.tol);
-            if (rank == 0 && wid == 0 && lane == 0) {   // the record the fp64 companion launch and pmb_gram_level_counts read
-                unsigned long long* sp = a.stats + inst * kGramI8StatsStride;
-#pragma unroll
-                for (int s2 = 0; s2 < 8; ++s2) sp[s2] = m[s2];
-                sp[8] = 0ull; sp[14] = (unsigned long long)n; sp[15] = (unsigned long long)lv;
-                if (lv != 5) atomicAdd(a.stats + a.batch * kGramI8StatsStride, 1ull);
+                for (int s2 = 0; s2 < 8; ++s2) m[s2] = xstat[par][0][s2] > xstat[par][1][s2] ? xstat[par][0][s2] : xstat[par][1][s2];
+                lv = fused_level(m[0], m[1], m[2], m + 3, a.tol);
             }
             if (lv != 5) continue;
-            // ---------- (b) epilogue: rows = this CTA's columns (lane quarter q), 64 output columns per warp and half ----------
-            const int64_t row0 = (int64_t)kCols * rank + q * 32;   // first row of this warp
-            const int64_t gi = row0 + lane;
-            const bool row_ok = gi < n;
             const double scl = a.scale.ptr ? a.scale.c * a.scale.ptr[inst * a.scale.bstride] : a.scale.c;
             const double sgi = row_ok ? sig[par][gi] : 0.0;   // sigma_i 2^-23
             const double fgi = scl * sgi;
-            const int64_t om = row_ok ? (a.map ? a.map[gi] : gi) : 0;
             double* outp = a.out + inst * a.o_bstride;
             for (int h = 0; h < nh; ++h) {
-                const int64_t gj0 = (int64_t)kCols * chalf + 64 * h;   // global column of this warp's first output column
+                const int gj0 = kCols * chalf + 64 * h;   // global column of this warp's first output column
                 const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * chalf);
-                long long acc[64];
-                // unit 0: levels 0, 1 -> a0 * 256 + a1 (exact in int32: |a0| <= 2^22, |a1| <= 2^23)
+                uint32_t wlo[64];     // low 32 bits of w = (a2 256 + a3) 256 + a4   (first: a4 itself)
+                uint32_t whi[22];     // bits 32-41 of w, three 10-bit fields per register
+#pragma unroll
+                for (int r = 0; r < 22; ++r) whi[r] = 0u;
+                // unit 0: level 4
                 {
                     const uint32_t buf = uc & 1u;
                     i8::mb_wait(&tmem_full[buf], (uc >> 1) & 1u);
+                    TL_STAMP(0, 1000 * ii + 10 * (h + 1) + 1);
                     i8::tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        int32_t a0[16], a1[16];
-                        i8::tmem_ld16(trow + buf * 256u + 16u * c, a0);
-                        i8::tmem_ld16(trow + buf * 256u + 128u + 16u * c, a1);
+                    for (int c = 0; c < 8; ++c) {
+                        int32_t a4[8];
+                        tmem_ld8(trow + buf * 256u + 8u * c, a4);
                         i8::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[16 * c + j] = (long long)(a0[j] * 256 + a1[j]);
+                        for (int j = 0; j < 8; ++j) wlo[8 * c + j] = (uint32_t)a4[j];
                     }
                     i8::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mb_arrive_cluster_relaxed(buf ? empty_remote1 : empty_remote0);
                     ++uc;
                 }
-                // unit 1: levels 2, 3 -> acc * 65536 + a2 * 256 + a3 (exact, < 2^47)
+                // unit 1: levels 2, 3 -> w = (a2 256 + a3) 256 + a4, |w| < 2^40
                 {
                     const uint32_t buf = uc & 1u;
                     i8::mb_wait(&tmem_full[buf], (uc >> 1) & 1u);
+                    TL_STAMP(0, 1000 * ii + 10 * (h + 1) + 2);
                     i8::tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        int32_t a2[16], a3[16];
-                        i8::tmem_ld16(trow + buf * 256u + 16u * c, a2);
-                        i8::tmem_ld16(trow + buf * 256u + 128u + 16u * c, a3);
+                    for (int c = 0; c < 8; ++c) {
+                        int32_t a2[8], a3[8];
+                        tmem_ld8(trow + buf * 256u + 8u * c, a2);
+                        tmem_ld8(trow + buf * 256u + 128u + 8u * c, a3);
                         i8::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[16 * c + j] = acc[16 * c + j] * 65536 + ((long long)a2[j] * 256 + (long long)a3[j]);
+                        for (int j = 0; j < 8; ++j) {
+                            const int e = 8 * c + j;
+                            const long long w = (((long long)a2[j] << 8) + (long long)a3[j]) * 256 + (long long)(int32_t)wlo[e];
+                            wlo[e] = (uint32_t)w;
+                            whi[e / 3] |= ((uint32_t)(w >> 32) & 0x3FFu) << (10 * (e % 3));
+                        }
                     }
                     i8::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mb_arrive_cluster_relaxed(buf ? empty_remote1 : empty_remote0);
                     ++uc;
                 }
-                // unit 2: level 4 -> acc * 256 + a4, the one rounding to fp64, scale, store
+                // unit 2: levels 0, 1 -> t = (a0 256 + a1) 2^24 + w, the one rounding to fp64, scale, store.  Every unordered pair of columns is
+                // scaled as (t * (scale sigma_lo 2^-23)) * (sigma_hi 2^-23), lo <= hi the column indices: what the two-kernel route computes once
+                // and mirrors -- both triangles are bit-identical to it.  A chunk of 8 columns lies right of, left of, or across the diagonal for
+                // the whole warp (rows row0 .. row0 + 31)
                 {
                     const uint32_t buf = uc & 1u;
                     i8::mb_wait(&tmem_full[buf], (uc >> 1) & 1u);
+                    TL_STAMP(0, 1000 * ii + 10 * (h + 1) + 3);
                     i8::tc_fence_after();
+                    const bool fast = vec_ok && row0 + 32 <= nn && gj0 + 64 <= nn;
+                    const int64_t om = (!fast && row_ok) ? (a.map ? (int64_t)a.map[gi] : (int64_t)gi) : 0;
+                    double* pcol = outp + gj0 + (int64_t)gi * a.ldo;
+                    const double* sg = &sig[par][gj0];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        int32_t a4[16];
-                        i8::tmem_ld16(trow + buf * 256u + 16u * c, a4);
+                    for (int c = 0; c < 16; ++c) {
+                        int32_t a0[4], a1[4];
+                        tmem_ld4(trow + buf * 256u + 4u * c, a0);
+                        tmem_ld4(trow + buf * 256u + 128u + 4u * c, a1);
                         i8::tmem_ld_wait();
-                        if (c == 3) {   // the last read of this unit: hand the buffer back before the stores
+                        if (c == 15) {   // the last read of this unit: hand the buffer back before the last conversions and stores
                             i8::tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mb_arrive_cluster_relaxed(buf ? empty_remote1 : empty_remote0);
                         }
+#ifdef FZ_DEBUG
                         if (a.dbg & 4) continue;
-                        const int64_t gc = gj0 + 16 * c;
-                        double val[16];
-                        // every unordered pair of columns is scaled as (t * (scale sigma_lo 2^-23)) * (sigma_hi 2^-23), lo <= hi the column
-                        // indices: what the two-kernel route computes once and mirrors -- both triangles are bit-identical to it.  A chunk
-                        // of 16 columns lies right of, left of, or across the diagonal for the whole warp (rows row0 .. row0 + 31)
-                        if (gc >= row0 + 32) {
+#endif
+                        const int gc = gj0 + 4 * c;
+                        double val[4];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const double t = i64_to_f64(acc[16 * c + j] * 256 + (long long)a4[j]);
-                                val[j] = (t * fgi) * (gc + j < n ? sig[par][gc + j] : 0.0);
-                            }
-                        } else if (gc + 16 <= row0) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const double t = i64_to_f64(acc[16 * c + j] * 256 + (long long)a4[j]);
-                                val[j] = (t * (scl * sig[par][gc + j])) * sgi;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int64_t gj = gc + j;
-                                const double t = i64_to_f64(acc[16 * c + j] * 256 + (long long)a4[j]);
-                                const double sgj = gj < n ? sig[par][gj] : 0.0;
-                                val[j] = gi <= gj ? (t * fgi) * sgj : (t * (scl * sgj)) * sgi;
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = 4 * c + j;
+                            // t = (a0 256 + a1) 2^24 + w as a 64-bit integer in two words: low = wlo + (p << 24), high = hi10 + (p >> 8) + carry
+                            const int32_t p01 = a0[j] * 256 + a1[j];
+                            const int32_t hi10 = ((int32_t)(whi[e / 3] << (22 - 10 * (e % 3)))) >> 22;   // sign-extended 10-bit field
+                            const uint32_t plo = (uint32_t)p01 << 24;
+                            const uint32_t tlo = wlo[e] + plo;
+                            const int32_t thi = hi10 + (p01 >> 8) + (int32_t)(tlo < plo);
+                            const double dh = __hiloint2double(0x43300000, thi ^ (int)0x80000000) - 4503601774854144.0;   // exact: 2^52 + 2^31 offset
+                            const double dl = __hiloint2double(0x43300000, (int)tlo) - 4503599627370496.0;                 // exact: 2^52 offset
+                            const double t = fma(dh, 4294967296.0, dl);                                                     // the one rounding
+                            const double sgj = sg[e];
+                            const bool up = gi <= gc + j;
+                            const double fa = up ? fgi : scl * sgj, fb = up ? sgj : sgi;
+                            val[j] = (t * fa) * fb;
                         }
-                        if (a.dbg & 8) { if (val[0] == 1.2345e-300 && val[7] == 5.0 && val[15] == 7.0) outp[0] = val[3]; continue; }
-                        if (vec_ok && row_ok && gc + 16 <= n) {
-                            // H is symmetric and the values are bit-symmetric: write this thread's 16 entries of ROW gi as 16 consecutive
-                            // entries of COLUMN gi (4 x 256-bit streaming stores)
-                            double* p2 = outp + gc + gi * a.ldo;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4)
-                                asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p2 + j), "d"(val[j]), "d"(val[j + 1]), "d"(val[j + 2]), "d"(val[j + 3]) : "memory");
+#ifdef FZ_DEBUG
+                        if (a.dbg & 8) { if (val[0] == 1.2345e-300 && val[3] == 5.0) outp[0] = val[1]; continue; }
+#endif
+                        if (fast) {
+                            // H is symmetric and the values are bit-symmetric: this thread's entries of ROW gi go out as consecutive entries of
+                            // COLUMN gi (256-bit streaming stores)
+                            asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(pcol + 4 * c), "d"(val[0]), "d"(val[1]), "d"(val[2]), "d"(val[3]) : "memory");
                         } else if (row_ok) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int64_t gj = gc + j;
-                                if (gj < n) {
-                                    const int64_t on = a.map ? a.map[gj] : gj;
-                                    double* p1 = outp + on + om * a.ldo;   // the MIRRORED entry, like the vector path: every (row, column) is written exactly once
-                                    if (a.accumulate) *p1 += val[j]; else *p1 = val[j];
-                                }
-                            }
+                            fused_store_generic(outp, a.ldo, a.map, a.accumulate, om, gc, nn, val[0], val[1], val[2], val[3]);
                         }
                     }
+                    TL_STAMP(0, 1000 * ii + 10 * (h + 1) + 4);
                     ++uc;
                 }
             }
@@ -554,7 +687,7 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
     }
     i8::tc_fence_before();
     i8::cluster_sync_all();
-    if (warp == 1) {
+    if (warp == fz::kEpiWarps + fz::kSlicers + 1) {
         i8::tc_fence_after();
         i8::tmem_dealloc_pair(tmem_base, fz::kTmemCols);
     }
@@ -615,6 +748,7 @@ bool launch_gram_i8_fused(const GramArgs& g, const GramI8Scratch& sc, int64_t ba
     a.stats = sc.stats; a.tol = sc.tol; a.force = sc.force_ns != 0;
     a.npairs = (int32_t)std::min<int64_t>(batch, fused_max_pairs(sm_count));
     if (const char* e = getenv("PMB_FUSED_DBG")) a.dbg = atoi(e);
+    a.tl = sc.stats + batch * kGramI8StatsStride + 2;   // the planner / probe reserves 1024 more entries when the timeline is wanted
     if (a.npairs < 1) return false;
     cudaMemsetAsync(sc.stats + batch * kGramI8StatsStride, 0, sizeof(unsigned long long), stream);   // uncertified-instance counter
     cudaLaunchConfig_t cfg{};
