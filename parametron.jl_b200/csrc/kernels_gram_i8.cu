@@ -537,8 +537,9 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread, all digit-plane pairs with s + t <= NS - 1, level s + t -> TMEM columns [(s+t) BN, +BN) =====
-        if (lane == 0 && rank == 0) {
+        // ===== MMA issuer: all digit-plane pairs with s + t <= NS - 1, level s + t -> TMEM columns [(s+t) BN, +BN).  The WHOLE warp runs the
+        // loop with warp-uniform values (descriptors in uniform registers), one elected lane issues (pmb_i8_ptx.h) =====
+        if (rank == 0) {
             uint32_t it = 0, tile_it = 0;
             [[maybe_unused]] uint32_t ita = 0;
             for (int64_t u = unit0; u < a.total_tiles; u += ustride) {
@@ -568,13 +569,13 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                                     for (int c = 0; c < W; c += per) {
                                         const int wn = (W - c) < per ? (W - c) : per;
                                         const uint64_t bd = i8::smem_desc_sw64<KC>(stage + c * KC + kk * 32);
-                                        i8::mma_i8(tmem_base + (uint32_t)(ab * NS * BN + si * BN + c), ad, bd, i8_idesc(wn), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
+                                        i8::mma_i8_elect(tmem_base + (uint32_t)(ab * NS * BN + si * BN + c), ad, bd, i8_idesc(wn), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
                                     }
                                 }
                             }
-                            i8::mma_commit(&empty_a[sa]);   // this row-panel slot may be refilled
+                            i8::mma_commit_elect(&empty_a[sa]);   // this row-panel slot may be refilled
                         }
-                        i8::mma_commit(&empty_bar[s]);
+                        i8::mma_commit_elect(&empty_bar[s]);
                     } else {
 #pragma unroll
                     for (int kk = 0; kk < KC / 32; ++kk) {
@@ -590,11 +591,11 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
 #pragma unroll
                                 for (int t0 = 0; t0 + 1 < NS - si; t0 += 2) {
                                     const uint64_t bd = i8::smem_desc_sw64<KC>(stage + NS * C::kITile + (t0 / 2) * C::kJTile + kk * 32);
-                                    i8::mma_i8_pair(tmem_base + (uint32_t)(ab * NS * BN + (si + t0) * BN), ad, bd, i8_idesc(2 * BN, 256), first);
+                                    i8::mma_i8_pair_elect(tmem_base + (uint32_t)(ab * NS * BN + (si + t0) * BN), ad, bd, i8_idesc(2 * BN, 256), first);
                                 }
                                 if ((NS - si) & 1) {
                                     const uint64_t bd = i8::smem_desc_sw64<KC>(stage + NS * C::kITile + C::kNPair * C::kJTile + ((NS - 1 - si) / 2) * C::kHalfTile + kk * 32);
-                                    i8::mma_i8_pair(tmem_base + (uint32_t)(ab * NS * BN + (NS - 1) * BN), ad, bd, i8_idesc(BN, 256), first);
+                                    i8::mma_i8_pair_elect(tmem_base + (uint32_t)(ab * NS * BN + (NS - 1) * BN), ad, bd, i8_idesc(BN, 256), first);
                                 }
                             }
                         } else {
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
 #pragma unroll
                                 for (int c = 0; c < NS * BN; c += NS * BN / 2) {
                                     const uint64_t bd = i8::smem_desc_sw64<KC>(stage + NS * C::kITile + c * KC + kk * 32);
-                                    i8::mma_i8(tmem_base + (uint32_t)(ab * NS * BN + c), ad, bd, i8_idesc(NS * BN / 2), (kc > 0 || kk > 0 || rep3 > 0) ? 1u : 0u);
+                                    i8::mma_i8_elect(tmem_base + (uint32_t)(ab * NS * BN + c), ad, bd, i8_idesc(NS * BN / 2), (kc > 0 || kk > 0 || rep3 > 0) ? 1u : 0u);
                                 }
                             }
                         } else
@@ -625,15 +626,15 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
                             for (int c = 0; c < W; c += per) {
                                 const int wn = (W - c) < per ? (W - c) : per;
                                 const uint64_t bd = i8::smem_desc_sw64<KC>(stage + NS * C::kITile + c * KC + kk * 32);
-                                i8::mma_i8(tmem_base + (uint32_t)(ab * NS * BN + si * BN + c), ad, bd, i8_idesc(wn), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
+                                i8::mma_i8_elect(tmem_base + (uint32_t)(ab * NS * BN + si * BN + c), ad, bd, i8_idesc(wn), (kc > 0 || kk > 0 || si > 0) ? 1u : 0u);
                             }
                         }
                         }
                     }
-                    if constexpr (CTAS == 2) i8::mma_commit_pair(&empty_bar[s]); else i8::mma_commit(&empty_bar[s]);   // the stage may be refilled once these MMAs have read it
+                    if constexpr (CTAS == 2) i8::mma_commit_pair_elect(&empty_bar[s]); else i8::mma_commit_elect(&empty_bar[s]);   // the stage may be refilled once these MMAs have read it
                     }
                 }
-                if constexpr (CTAS == 2) i8::mma_commit_pair(&tmem_full_bar[ab]); else i8::mma_commit(&tmem_full_bar[ab]);
+                if constexpr (CTAS == 2) i8::mma_commit_pair_elect(&tmem_full_bar[ab]); else i8::mma_commit_elect(&tmem_full_bar[ab]);
                 ++tile_it;
             }
         }

@@ -82,27 +82,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {   //
                  : "r"(taddr)
                  : "memory");
 }
-// whole-warp flavours: every lane executes them with warp-uniform operands (so the descriptors live in uniform registers), ONE elected lane issues
-__device__ __forceinline__ void mma_i8_pair_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p, q;\n"
-        "elect.sync _|q, 0xffffffff;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "@q tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit_pair_elect(uint64_t* bar) {
-    asm volatile(
-        "{\n"
-        ".reg .pred q;\n"
-        "elect.sync _|q, 0xffffffff;\n"
-        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
-        "}\n" ::"r"(i8::s_u32(bar)), "h"((uint16_t)3)
-        : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void slicer_bar() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kSlicers) : "memory"); }
 __device__ __forceinline__ double2 lds_v2(uint32_t addr) {
@@ -283,7 +262,10 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
             // ===== MMA issuer (leader CTA, whole warp): per instance 2 halves x 3 units of digit-plane products into alternating 256-column
             // TMEM buffers.  Descriptors: the high word is constant (128-byte rows, 1024 bytes between 8-row groups, SWIZZLE_128B), the low
             // word is 1 << 16 | address >> 4 -- one add per instruction =====
-            uint32_t ii = 0, uc = 0;
+            // TMEM regions: A = columns [0, 256) takes unit 0 (level 4, 128 columns) and then unit 1 (levels 2, 3) -- both drained by a few
+            // tcgen05.ld; B = columns [256, 512) takes unit 2 (levels 0, 1), whose drain is interleaved with the conversions and stores: while it
+            // lasts the products of the NEXT half's units 0 and 1 already run in region A
+            uint32_t ii = 0, ucA = 0, ucB = 0;
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             const uint32_t free_remote = i8::mapa_u32(i8::s_u32(&planes_free), 1);
             const uint64_t dproto = i8::smem_desc_sw64<128>(0);
@@ -308,9 +290,10 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                 i8::tc_fence_after();
                 for (int h = 0; h < nh; ++h) {
 #pragma unroll
-                    for (int u = 0; u < 3; ++u, ++uc) {
-                        const uint32_t buf = uc & 1u;
-                        i8::mb_wait(&tmem_empty[buf], ((uc >> 1) & 1u) ^ 1u);
+                    for (int u = 0; u < 3; ++u) {
+                        const uint32_t buf = u == 2 ? 1u : 0u;
+                        const uint32_t use = u == 2 ? ucB++ : ucA++;
+                        i8::mb_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
                         i8::tc_fence_after();
                         TL_STAMP(2, 1000 * ii + 10 + 3 * h + u);
                         uint32_t dlo = dlo0;
@@ -332,15 +315,15 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                                 for (int ks = 0; ks < 8; ++ks) {
                                     if (ks < nks) {
                                         const uint32_t off = (uint32_t)((ks >> 2) * kPanel + (ks & 3) * 32) >> 4;
-                                        mma_i8_pair_elect(dcol, dhi | (uint64_t)(alo + off), dhi | (uint64_t)(blo + off), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                                        i8::mma_i8_pair_elect(dcol, dhi | (uint64_t)(alo + off), dhi | (uint64_t)(blo + off), idesc, (s > 0 || ks > 0) ? 1u : 0u);
                                     }
                                 }
                             }
                         }
-                        mma_commit_pair_elect(&tmem_full[buf]);
+                        i8::mma_commit_pair_elect(&tmem_full[buf]);
                     }
                 }
-                mma_commit_pair_elect(&planes_free);   // every product of this instance has read its operands
+                i8::mma_commit_pair_elect(&planes_free);   // every product of this instance has read its operands
                 TL_STAMP(2, 1000 * ii + 99);
             }
         }
@@ -553,7 +536,7 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
         const int row0 = kCols * (int)rank + q * 32;   // first row of this warp
         const int gi = row0 + lane;
         const bool row_ok = gi < nn;
-        uint32_t ii = 0, uc = 0;
+        uint32_t ii = 0, ucA = 0, ucB = 0;
         for (int64_t inst = pair0; inst < a.batch; inst += a.npairs, ++ii) {
             const uint32_t par = ii & 1u;
             TL_STAMP(0, 1000 * ii + 0);
@@ -578,10 +561,10 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                 uint32_t whi[22];     // bits 32-41 of w, three 10-bit fields per register
 #pragma unroll
                 for (int r = 0; r < 22; ++r) whi[r] = 0u;
-                // unit 0: level 4
+                // unit 0: level 4 (region A)
                 {
-                    const uint32_t buf = uc & 1u;
-                    i8::mb_wait(&tmem_full[buf], (uc >> 1) & 1u);
+                    const uint32_t buf = 0u;
+                    i8::mb_wait(&tmem_full[buf], ucA & 1u);
                     TL_STAMP(0, 1000 * ii + 10 * (h + 1) + 1);
                     i8::tc_fence_after();
 #pragma unroll
@@ -594,13 +577,13 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                     }
                     i8::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mb_arrive_cluster_relaxed(buf ? empty_remote1 : empty_remote0);
-                    ++uc;
+                    if (lane == 0) mb_arrive_cluster_relaxed(empty_remote0);
+                    ++ucA;
                 }
-                // unit 1: levels 2, 3 -> w = (a2 256 + a3) 256 + a4, |w| < 2^40
+                // unit 1: levels 2, 3 -> w = (a2 256 + a3) 256 + a4, |w| < 2^40 (region A)
                 {
-                    const uint32_t buf = uc & 1u;
-                    i8::mb_wait(&tmem_full[buf], (uc >> 1) & 1u);
+                    const uint32_t buf = 0u;
+                    i8::mb_wait(&tmem_full[buf], ucA & 1u);
                     TL_STAMP(0, 1000 * ii + 10 * (h + 1) + 2);
                     i8::tc_fence_after();
 #pragma unroll
@@ -619,16 +602,16 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                     }
                     i8::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mb_arrive_cluster_relaxed(buf ? empty_remote1 : empty_remote0);
-                    ++uc;
+                    if (lane == 0) mb_arrive_cluster_relaxed(empty_remote0);
+                    ++ucA;
                 }
-                // unit 2: levels 0, 1 -> t = (a0 256 + a1) 2^24 + w, the one rounding to fp64, scale, store.  Every unordered pair of columns is
+                // unit 2 (region B): levels 0, 1 -> t = (a0 256 + a1) 2^24 + w, the one rounding to fp64, scale, store.  Every unordered pair of columns is
                 // scaled as (t * (scale sigma_lo 2^-23)) * (sigma_hi 2^-23), lo <= hi the column indices: what the two-kernel route computes once
                 // and mirrors -- both triangles are bit-identical to it.  A chunk of 8 columns lies right of, left of, or across the diagonal for
                 // the whole warp (rows row0 .. row0 + 31)
                 {
-                    const uint32_t buf = uc & 1u;
-                    i8::mb_wait(&tmem_full[buf], (uc >> 1) & 1u);
+                    const uint32_t buf = 1u;
+                    i8::mb_wait(&tmem_full[buf], ucB & 1u);
                     TL_STAMP(0, 1000 * ii + 10 * (h + 1) + 3);
                     i8::tc_fence_after();
                     const bool fast = vec_ok && row0 + 32 <= nn && gj0 + 64 <= nn;
@@ -644,7 +627,7 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                         if (c == 15) {   // the last read of this unit: hand the buffer back before the last conversions and stores
                             i8::tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mb_arrive_cluster_relaxed(buf ? empty_remote1 : empty_remote0);
+                            if (lane == 0) mb_arrive_cluster_relaxed(empty_remote1);
                         }
 #ifdef FZ_DEBUG
                         if (a.dbg & 4) continue;
@@ -680,7 +663,7 @@ __global__ void __launch_bounds__(fz::kThreads, 1) gram_i8_fused_kernel(const Gr
                         }
                     }
                     TL_STAMP(0, 1000 * ii + 10 * (h + 1) + 4);
-                    ++uc;
+                    ++ucB;
                 }
             }
         }
