@@ -209,9 +209,27 @@ typedef struct {
     int64_t variable;      /* MOI.ScalarAffineTerm.variable_index.value (1-based) */
 } pmb_vector_affine_term;
 /* Writes batch * nterms records to the DEVICE buffer `terms_dev` and (if non-NULL) batch * rows constants to `constants_dev`,
- * asynchronously on the context stream, from the Parameter values of the most recent pmb_update.  PMB_EUNSUPPORTED for sparse
- * blocks and for blocks whose rows do not all have the same term layout (vcat of different shapes). */
+ * asynchronously on the context stream, from the Parameter values of the most recent pmb_update.  Rows with different term layouts
+ * (a vcat of blocks of different shapes) go through a per-term gather table instead of the per-row template.  PMB_EUNSUPPORTED for
+ * sparse blocks (the reference would emit the structural zeros). */
 int pmb_block_export_terms(pmb_ctx* ctx, int32_t update_pos, pmb_vector_affine_term* terms_dev, double* constants_dev);
+
+/* The objective as the MOI function update!(::MOI.ScalarQuadraticFunction, f, varmap) fills (moi_interop.jl:45-62), in COMBINED form: the
+ * reference appends one ScalarQuadraticTerm per product (k n^2 of them for ||Ax - b||^2, duplicates left to the solver, coefficient x 2 when
+ * both variables coincide); the device holds the sum, so it writes one term per unordered pair of OPTIMIZER variables i <= j (row-outer:
+ * (1,1), (1,2), .., (1,N), (2,2), ..), coefficient = entry (i, j) of the symmetric MOI Hessian of 1/2 x'Qx -- the value MOI's
+ * duplicate-summing gives the reference's list -- plus one ScalarAffineTerm per variable and the constant.  quad_dev: batch * N (N + 1) / 2
+ * records (NULL: skip; error for an affine objective), aff_dev: batch * N records (NULL: skip), constant_dev: batch doubles (NULL: skip). */
+typedef struct {
+    double coefficient;    /* MOI.ScalarQuadraticTerm.coefficient */
+    int64_t variable_1;    /* .variable_index_1.value (1-based) */
+    int64_t variable_2;    /* .variable_index_2.value */
+} pmb_scalar_quadratic_term;
+typedef struct {
+    double coefficient;    /* MOI.ScalarAffineTerm.coefficient */
+    int64_t variable;      /* .variable_index.value (1-based) */
+} pmb_scalar_affine_term;
+int pmb_objective_export_terms(pmb_ctx* ctx, pmb_scalar_quadratic_term* quad_dev, pmb_scalar_affine_term* aff_dev, double* constant_dev);
 
 /* ---- solver-side ingest: the QP in the form an OSQP-style solver consumes ---------------------------
  *     minimize 1/2 x'Px + q'x + c0   subject to   l <= A x <= u
@@ -248,6 +266,10 @@ int pmb_host_alloc(pmb_ctx* ctx, size_t bytes, void** out);   /* cudaHostAlloc; 
 int pmb_host_free(pmb_ctx* ctx, void* p);
 int pmb_memcpy_d2h(pmb_ctx* ctx, void* host, const void* dev, size_t bytes);  /* async on the context stream */
 int pmb_memcpy_h2d(pmb_ctx* ctx, void* dev, const void* host, size_t bytes);  /* async on the context stream */
+/* scratch DEVICE memory on the context's device (the export calls write into caller-provided device buffers): cudaSetDevice(ctx device) +
+ * cudaMalloc, tracked by the context (freed by pmb_device_free or pmb_ctx_destroy) */
+int pmb_device_alloc(pmb_ctx* ctx, size_t bytes, void** out);
+int pmb_device_free(pmb_ctx* ctx, void* p);
 
 /* ---- result path: value.(model, x) / objectivevalue(model), model.jl:166-173 ----------------------------
  * The external solver hands back its primal solution in OPTIMIZER variable order (MOI.VariablePrimal per optimizer index).

@@ -1,20 +1,12 @@
-# ParametronB200.jl -- the Julia `ccall` shim a Parametron.jl maintainer would add to route `update!` through libpmb200.so.
+# libpmb.jl -- the thin `ccall` layer over libpmb200.so (include/parametron_b200.h).  One Julia function per C entry point; every signature
+# here is cross-checked against the tested Python ctypes binding (parametron.jl_b200/_capi.py) by tests/test_julia_binding.py.
 #
-# WRITTEN, NOT EXECUTED: neither this container nor the GPU box has Julia (SURVEY.md section 8c).  Every symbol bound here is
-# declared in include/parametron_b200.h and is exercised through the equivalent Python ctypes binding
-# (parametron.jl_b200/_capi.py), so signatures and argument order are the tested ones.
-#
-# Usage inside Parametron.jl (src/model.jl):
-#   Model(optimizer)                -> also `ctx = ParametronB200.Ctx()`
-#   Variable(m)                     -> `ParametronB200.add_variables!(m.ctx, 1)`                       (model.jl:49-53)
-#   Parameter(f, val, m)            -> `ParametronB200.register_parameter!(m.ctx, p, val)`             (parameter.jl:57)
-#   optimize_toplevel(expr)         -> emit the matching `ParametronB200.matvec/dot_/add/sub/mul/...`  (lazyexpression.jl:184-302)
-#   setobjective! / add_constraint  -> `set_objective!` / `add_constraint!`                            (model.jl:60-98)
-#   initialize!(m)                  -> `initialize!(m.ctx, varmap)`                                    (model.jl:117-122)
-#   update!(m)                      -> `update!(m.ctx)`                                                (model.jl:132-143)
-module ParametronB200
+# WRITTEN, NOT EXECUTED: neither this container nor the GPU box has Julia (SURVEY.md section 8c).
+module LibPMB
 
-const lib = joinpath(@__DIR__, "..", "parametron.jl_b200", "lib", "libpmb200.so")
+const lib = get(ENV, "PARAMETRON_B200_LIB", joinpath(@__DIR__, "..", "..", "..", "parametron.jl_b200", "lib", "libpmb200.so"))
+
+
 
 # status codes (include/parametron_b200.h)
 const PMB_OK, PMB_EINVAL, PMB_EDIM, PMB_EINITIALIZED, PMB_ENOTINIT, PMB_ECUDA, PMB_EUNSUPPORTED, PMB_ENOMEM = 0, -1, -2, -3, -4, -5, -6, -7
@@ -62,7 +54,7 @@ _shape(val) = ndims(val) == 0 ? (0, 0, 0) : ndims(val) == 1 ? (1, length(val), 0
 # the in-place update function of a Parameter, called exactly once per update! (parameter.jl:93-102)
 function _host_callback(val::Ptr{Float64}, rows::Int64, cols::Int64, batch::Int64, user::Ptr{Cvoid})::Cvoid
     p = unsafe_pointer_to_objref(user)
-    p.f(p.val[])
+    p()                                                            # evaluates f at most once per update! (dirty flag, parameter.jl:93-102); in-place: fills p.val[]
     nothing
 end
 
@@ -74,6 +66,21 @@ function register_parameter!(ctx::Ctx, p, val::Array{Float64})      # Parameter(
     push!(ctx.roots, p); push!(ctx.roots, val)
     check(ctx, ccall((:pmb_param_set_host_ptr, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Cvoid}, Any), ctx.ptr, node[], val, cb, p))
     node[]                                                          # Julia arrays are column-major: no re-layout
+end
+
+# scalar (number-valued) Parameter: out-of-place in the reference (parameter.jl:48,73); `holder` is the 1-element staging buffer the callback fills
+function _host_callback_scalar(val::Ptr{Float64}, rows::Int64, cols::Int64, batch::Int64, user::Ptr{Cvoid})::Cvoid
+    p = unsafe_pointer_to_objref(user)
+    unsafe_store!(val, Float64(p()))                               # p() evaluates the Parameter once (it was marked dirty by setdirty!)
+    nothing
+end
+function register_scalar_parameter!(ctx::Ctx, p, holder::Vector{Float64})
+    node = Ref{Int32}(0)
+    check(ctx, ccall((:pmb_param_create, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Cint, Ref{Int32}), ctx.ptr, 0, 0, 0, PARAM_HOST, node))
+    cb = @cfunction(_host_callback_scalar, Cvoid, (Ptr{Float64}, Int64, Int64, Int64, Ptr{Cvoid}))
+    push!(ctx.roots, p); push!(ctx.roots, holder)
+    check(ctx, ccall((:pmb_param_set_host_ptr, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Cvoid}, Any), ctx.ptr, node[], holder, cb, p))
+    node[]
 end
 
 function register_device_parameter!(ctx::Ctx, dptr::Ptr{Float64}, dims::Tuple)   # Parameter(model; val = CuArray), parameter.jl:88
@@ -175,4 +182,50 @@ end
 
 # With CUDA.jl a device-aware solver wraps the views without copies, e.g.
 #   v = objective_view(ctx); Q = unsafe_wrap(CuArray, CuPtr{Float64}(UInt(v.Q)), (v.nvars, v.nvars))
-end # module
+
+# ---- term-list export for unmodified MOI optimizers (moi_interop.jl:35-81) and scratch device memory ---------------------------------------
+function device_alloc(ctx::Ctx, bytes::Integer)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:pmb_device_alloc, lib), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx.ptr, bytes, out))
+    out[]
+end
+device_free(ctx::Ctx, p::Ptr{Cvoid}) = check(ctx, ccall((:pmb_device_free, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.ptr, p))
+memcpy_d2h(ctx::Ctx, host::Ptr{Cvoid}, dev::Ptr{Cvoid}, bytes::Integer) =
+    check(ctx, ccall((:pmb_memcpy_d2h, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx.ptr, host, dev, bytes))
+# 24-byte MOI.VectorAffineTerm records of block `update_pos` (row-outer / term-inner, optimizer indices) + its constants, to DEVICE buffers
+block_export_terms!(ctx::Ctx, update_pos::Integer, terms_dev::Ptr{Cvoid}, constants_dev::Ptr{Cvoid}) =
+    check(ctx, ccall((:pmb_block_export_terms, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}), ctx.ptr, update_pos, terms_dev, constants_dev))
+# the objective as MOI.ScalarQuadraticFunction records: N (N + 1) / 2 ScalarQuadraticTerm (24 B), N ScalarAffineTerm (16 B), the constant
+objective_export_terms!(ctx::Ctx, quad_dev::Ptr{Cvoid}, aff_dev::Ptr{Cvoid}, constant_dev::Ptr{Cvoid}) =
+    check(ctx, ccall((:pmb_objective_export_terms, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), ctx.ptr, quad_dev, aff_dev, constant_dev))
+function num_blocks(ctx::Ctx)
+    n = Ref{Int32}(0)
+    code = ccall((:pmb_num_blocks, lib), Cint, (Ptr{Cvoid}, Ref{Int32}), ctx.ptr, n)
+    check(ctx, code)
+    n[]
+end
+# instance-shard data parallelism: this context owns global instances [first, first + batch) (build phase)
+set_instance_offset!(ctx::Ctx, first::Integer) = check(ctx, ccall((:pmb_set_instance_offset, lib), Cint, (Ptr{Cvoid}, Int64), ctx.ptr, first))
+function convert_(ctx::Ctx, a::Int32)                                 # convert(Vector, x) -> copyto!, lazyexpression.jl:280-282
+    out = Ref{Int32}(0)
+    check(ctx, ccall((:pmb_op_convert, lib), Cint, (Ptr{Cvoid}, Int32, Ref{Int32}), ctx.ptr, a, out))
+    out[]
+end
+function const_affine(ctx::Ctx, coeffs::Vector{Float64}, vars::Vector{Int64}, constant::Float64)   # a constant AffineFunction, terms in reference order
+    out = Ref{Int32}(0)
+    check(ctx, ccall((:pmb_const_affine, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}, Cdouble, Ref{Int32}), ctx.ptr, length(coeffs), coeffs, vars, constant, out))
+    out[]
+end
+function const_quadratic(ctx::Ctx, qc::Vector{Float64}, rv::Vector{Int64}, cv::Vector{Int64}, lc::Vector{Float64}, lv::Vector{Int64}, constant::Float64)
+    out = Ref{Int32}(0)
+    check(ctx, ccall((:pmb_const_quadratic, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Int64}, Cdouble, Ref{Int32}),
+                     ctx.ptr, length(qc), qc, rv, cv, length(lc), lc, lv, constant, out))
+    out[]
+end
+function node_kind(ctx::Ctx, node::Int32)
+    kind = Ref{Int32}(0); rows = Ref{Int64}(0); cols = Ref{Int64}(0); isconst = Ref{Int32}(0)
+    check(ctx, ccall((:pmb_node_info, lib), Cint, (Ptr{Cvoid}, Int32, Ref{Int32}, Ref{Int64}, Ref{Int64}, Ref{Int32}), ctx.ptr, node, kind, rows, cols, isconst))
+    (kind[], rows[], cols[], isconst[] != 0)
+end
+
+end # module LibPMB

@@ -92,6 +92,7 @@ SIGNATURES = {
     "pmb_get_block": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(BlockView)]),
     "pmb_block_term_index": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmb_block_export_terms": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pmb_objective_export_terms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmb_enable_qp_pack": (C.c_int, [C.c_void_p]),
     "pmb_get_qp": (C.c_int, [C.c_void_p, C.POINTER(QpView)]),
     "pmb_qp_set_host_sink": (C.c_int, [C.c_void_p] * 7),
@@ -107,6 +108,8 @@ SIGNATURES = {
     "pmb_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_i64p]),
     "pmb_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "pmb_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pmb_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "pmb_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pmb_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "pmb_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
 }

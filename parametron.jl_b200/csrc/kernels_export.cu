@@ -5,6 +5,8 @@
 //   pack_constraints     -- all constraint blocks stacked into one CSC value array + row bounds from the set kinds
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "pmb_kernels.h"
 
 namespace pmb {
@@ -53,6 +55,74 @@ __global__ void __launch_bounds__(256) export_terms_kernel(ExportArgs a, int64_t
         __syncthreads();
     }
 }
+// generic term list (rows with different term layouts, e.g. a vcat of blocks of different shapes): one static gather entry per term
+__global__ void __launch_bounds__(256) export_terms_gather_kernel(const TermGatherDev* tab, int64_t nterms, const AffMatTermDev* mats, const AffUnitTermDev* units,
+                                                                  void* outv, int64_t batch) {
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        TermRec* out = reinterpret_cast<TermRec*>(outv) + inst * nterms;
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nterms; t += (int64_t)gridDim.x * blockDim.x) {
+            const TermGatherDev e = tab[t];
+            TermRec rec;
+            rec.row = e.row;
+            rec.var = e.var;
+            if (e.kind == 0) {
+                const AffMatTermDev m = mats[e.term];
+                rec.coeff = alpha_e(m.alpha, inst) * m.src[inst * m.src_bstride + e.src_off];
+            } else {
+                rec.coeff = alpha_e(units[e.term].alpha, inst);
+            }
+            out[t] = rec;
+        }
+    }
+}
+void launch_export_terms_gather(const TermGatherDev* tab, int64_t nterms, const AffMatTermDev* mats, const AffUnitTermDev* units, void* out, int64_t batch,
+                                cudaStream_t stream) {
+    if (nterms == 0) return;
+    dim3 grid((unsigned)std::min<int64_t>((nterms + 255) / 256, 4096), (unsigned)(batch < 65535 ? batch : 65535));
+    export_terms_gather_kernel<<<grid, 256, 0, stream>>>(tab, nterms, mats, units, out, batch);
+}
+
+// MOI.ScalarQuadraticFunction of the objective (moi_interop.jl:45-62) in combined form: one ScalarQuadraticTerm per unordered pair of
+// variables (i <= j, i outer), coefficient = the entry of the symmetric MOI Hessian (1/2 x'Qx: diagonal terms carry Q_ii, an off-diagonal
+// term carries Q_ij = Q_ji once), one ScalarAffineTerm per variable, the constant.  Records: {coefficient, variable_1, variable_2} 24 bytes,
+// {coefficient, variable} 16 bytes, 1-based optimizer indices.
+struct QuadRec { double coeff; int64_t v1; int64_t v2; };
+struct AffRec { double coeff; int64_t v; };
+__global__ void __launch_bounds__(256) export_objective_kernel(const double* Q, const double* q, int64_t N, int64_t q_bstride, int64_t qq_bstride, void* quadv,
+                                                               void* affv, int64_t batch) {
+    const int64_t npairs = N * (N + 1) / 2;
+    for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        if (Q && quadv) {
+            QuadRec* out = reinterpret_cast<QuadRec*>(quadv) + inst * npairs;
+            const double* Qi = Q + inst * q_bstride;
+            for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npairs; t += (int64_t)gridDim.x * blockDim.x) {
+                // row-outer enumeration of the upper triangle: row i holds N - i pairs, starting at i N - i (i - 1) / 2
+                int64_t i = (int64_t)((2.0 * N + 1.0 - sqrt((2.0 * N + 1.0) * (2.0 * N + 1.0) - 8.0 * (double)t)) * 0.5);
+                while (i > 0 && i * N - i * (i - 1) / 2 > t) --i;
+                while ((i + 1) * N - (i + 1) * i / 2 <= t) ++i;
+                const int64_t j = i + (t - (i * N - i * (i - 1) / 2));
+                QuadRec r;
+                r.coeff = Qi[i + j * N]; r.v1 = i + 1; r.v2 = j + 1;
+                out[t] = r;
+            }
+        }
+        if (affv) {
+            AffRec* out = reinterpret_cast<AffRec*>(affv) + inst * N;
+            for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < N; t += (int64_t)gridDim.x * blockDim.x) {
+                AffRec r;
+                r.coeff = q[inst * qq_bstride + t]; r.v = t + 1;
+                out[t] = r;
+            }
+        }
+    }
+}
+void launch_export_objective(const double* Q, const double* q, int64_t N, void* quad_out, void* aff_out, int64_t batch, cudaStream_t stream) {
+    if (N == 0) return;
+    const int64_t work = std::max<int64_t>(N * (N + 1) / 2, N);
+    dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 8192), (unsigned)(batch < 65535 ? batch : 65535));
+    export_objective_kernel<<<grid, 256, 0, stream>>>(Q, q, N, N * N, N, quad_out, aff_out, batch);
+}
+
 void launch_export_terms(const ExportArgs& a, int64_t batch, cudaStream_t stream) {
     if (a.rows == 0 || a.T == 0) return;
     dim3 grid((unsigned)((a.rows + 31) / 32), (unsigned)((a.T + 31) / 32), (unsigned)(batch < 65535 ? batch : 65535));

@@ -712,11 +712,13 @@ bool gram_i8_fused_applicable(const GramArgs& g, int64_t batch) {
     return true;
 }
 
-// predicted seconds: the pair spends ~3 us of hand-shakes + the slicing of 128 columns + 15 products x nh halves of (M 256, N 128, K 32)
-// instructions per instance; the fp64 kernel reaches ~19 TFLOP/s of SYRK-counted flops on small instances (profiles/r01_o_bench_all_configs)
+// predicted seconds, fitted to the measured timeline of a CTA pair (profiles/r02_e_fused_v6_timeline.txt, n = k = 256: 37 us per instance):
+// ~6 us of hand-shakes and TMEM drains that nothing hides, the slicing of the CTA's 128 columns at ~14 GB/s per SM, and the span of the 15
+// products x nh halves of (M 256, N 128, K 32) instructions, stretched 1.5x by the epilogue it waits for.  The fp64 kernel reaches ~19 TFLOP/s
+// of SYRK-counted flops on small instances (profiles/r02_a_gram_tma_cfg3_ncu_full.txt)
 bool gram_i8_fused_pays_off(int64_t k, int64_t n, int64_t batch, int sm_count) {
     if (const char* e = getenv("PMB_GRAM_I8_FUSED")) return atoi(e) != 0;
-    const double per = 3e-6 + (double)std::min<int64_t>(n, 128) * (double)k * 8.0 / 45e9 + (double)((k + 31) / 32) * 15.0 * (n > 64 ? 2.0 : 1.0) * 64.0 / 1.7e9;
+    const double per = 6e-6 + (double)std::min<int64_t>(n, 128) * (double)k * 8.0 / 14e9 + 1.5 * (double)((k + 31) / 32) * 15.0 * (n > 64 ? 2.0 : 1.0) * 64.0 / 1.9e9;
     const double t_fused = std::ceil((double)batch / (double)(sm_count / 2)) * per + 8e-6;
     const double t_f64 = (double)batch * k * n * (n + 1) / 19e12 + 6e-6;
     return t_fused < t_f64;

@@ -171,28 +171,12 @@ int pmb_block_export_terms(pmb_ctx* ctx, int32_t update_pos, pmb_vector_affine_t
     if (con.is_quad) fail(PMB_EUNSUPPORTED, "quadratic constraints have no affine term list");
     if (!f.order_exact) fail(PMB_EUNSUPPORTED, "the reference's term order of this block is not reproducible from the device lowering");
     if (!con.export_ready) {
-        // per-row template: every segment must cover all rows so that every row has the same layout
-        std::vector<TermEntryDev> tmpl;
-        std::vector<int64_t> unit_vars;
+        // per-row template when every segment covers all rows (every row has the same layout); otherwise one gather entry per term
+        bool uniform_rows = true;
         for (auto& seg : f.order) {
-            if (seg.is_unit) {
-                const UnitTerm& u = f.units[(size_t)seg.idx[0]];
-                if (u.row_off != 0 || u.rows != f.rows) fail(PMB_EUNSUPPORTED, "rows of this block have different term layouts");
-                TermEntryDev e{1, seg.idx[0], (int64_t)unit_vars.size(), 0};
-                for (int64_t r = 0; r < u.rows; ++r) unit_vars.push_back(ctx->varmap[(size_t)(u.vars[(size_t)r] - 1)]);
-                tmpl.push_back(e);
-            } else {
-                const MatTerm& m0 = f.mats[(size_t)seg.idx[0]];
-                if (m0.row_off != 0 || m0.rows != f.rows) fail(PMB_EUNSUPPORTED, "rows of this block have different term layouts");
-                for (int64_t j = 0; j < m0.cols; ++j)
-                    for (int mi : seg.idx) {
-                        const MatTerm& m = f.mats[(size_t)mi];
-                        tmpl.push_back(TermEntryDev{0, mi, m.src_col_off + j, ctx->varmap[(size_t)(m.vars[(size_t)j] - 1)]});
-                    }
-            }
+            if (seg.is_unit) { const UnitTerm& u = f.units[(size_t)seg.idx[0]]; uniform_rows = uniform_rows && u.row_off == 0 && u.rows == f.rows; }
+            else { const MatTerm& m0 = f.mats[(size_t)seg.idx[0]]; uniform_rows = uniform_rows && m0.row_off == 0 && m0.rows == f.rows; }
         }
-        if ((int64_t)tmpl.size() * f.rows != con.nterms) fail(PMB_EINVAL, "internal: template covers %lld terms, expected %lld",
-                                                              (long long)(tmpl.size() * f.rows), (long long)con.nterms);
         std::vector<AffMatTermDev> mats;
         for (auto& m : f.mats) {
             const Node& sn = ctx->nodes[(size_t)m.mat];
@@ -200,10 +184,65 @@ int pmb_block_export_terms(pmb_ctx* ctx, int32_t update_pos, pmb_vector_affine_t
         }
         std::vector<AffUnitTermDev> units;
         for (auto& u : f.units) units.push_back(AffUnitTermDev{alpha_dev(ctx, u.a)});
-        con.ex.tmpl = upload(ctx, tmpl); con.ex.T = (int32_t)tmpl.size();
-        con.ex.mats = upload(ctx, mats); con.ex.units = upload(ctx, units); con.ex.unit_vars = upload(ctx, unit_vars);
+        con.ex.mats = upload(ctx, mats); con.ex.units = upload(ctx, units);
         con.ex.rows = f.rows;
+        if (uniform_rows) {
+            std::vector<TermEntryDev> tmpl;
+            std::vector<int64_t> unit_vars;
+            for (auto& seg : f.order) {
+                if (seg.is_unit) {
+                    const UnitTerm& u = f.units[(size_t)seg.idx[0]];
+                    TermEntryDev e{1, seg.idx[0], (int64_t)unit_vars.size(), 0};
+                    for (int64_t r = 0; r < u.rows; ++r) unit_vars.push_back(ctx->varmap[(size_t)(u.vars[(size_t)r] - 1)]);
+                    tmpl.push_back(e);
+                } else {
+                    const MatTerm& m0 = f.mats[(size_t)seg.idx[0]];
+                    for (int64_t j = 0; j < m0.cols; ++j)
+                        for (int mi : seg.idx) {
+                            const MatTerm& m = f.mats[(size_t)mi];
+                            tmpl.push_back(TermEntryDev{0, mi, m.src_col_off + j, ctx->varmap[(size_t)(m.vars[(size_t)j] - 1)]});
+                        }
+                }
+            }
+            if ((int64_t)tmpl.size() * f.rows != con.nterms) fail(PMB_EINVAL, "internal: template covers %lld terms, expected %lld",
+                                                                  (long long)(tmpl.size() * f.rows), (long long)con.nterms);
+            con.ex.tmpl = upload(ctx, tmpl); con.ex.T = (int32_t)tmpl.size();
+            con.ex.unit_vars = upload(ctx, unit_vars);
+        } else {
+            // update!(::VectorAffineFunction): row-outer, term-inner, varmap applied (moi_interop.jl:64-81) -- the enumeration of pmb_block_term_index
+            std::vector<TermGatherDev> tab;
+            tab.reserve((size_t)con.nterms);
+            for (int64_t r = 0; r < f.rows; ++r)
+                for (auto& seg : f.order) {
+                    if (seg.is_unit) {
+                        const UnitTerm& u = f.units[(size_t)seg.idx[0]];
+                        const int64_t i = r - u.row_off;
+                        if (i < 0 || i >= u.rows) continue;
+                        tab.push_back(TermGatherDev{1, seg.idx[0], 0, r + 1, ctx->varmap[(size_t)(u.vars[(size_t)i] - 1)]});
+                    } else {
+                        const MatTerm& m0 = f.mats[(size_t)seg.idx[0]];
+                        const int64_t i = r - m0.row_off;
+                        if (i < 0 || i >= m0.rows) continue;
+                        for (int64_t j = 0; j < m0.cols; ++j)
+                            for (int mi : seg.idx) {
+                                const MatTerm& m = f.mats[(size_t)mi];
+                                const Node& sn = ctx->nodes[(size_t)m.mat];
+                                const int64_t ld = sn.kind == PMB_KIND_NUM_MATRIX ? sn.rows : 1;
+                                tab.push_back(TermGatherDev{0, mi, i + (m.src_col_off + j) * ld, r + 1, ctx->varmap[(size_t)(m.vars[(size_t)j] - 1)]});
+                            }
+                    }
+                }
+            if ((int64_t)tab.size() != con.nterms) fail(PMB_EINVAL, "internal: enumerated %lld terms, expected %lld", (long long)tab.size(), (long long)con.nterms);
+            con.ex_gather = upload(ctx, tab);
+        }
         con.export_ready = true;
+    }
+    if (con.ex_gather) {
+        launch_export_terms_gather(con.ex_gather, con.nterms, con.ex.mats, con.ex.units, terms_dev, ctx->batch, ctx->stream);
+        CK(cudaGetLastError());
+        if (constants_dev && con.rows > 0)
+            CK(cudaMemcpyAsync(constants_dev, con.d, (size_t)(ctx->batch * con.rows) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        return PMB_OK;
     }
     ExportArgs a = con.ex;
     a.out = terms_dev;
@@ -211,6 +250,19 @@ int pmb_block_export_terms(pmb_ctx* ctx, int32_t update_pos, pmb_vector_affine_t
     CK(cudaGetLastError());
     if (constants_dev && con.rows > 0)
         CK(cudaMemcpyAsync(constants_dev, con.d, (size_t)(ctx->batch * con.rows) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    API_END(ctx)
+}
+
+int pmb_objective_export_terms(pmb_ctx* ctx, pmb_scalar_quadratic_term* quad_dev, pmb_scalar_affine_term* aff_dev, double* constant_dev) {
+    API_BEGIN(ctx)
+    if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_objective_export_terms before pmb_initialize");
+    const int64_t N = ctx->nvars;
+    if (quad_dev && !(ctx->obj_kind == PMB_KIND_QUAD && ctx->Q)) fail(PMB_EINVAL, "the objective is affine: it has no quadratic terms");
+    if (N > 0 && (quad_dev || aff_dev)) {
+        launch_export_objective(quad_dev ? ctx->Q : nullptr, ctx->q, N, quad_dev, aff_dev, ctx->batch, ctx->stream);
+        CK(cudaGetLastError());
+    }
+    if (constant_dev && ctx->c0) CK(cudaMemcpyAsync(constant_dev, ctx->c0, (size_t)ctx->batch * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     API_END(ctx)
 }
 

@@ -187,6 +187,7 @@ struct Constraint {
     // term-list export (built lazily by pmb_block_export_terms)
     bool export_ready = false;
     ExportArgs ex{};
+    const TermGatherDev* ex_gather = nullptr;   // rows with different term layouts: one gather entry per term instead of the per-row template
     AffForm form;
 };
 

@@ -305,6 +305,17 @@ struct ExportArgs {
     void* out;                                    // batch * rows * T records of 24 bytes
 };
 void launch_export_terms(const ExportArgs& a, int64_t batch, cudaStream_t stream);
+struct TermGatherDev {     // one term of a block whose rows have different layouts (static, reference order)
+    int32_t kind;          // 0: matrix term, 1: unit term
+    int32_t term;          // index into mats / units
+    int64_t src_off;       // matrix: row + srccol * ld inside one instance of the source
+    int64_t row;           // 1-based output row
+    int64_t var;           // 1-based optimizer variable
+};
+void launch_export_terms_gather(const TermGatherDev* tab, int64_t nterms, const AffMatTermDev* mats, const AffUnitTermDev* units, void* out, int64_t batch,
+                                cudaStream_t stream);
+// objective as MOI.ScalarQuadraticFunction records (combined upper triangle, row-outer) + ScalarAffineTerm records
+void launch_export_objective(const double* Q, const double* q, int64_t N, void* quad_out, void* aff_out, int64_t batch, cudaStream_t stream);
 // P_x[j(j+1)/2 + i] = Q[i + j*N]  (i <= j)
 void launch_pack_upper(const double* Q, int64_t N, int64_t q_bstride, double* Px, int64_t px_bstride, int64_t batch, cudaStream_t stream);
 struct PackBlockDev {      // one constraint block inside the stacked CSC matrix

@@ -1145,6 +1145,9 @@ int pmb_update(pmb_ctx* ctx) {
     if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_update before pmb_initialize");
     // setdirty! + evaluate every Parameter exactly once (model.jl:133, parameter.jl:93-104)
     const bool graph_path = !ctx->timing && ctx->graph_exec;
+    // HOST Parameters are read from their (pinned) staging buffers by copies that run asynchronously: the previous update's copies must
+    // have consumed the buffers before the callbacks below overwrite them (the reference's update! is synchronous, model.jl:132-143)
+    if (ctx->memcpy_per_update > 0 && ctx->updates > 0) CK(cudaStreamSynchronize(ctx->stream));
     for (auto& n : ctx->nodes) {
         if (!n.needed || n.nop != NOP_PARAM || n.pmode != PMB_PARAM_HOST) continue;
         if (!n.hptr) fail(PMB_EINVAL, "host Parameter has no buffer (pmb_param_set_host_ptr)");
@@ -1486,6 +1489,34 @@ int pmb_host_free(pmb_ctx* ctx, void* p) {
     if (it == ctx->pinned.end()) fail(PMB_EINVAL, "pointer was not allocated by pmb_host_alloc");
     ctx->pinned.erase(it);
     if (p) CK(cudaFreeHost(p));
+    API_END(ctx)
+}
+
+int pmb_device_alloc(pmb_ctx* ctx, size_t bytes, void** out) {
+    API_BEGIN(ctx)
+    if (!out) fail(PMB_EINVAL, "null out");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    if (bytes > 0) {
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) fail(PMB_ENOMEM, "cudaMalloc of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+        ctx->allocs.push_back(p);
+        ctx->bytes_alloc += (int64_t)bytes;
+    }
+    *out = p;
+    API_END(ctx)
+}
+
+int pmb_device_free(pmb_ctx* ctx, void* p) {
+    API_BEGIN(ctx)
+    if (!p) return PMB_OK;
+    auto it = std::find(ctx->allocs.begin(), ctx->allocs.end(), p);
+    if (it == ctx->allocs.end()) fail(PMB_EINVAL, "pointer was not allocated by pmb_device_alloc");
+    ctx->allocs.erase(it);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(p));
     API_END(ctx)
 }
 

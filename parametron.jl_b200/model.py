@@ -24,14 +24,46 @@ Minimize, Maximize = K.MINIMIZE, K.MAXIMIZE  # Parametron.jl:50
 
 
 class Variable:
-    """src/functions.jl:96-98 -- an index into the model's variables (1-based)."""
-    __slots__ = ("index",)
+    """src/functions.jl:96-98 -- an index into the model's variables (1-based).  Arithmetic on a Variable that knows its model builds
+    expression nodes (`x + 2 * y >= 4`, test/model.jl:289): Variable -> AffineFunction with one unit term."""
+    __slots__ = ("index", "model")
 
-    def __init__(self, model_or_index):
+    def __init__(self, model_or_index, model=None):
         if isinstance(model_or_index, Model):
+            self.model = model_or_index
             self.index = model_or_index._add_variables(1)
         else:
             self.index = int(model_or_index)
+            self.model = model
+
+    def _expr(self):
+        if self.model is None:
+            raise TypeError("this Variable is not attached to a Model (use Variable(model) or model.variables(n))")
+        return self.model.expr(self)
+
+    def __add__(self, o):
+        return self._expr() + o
+
+    def __radd__(self, o):
+        return o + self._expr()
+
+    def __sub__(self, o):
+        return self._expr() - o
+
+    def __rsub__(self, o):
+        return o - self._expr()
+
+    def __mul__(self, o):
+        return self._expr() * o
+
+    def __rmul__(self, o):
+        return o * self._expr()
+
+    def __neg__(self):
+        return -self._expr()
+
+    def __pow__(self, o):
+        raise K.Unsupported(K.EUNSUPPORTED, "`^` has no device lowering: write x * x through a bilinear form (reference: lazyexpression.jl has no pow rule either)")
 
     def __repr__(self):
         return f"x{self.index}"
@@ -193,6 +225,12 @@ class Parameter(Expr):
             self.evaluations += 1
         self._store(self.val)
 
+    def _needed(self):
+        """reachable from the objective or a constraint?  (pmb_param_device_ptr is null for dead Parameters: the reference never evaluates them either)"""
+        if getattr(self, "_needed_cache", None) is None:
+            self._needed_cache = (not self.model.initialized) or bool(self.device_ptr)
+        return self._needed_cache
+
     # device-resident manual mode
     def upload(self, val):
         m = self.model
@@ -218,9 +256,6 @@ class Parameter(Expr):
             if len(self.shape) == 2:
                 out = np.transpose(out, (0, 2, 1))
         return out if m.batch > 1 else out[0]
-
-
-_rt = None
 
 
 class RecordParameter(Parameter):
@@ -264,24 +299,6 @@ class RecordParameter(Parameter):
         return self.field(name)
 
 
-def _cudart():
-    """libcudart (already loaded by libpmb200.so) for the two scratch allocations of export_block_terms"""
-    global _rt
-    if _rt is None:
-        import ctypes.util
-        for name in ("libcudart.so.12", "libcudart.so", ctypes.util.find_library("cudart")):
-            try:
-                _rt = C.CDLL(name)
-                break
-            except (OSError, TypeError):
-                continue
-        if _rt is None:
-            raise OSError("libcudart not found")
-        _rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
-        _rt.cudaFree.argtypes = [C.c_void_p]
-    return _rt
-
-
 def _flatten_vars(x):
     if isinstance(x, np.ndarray) and x.dtype == object:
         x = list(x.ravel())
@@ -315,6 +332,7 @@ class Model:
         self.nvars = 0
         self._pins = []
         self._varvec_cache = {}
+        self._has_host_params = None
 
     # -- plumbing
     def _ck(self, code):
@@ -353,6 +371,15 @@ class Model:
             self.synchronize()
         return out
 
+    def _dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self._lib.pmb_device_alloc(self._ctx, int(nbytes), C.byref(p)))
+        return p.value
+
+    def _dev_free(self, ptr):
+        if ptr:
+            self._ck(self._lib.pmb_device_free(self._ctx, C.c_void_p(ptr)))
+
     def synchronize(self):
         self._ck(self._lib.pmb_synchronize(self._ctx))
 
@@ -365,7 +392,7 @@ class Model:
     def variables(self, n):
         """[Variable(model) for _ = 1 : n]"""
         first = self._add_variables(n)
-        return [Variable(first + i) for i in range(n)]
+        return [Variable(first + i, model=self) for i in range(n)]
 
     def _as_node(self, x):
         """numbers / arrays -> constants (constant folding, lazyexpression.jl:189-192); Variable lists -> Vector{Variable}."""
@@ -421,6 +448,14 @@ class Model:
     def add_zero_constraint(self, e):
         return self._add(e, K.SET_ZERO)
 
+    def add_integer_constraint(self, x):
+        """model.jl:97: SingleVariable-in-Integer carries no updatable data and belongs to the external solver, which is out of scope"""
+        raise K.Unsupported(K.EUNSUPPORTED, "integer constraints are not lowered to the device (no coefficient data; declare them on the solver)")
+
+    def add_binary_constraint(self, x):
+        """model.jl:98"""
+        raise K.Unsupported(K.EUNSUPPORTED, "binary constraints are not lowered to the device (no coefficient data; declare them on the solver)")
+
     # -- model.jl:117-159
     def initialize(self, idxmap=None):
         """initialize!: `idxmap[i-1]` = optimizer index of model variable i (MOI.copy_to's index map); None = identity."""
@@ -432,7 +467,13 @@ class Model:
 
     def update(self):
         """update!: every Parameter evaluated exactly once, then ONE device pass re-assembles (Q, q, c0) and all (C_i, d_i)."""
+        if self._has_host_params is None:   # only Parameters the objective / a constraint reaches are evaluated (the reference evaluates lazily)
+            self._has_host_params = any(p.mode == K.PARAM_HOST for p in self.params)
+        if self._has_host_params and self.initialized:
+            self.synchronize()               # the previous update's H2D copies have consumed the pinned staging buffers rewritten below
         for p in self.params:
+            if p.mode == K.PARAM_HOST and not p._needed():
+                continue
             p._evaluate()
         self._ck(self._lib.pmb_update(self._ctx))
 
@@ -550,17 +591,41 @@ class Model:
         (records[batch?, nterms] of TERM_DTYPE, constants[batch?, rows])."""
         v = self.block_view(pos)
         b, nt, m = self.batch, v.nterms, v.rows
-        rt = _cudart()  # two scratch device buffers owned by the caller, as a Julia/MOI consumer would
-        dterms, dconst = C.c_void_p(), C.c_void_p()
-        assert rt.cudaMalloc(C.byref(dterms), max(b * nt * 24, 8)) == 0 and rt.cudaMalloc(C.byref(dconst), max(b * m * 8, 8)) == 0
+        dterms, dconst = self._dev_alloc(max(b * nt * 24, 8)), None   # two scratch device buffers owned by the caller, as a Julia/MOI consumer would
         try:
-            self._ck(self._lib.pmb_block_export_terms(self._ctx, pos, dterms, dconst))
-            recs = self._d2h(dterms.value, b * nt, self.TERM_DTYPE).reshape(b, nt)
-            consts = self._d2h(dconst.value, b * m).reshape(b, m)
+            dconst = self._dev_alloc(max(b * m * 8, 8))
+            self._ck(self._lib.pmb_block_export_terms(self._ctx, pos, C.c_void_p(dterms), C.c_void_p(dconst)))
+            recs = self._d2h(dterms, b * nt, self.TERM_DTYPE).reshape(b, nt)
+            consts = self._d2h(dconst, b * m).reshape(b, m)
         finally:
-            rt.cudaFree(dterms)
-            rt.cudaFree(dconst)
+            self._dev_free(dterms)
+            self._dev_free(dconst)
         return (recs[0], consts[0]) if b == 1 else (recs, consts)
+
+    QUAD_TERM_DTYPE = np.dtype([("coefficient", np.float64), ("variable_1", np.int64), ("variable_2", np.int64)])
+    AFF_TERM_DTYPE = np.dtype([("coefficient", np.float64), ("variable", np.int64)])
+
+    def export_objective_terms(self):
+        """The objective as MOI.ScalarQuadraticFunction records (moi_interop.jl:45-62, combined form): (quadratic_terms[batch?, N(N+1)/2] or None
+        for an affine objective, affine_terms[batch?, N], constant[batch?]) -- produced on the device from the last update."""
+        v = self.objective_view()
+        b, N = self.batch, v.nvars
+        npairs = N * (N + 1) // 2
+        dq = self._dev_alloc(max(b * npairs * 24, 8)) if v.Q else None
+        da = dc = None
+        try:
+            da = self._dev_alloc(max(b * N * 16, 8))
+            dc = self._dev_alloc(max(b * 8, 8))
+            self._ck(self._lib.pmb_objective_export_terms(self._ctx, C.c_void_p(dq) if dq else None, C.c_void_p(da), C.c_void_p(dc)))
+            quad = self._d2h(dq, b * npairs, self.QUAD_TERM_DTYPE).reshape(b, npairs) if dq else None
+            aff = self._d2h(da, b * N, self.AFF_TERM_DTYPE).reshape(b, N)
+            const = self._d2h(dc, b)
+        finally:
+            for p_ in (dq, da, dc):
+                self._dev_free(p_)
+        if b == 1:
+            return (quad[0] if quad is not None else None), aff[0], float(const[0])
+        return quad, aff, const
 
     def enable_qp_pack(self):
         self._ck(self._lib.pmb_enable_qp_pack(self._ctx))

@@ -200,3 +200,100 @@ def test_upload_compute_overlap_gated_gram(n, k):
         assert np.array_equal(sink["P_x"][0], Q.T[iu[1], iu[0]][np.lexsort((iu[0], iu[1]))]) or \
             np.array_equal(sink["P_x"][0], np.concatenate([Q[:j + 1, j] for j in range(n)]))
         assert np.array_equal(sink["A_x"][0], P["C"].val.T.ravel())
+
+
+def test_term_list_export_of_rows_with_different_layouts():
+    """A vcat of blocks of different shapes (test/lazyexpression.jl:188-245): rows 0..m-1 carry n matrix terms, the remaining rows one unit
+    term each -- no common per-row template, the export goes through the per-term gather table.  Order, indices and coefficients bit-exact
+    against the literal oracle's VectorAffineFunction (moi_interop.jl:64-81)."""
+    rng = np.random.default_rng(21)
+    n, m = 5, 3
+    hs = {"C": {"v": rng.random((m, n))}, "d": {"v": rng.random(m)}, "lb": {"v": rng.random(n)}, "s": {"v": 0.5}}
+    perm = [int(i) + 1 for i in rng.permutation(n)]
+
+    def build(s):
+        x = s.variables(n)
+        P = {k_: s.parameter(h) for k_, h in hs.items()}
+        top = s.sub(s.mul(P["C"], x), P["d"])                 # m rows, n terms each
+        bottom = s.sub(s.mul(P["s"], x), P["lb"])             # n rows, one term each
+        s.constraint(s.vcat(top, bottom), ">=", np.zeros(m + n))
+
+    o, d = OracleSide(), DeviceSide()
+    build(o); build(d)
+    o.model.initialize(idxmap={i + 1: perm[i] for i in range(n)})
+    d.model.initialize(idxmap=perm)
+    for step in range(2):
+        for h in hs.values():
+            h["v"] = rng.random(np.shape(h["v"])) if np.ndim(h["v"]) else float(rng.random())
+        oracle_outputs(o.model, n)
+        d.model.update()
+        f = _moi_vector_terms(o.model)[0]
+        recs, consts = d.model.export_block_terms(0)
+        assert len(recs) == m * n + n
+        assert [(int(r["output_index"]), float(r["coefficient"]), int(r["variable"])) for r in recs] == \
+               [(int(a), float(b), int(c)) for a, b, c in f.terms]
+        assert_close(consts, [float(z) for z in f.constants], 1e-10, "constants")
+
+
+@pytest.mark.parametrize("n,k", [(8, 8), (37, 20), (256, 96)])
+def test_objective_term_export_matches_the_reference_function(n, k):
+    """update!(::MOI.ScalarQuadraticFunction, f, varmap) (moi_interop.jl:45-62) appends one ScalarQuadraticTerm per product, coefficient x 2 when
+    both variables coincide, duplicates left to the solver; MOI reads them as 1/2 x'Qx with duplicates summed.  The device exports the SUM:
+    one term per unordered optimizer-variable pair (row-outer), the affine terms, the constant.  Checked: structure (indices) exactly, values
+    at 1e-10 against the literal oracle's term list summed the way MOI does, and the quadratic form itself at a random point."""
+    rng = np.random.default_rng(n + k)
+    hs = {"A": {"v": rng.random((k, n))}, "b": {"v": rng.random(k)}}
+    perm = [int(i) + 1 for i in rng.permutation(n)]
+
+    def build(s):
+        x = s.variables(n)
+        A, b = s.parameter(hs["A"]), s.parameter(hs["b"])
+        r = s.sub(s.mul(A, x), b)
+        s.objective("min", s.dot(r, r))
+
+    small = n <= 64
+    d = DeviceSide()
+    build(d)
+    d.model.initialize(idxmap=perm)
+    if small:
+        o = OracleSide()
+        build(o)
+        o.model.initialize(idxmap={i + 1: perm[i] for i in range(n)})
+    for step in range(2):
+        hs["A"]["v"] = rng.random((k, n)); hs["b"]["v"] = rng.random(k)
+        d.model.update()
+        quad, aff, const = d.model.export_objective_terms()
+        iu = np.triu_indices(n)
+        assert np.array_equal(quad["variable_1"], iu[0] + 1) and np.array_equal(quad["variable_2"], iu[1] + 1)   # row-outer upper triangle
+        assert np.array_equal(aff["variable"], np.arange(1, n + 1))
+        Q, q, c0 = d.model.objective_arrays()
+        assert np.array_equal(quad["coefficient"], Q[iu]) and np.array_equal(aff["coefficient"], q) and const == c0
+        if small:
+            obj, _, _ = oracle_outputs(o.model, n)       # the literal oracle's MOI function, densified with MOI's conventions
+            assert_close(Q, obj[0], 1e-10, "Q"); assert_close(q, obj[1], 1e-10, "q"); assert_close([c0], [obj[2]], 1e-10, "c0")
+        xs = rng.standard_normal(n)                      # the exported records ARE the function: evaluate them the way MOI does
+        val = const + float(aff["coefficient"] @ xs[aff["variable"] - 1])
+        v1, v2, cc = quad["variable_1"] - 1, quad["variable_2"] - 1, quad["coefficient"]
+        val += float(np.sum(np.where(v1 == v2, 0.5, 1.0) * cc * xs[v1] * xs[v2]))
+        pinv = np.argsort(np.asarray(perm) - 1)          # optimizer variable -> model variable
+        xm = xs[np.asarray(perm) - 1]                    # model-order point
+        ref = float(np.sum((hs["A"]["v"] @ xm - hs["b"]["v"]) ** 2))
+        assert abs(val - ref) <= 1e-10 * abs(ref)
+
+
+def test_objective_term_export_batched_and_affine_objective():
+    import parametron_b200 as pm
+    n, B = 12, 3
+    rng = np.random.default_rng(2)
+    model = pm.Model(batch=B)
+    x = model.variables(n)
+    c = pm.Parameter(model, shape=(n,), device=True)
+    pm.objective(model, pm.Minimize, pm.dot(c, x))
+    model.initialize()
+    cv = rng.random((B, n))
+    c.upload(cv)
+    model.update()
+    quad, aff, const = model.export_objective_terms()
+    assert quad is None and aff.shape == (B, n)
+    assert np.array_equal(aff["coefficient"], cv) and np.array_equal(aff["variable"], np.tile(np.arange(1, n + 1), (B, 1)))
+    assert not const.any()

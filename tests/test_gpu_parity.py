@@ -636,3 +636,36 @@ def test_convert_rule():
     assert any(np.array_equal(C_, Av) and np.array_equal(d_, np.zeros(3)) for C_, d_ in arrs)
     assert any(np.array_equal(C_, np.eye(3)) and np.array_equal(d_, -np.ones(3)) for C_, d_ in arrs)
     assert len(views) == 2
+
+
+def test_variable_arithmetic_builds_affine_rows():
+    """`x + 2y + 3z >= 4`, `x + y >= 1` written with operators on Variables (test/model.jl:288-290): each Variable lowers to an AffineFunction
+    with one unit term; unused Parameters are never evaluated (the reference evaluates Parameters lazily, parameter.jl:93-102)."""
+    import parametron_b200 as pm
+    model = pm.Model()
+    x, y, z = model.variables(3)
+    calls = {"used": 0, "unused": 0}
+
+    def f_used():
+        calls["used"] += 1
+        return 4.0
+
+    def f_unused():
+        calls["unused"] += 1
+        return np.ones(3)
+    rhs = pm.Parameter(model, f=f_used)
+    pm.Parameter(model, f=f_unused)        # declared, reached by nothing
+    pm.constraint(model, x + 2 * y + 3 * z, ">=", rhs)
+    pm.constraint(model, x + y, ">=", 1.0)
+    model.initialize()
+    base_used, base_unused = calls["used"], calls["unused"]
+    for _ in range(3):
+        model.update()
+    assert calls["used"] - base_used == 3 and calls["unused"] == base_unused
+    blocks = sorted((model.block_arrays(i) for i in range(2)), key=lambda cd: cd[1][0])
+    assert np.array_equal(blocks[0][0], [[1.0, 2.0, 3.0]]) and np.array_equal(blocks[0][1], [-4.0])
+    assert np.array_equal(blocks[1][0], [[1.0, 1.0, 0.0]]) and np.array_equal(blocks[1][1], [-1.0])
+    with pytest.raises(pm.Unsupported):
+        model.add_integer_constraint(x)
+    with pytest.raises(pm.Unsupported):
+        x ** 2
