@@ -435,7 +435,6 @@ def test_c_abi_host_callback_and_external_device_pointer():
     import ctypes as C
     import parametron_b200 as pm
     from parametron_b200 import _capi as K
-    from parametron_b200.model import _cudart
     n, k = 4, 3
     m = pm.Model()
     lib, ctx = m._lib, m._ctx
@@ -453,9 +452,7 @@ def test_c_abi_host_callback_and_external_device_pointer():
             val[i] = float(len(calls))
     m._ck(lib.pmb_param_set_host_ptr(ctx, A.value, C.c_void_p(hostA.ctypes.data), C.cast(cb, C.c_void_p), None))
     # device Parameter d living in a buffer this test owns
-    rt = _cudart()
-    dbuf = C.c_void_p()
-    assert rt.cudaMalloc(C.byref(dbuf), k * 8) == 0
+    dbuf = C.c_void_p(m._dev_alloc(k * 8))     # a device buffer this test owns (pmb_device_alloc: on the context's device)
     d = C.c_int32()
     m._ck(lib.pmb_param_create(ctx, 1, k, 0, K.PARAM_DEVICE, d))
     m._ck(lib.pmb_param_set_device_ptr(ctx, d.value, dbuf))
@@ -471,8 +468,7 @@ def test_c_abi_host_callback_and_external_device_pointer():
         Cb, db = m.block_arrays(0)
         assert len(calls) == step and calls[-1] == (k, n, 1)
         assert np.array_equal(Cb, np.full((k, n), float(step))) and np.array_equal(db, -dv)
-    m.close()
-    rt.cudaFree(dbuf)
+    m.close()                                          # frees the tracked scratch as well
 
 
 def test_quadratic_constraint_blocks():
