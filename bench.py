@@ -258,6 +258,16 @@ def main():
     import parametron_b200 as pm
 
     torch.cuda.set_device(local_rank)
+    pinned_cores = None
+    if world > 1:
+        # every rank streams 269 MB per e2e update through ONE host: give each rank its own slice of the cores NVML lists as affine to its GPU
+        # (first-touch places the pinned staging buffers on that NUMA node) -- tools/pcie_probe_multi.py measures the ceiling this leaves
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from pcie_probe_multi import pin_to_gpu_cores
+            pinned_cores = pin_to_gpu_cores(local_rank, world)
+        except Exception:
+            pinned_cores = None
     if world > 1:
         # NCCL prints its version banner on STDOUT when the communicator comes up (NCCL_DEBUG=VERSION in this image); the contract is
         # ONE JSON line on stdout, so file descriptor 1 points at stderr until the first collective has run
@@ -589,7 +599,8 @@ def main():
             "config": {"workload": "cfg2: n=4096, m=1024 dense A,b,C,d; min ||Ax-b||^2 s.t. Cx==d (README Example 1 shape); one instance per GPU",
                        "parameters": "U[0,1) Philox4x32-10 regenerated on device every update (inside the timed step)",
                        "l2": "inputs_exceed_L2 (A 134 MB + Q 134 MB + C 2x33.5 MB per step; fresh inputs every step)",
-                       "parallelism": f"instance-shard x{world}, no collective"},
+                       "parallelism": f"instance-shard x{world}, no collective",
+                       "host_pinning": (f"rank 0 pinned to cores {pinned_cores[0]}-{pinned_cores[-1]}" if pinned_cores else "none")},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(st["kernel_launches_per_update"]) * args.steps,

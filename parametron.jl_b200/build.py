@@ -16,6 +16,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
          "-Xptxas", "-v", "--use_fast_math=false"]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+# extra nvcc flags for diagnostic builds, e.g. PMB_NVCC_EXTRA=-DFZ_WATCHDOG (kernels_gram_i8_fused.cu: watchdog warp + milestone record); forces a rebuild
+EXTRA = os.environ.get("PMB_NVCC_EXTRA", "").split()
 
 
 def _stale(target, deps):
@@ -26,6 +28,7 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
+    force = force or bool(EXTRA)
     os.makedirs(OUT_DIR, exist_ok=True)
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     objs = []
@@ -34,7 +37,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [NVCC] + FLAGS + ["-c", s, "-o", o]
+            cmd = [NVCC] + FLAGS + EXTRA + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             with open(o + ".ptxas.log", "w") as f:
                 f.write(r.stderr)

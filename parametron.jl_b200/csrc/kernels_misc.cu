@@ -41,6 +41,30 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
     }
 }
 
+// two chains, rounds interleaved
+__device__ __forceinline__ void philox4x32_10x2(uint32_t (&c)[4], uint32_t (&e)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t gi0 = __umulhi(0xD2511F53u, e[0]), go0 = 0xD2511F53u * e[0];
+        const uint32_t gi1 = __umulhi(0xCD9E8D57u, e[2]), go1 = 0xCD9E8D57u * e[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        const uint32_t m0 = gi1 ^ e[1] ^ k0, m2 = gi0 ^ e[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        e[0] = m0; e[1] = go1; e[2] = m2; e[3] = go0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// (double)((hi:lo) >> 11), exactly, without the 64-bit integer conversion of the XU pipe: both words of the 53-bit integer become doubles
+// through the 2^52 mantissa trick, one fma joins them (the sum has at most 53 significant bits: no rounding)
+__device__ __forceinline__ double u53_to_f64(uint32_t hi, uint32_t lo) {
+    const uint32_t xh = hi >> 11, xl = (lo >> 11) | (hi << 21);
+    const double dh = __hiloint2double(0x43300000, (int)xh) - 4503599627370496.0;
+    const double dl = __hiloint2double(0x43300000, (int)xl) - 4503599627370496.0;
+    return fma(dh, 4294967296.0, dl);
+}
+
 // ---------------- fused prologue: every built-in Parameter generator + the zeroing of (q, c0) + the update tick -------------
 // One launch replaces  tick + one Philox launch per Parameter + a memset node  (launch latency dominates the small configs).
 // All blocks read the update counter, use counter + 1 as this update's id, and the block that finishes LAST (atomic ticket)
@@ -56,18 +80,30 @@ __global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int 
     if (job.kind == 0) {
         const int64_t pairs = (job.numel + 1) / 2;
         const bool vec_ok = (job.numel % 2 == 0) && (((uintptr_t)job.out & 15) == 0);
+        const uint32_t k0 = (uint32_t)job.seed, k1 = (uint32_t)(job.seed >> 32);
+        const double sc = job.scale * (1.0 / 9007199254740992.0);   // scale 2^-53: a power of two times scale, the product below rounds once like (x 2^-53) scale
+        const int64_t stride = (int64_t)job.nblocks * 512;   // a block covers 512 consecutive pairs per pass: two per thread, 256 apart
         for (int64_t inst = blockIdx.y; inst < batch; inst += gridDim.y) {
             double* o = job.out + inst * job.numel;
-            for (int64_t p = (int64_t)b * 256 + threadIdx.x; p < pairs; p += (int64_t)job.nblocks * 256) {
-                uint32_t c[4] = {(uint32_t)p, (uint32_t)((uint64_t)p >> 32), (uint32_t)(inst + inst_offset), upd};
-                philox4x32_10(c, (uint32_t)job.seed, (uint32_t)(job.seed >> 32));
-                double d0 = (double)((((uint64_t)c[1] << 32) | c[0]) >> 11) * (1.0 / 9007199254740992.0) * job.scale;
-                double d1 = (double)((((uint64_t)c[3] << 32) | c[2]) >> 11) * (1.0 / 9007199254740992.0) * job.scale;
+            const uint32_t ci = (uint32_t)(inst + inst_offset);
+            // two independent Philox chains per iteration: the ten dependent rounds of one hide behind the other
+            for (int64_t p = (int64_t)b * 512 + threadIdx.x; p < pairs; p += stride) {
+                const int64_t p2 = p + 256;
+                uint32_t c[4] = {(uint32_t)p, (uint32_t)((uint64_t)p >> 32), ci, upd};
+                uint32_t e[4] = {(uint32_t)p2, (uint32_t)((uint64_t)p2 >> 32), ci, upd};
+                philox4x32_10x2(c, e, k0, k1);
+                const double d0 = u53_to_f64(c[1], c[0]) * sc, d1 = u53_to_f64(c[3], c[2]) * sc;
+                const double d2 = u53_to_f64(e[1], e[0]) * sc, d3 = u53_to_f64(e[3], e[2]) * sc;
                 if (vec_ok) {
                     *reinterpret_cast<double2*>(o + 2 * p) = make_double2(d0, d1);
+                    if (p2 < pairs) *reinterpret_cast<double2*>(o + 2 * p2) = make_double2(d2, d3);
                 } else {
                     o[2 * p] = d0;
                     if (2 * p + 1 < job.numel) o[2 * p + 1] = d1;
+                    if (p2 < pairs) {
+                        o[2 * p2] = d2;
+                        if (2 * p2 + 1 < job.numel) o[2 * p2 + 1] = d3;
+                    }
                 }
             }
         }

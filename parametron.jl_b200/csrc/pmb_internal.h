@@ -276,6 +276,7 @@ struct pmb_ctx {
     // 5 / 6 = force that many digit planes on every SYRK step (experiments: no certificate, no fp64 fallback)
     int gram_mode = 1;
     double gram_tol = 9e-11;   // worst-case bound; the fp64 reference itself rounds at ~1e-13, so 9/10 of the 1e-10 budget is the certificate's
+    unsigned long long* fused_diag = nullptr;    // host-mapped: the fused int8 kernel records here which wait timed out (GramI8Scratch::diag)
     unsigned long long* gram_counts = nullptr;   // device: instances per level {5 planes, 6 planes, fp64} of the last counted update
     bool timing = false;
     std::vector<cudaEvent_t> ev;         // 2 per step

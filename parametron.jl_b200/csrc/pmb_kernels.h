@@ -198,7 +198,10 @@ struct GramI8Scratch {
     double tol;                  // certification tolerance (relative to max |H|)
     int32_t force_ns;            // experiments: 5 / 6 = run that many planes whatever the certificate says, 0 = adaptive
     int32_t fused;               // the fused small-instance kernel (kernels_gram_i8_fused.cu) runs instead of slice + Gram launches: no planes in HBM
+    unsigned long long* diag;    // host-mapped 8-word record the fused kernel fills when one of its waits times out (may be null)
 };
+// text for a non-empty diagnostic record of the fused kernel ("" when the record is empty)
+const char* gram_i8_fused_diag_text(const unsigned long long* diag, char* buf, size_t len);
 // memset(stats) + slice kernel (gram_i8_slice) and the two tcgen05 Gram launches, 5 and 6 planes, of which at most one does work per
 // instance (gram_i8_mma).  false: not applicable (the caller runs the fp64 kernel alone).
 // [col0, col1): column range of this launch (upload pipelining: one slice + one Gram launch per arrived chunk); col1 < 0 = all columns.

@@ -451,6 +451,10 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                 i8.stats = dalloc<unsigned long long>(c, nb * kGramI8StatsStride + 2 + 1024, true);
                 i8.tol = c->gram_tol;
                 i8.force_ns = c->gram_mode == 5 ? 5 : 0;
+                if (!c->fused_diag && cudaHostAlloc((void**)&c->fused_diag, 32 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess)
+                    { for (int w = 0; w < 32; ++w) c->fused_diag[w] = 0ull; c->pinned.push_back(c->fused_diag); }
+                (void)cudaGetLastError();
+                i8.diag = c->fused_diag;
                 i8.fused = 1;
                 ga.cert_stats = i8.stats; ga.cert_tol = i8.tol; ga.cert_force = i8.force_ns != 0; ga.cert_none = i8.stats + nb * kGramI8StatsStride;
                 fz.cert_stats = ga.cert_stats; fz.cert_tol = ga.cert_tol; fz.cert_force = ga.cert_force; fz.cert_none = ga.cert_none;
@@ -1198,7 +1202,11 @@ int pmb_update(pmb_ctx* ctx) {
 // verdict was final: when the verdict ended at fp64 (the in-stream fp64 launch has then recomputed Q and P_x on the device) the host copy is
 // refreshed here.  Every entry point that hands results to the host goes through this helper.
 static void sync_and_repair(pmb_ctx* ctx) {
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (cudaError_t e = cudaStreamSynchronize(ctx->stream); e != cudaSuccess) {
+        char buf[1024];
+        const char* why = gram_i8_fused_diag_text(ctx->fused_diag, buf, sizeof buf);   // a bounded wait of the fused kernel trapped: say which
+        fail(PMB_ECUDA, "cudaStreamSynchronize(ctx->stream) failed: %s%s%s", cudaGetErrorString(e), *why ? "; " : "", why);
+    }
     if (ctx->pipe8_live && ctx->repair_flag_host && *ctx->repair_flag_host) {
         *ctx->repair_flag_host = 0;
         if (ctx->sink_Px && ctx->qp_Px && ctx->qp_nnzP > 0) {

@@ -35,6 +35,7 @@ int main(int argc, char** argv) {
     ga.scale = pmb::AlphaDev{2.0, nullptr, 0}; ga.accumulate = 0;
     ga.gvec = dg; ga.g_bstride = k; ga.qout = dq; ga.q_bstride = n; ga.c0out = dc0; ga.qscale = pmb::AlphaDev{2.0, nullptr, 0}; ga.cscale = pmb::AlphaDev{1.0, nullptr, 0};
     pmb::GramI8Scratch sc{}; sc.stats = dstats; sc.tol = 9e-11; sc.force_ns = 0; sc.fused = 1;
+    unsigned long long* diag = nullptr; CKP(cudaHostAlloc(&diag, 256, cudaHostAllocMapped)); for (int i = 0; i < 32; ++i) diag[i] = 0; sc.diag = diag;
     cudaStream_t st; CKP(cudaStreamCreate(&st));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int r = 0; r < reps; ++r) {
@@ -47,7 +48,7 @@ int main(int argc, char** argv) {
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
         printf("  sync: %s, %.3f ms (%.1f us / instance-slot, %.0f GB/s of 16 B per element)\n", cudaGetErrorString(se), ms,
                1e3 * ms / std::ceil(batch / 74.0), 16.0 * batch * n * k / (ms * 1e6));
-        if (se != cudaSuccess) return 1;
+        if (se != cudaSuccess) { char buf[1024]; printf("%s\n", pmb::gram_i8_fused_diag_text(diag, buf, sizeof buf)); return 1; }
     }
     std::vector<double> H((size_t)(batch * n * n)), q((size_t)(batch * n)), c0((size_t)batch);
     std::vector<unsigned long long> stats((size_t)(batch * 16 + 2 + 1024));
