@@ -31,7 +31,7 @@ SEED = 1234
 METRIC = "QP re-parameterizations/sec (update!+coeff-assemble) at n=4096,m=1024"
 GRAM_DRAM_TRAFFIC_BYTES = 410174464 + 167363328    # ncu --set full, one launch of gram_tma_kernel<1,128> at cfg2
 AFFINE_BATCHED_DRAM_TRAFFIC_BYTES = 537068800 + 487929344   # ncu --set full, the 16-instance launch (profiles/r01_o_affine_tma_batched_ncu_full.txt)
-GRAM_I8_DRAM_TRAFFIC_BYTES = 277568000 + 116847616    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r01_o_gram_i8_ncu_full.txt)
+GRAM_I8_DRAM_TRAFFIC_BYTES = 274125824 + 115179520    # ncu --set full, one launch of gram_i8_kernel<5,96> at cfg2 (profiles/r02_g_i8_cfg2_ncu_full.txt; r01_o: 278 + 117 MB)
 AFFINE_DRAM_TRAFFIC_BYTES = 33626880 + 1335808       # ncu --set full, one launch of affine_assemble_tma<0> at cfg2 (profiles/r01_n_affine_tma_ncu_full.txt)
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200: profiles/r01_probe_dmma.txt (mma.sync f64, all SMs)
 
@@ -216,6 +216,10 @@ def run_reference(args, rank, world):
     steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     s = cpu_termlist_sample(rows=2, reps=steps)
+    try:
+        fit = cpu_termlist_cubic_fit()      # full runs (no sampling) at n = 64 .. 512 and their n^3 extrapolation: cross-check of the row-sampled figure
+    except Exception as e:                  # noqa: BLE001 -- the fit is a cross-check, never the reported value
+        fit = {"unavailable": str(e)}
     wall = time.perf_counter() - t0
     val = 1.0 / s["seconds_per_update"]
     sample = (f"objective: {s['rows_sampled']} of {K_ROWS} residual rows of vecdot!/MOI copy (per-row work identical, scaled linearly) + "
@@ -227,7 +231,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": "updates/s", "cores": 1, "kind": "port", "sample": sample,
                          "note": "the reference is single-threaded Julia and is absent from this image; oracle/termlist.c is its literal C "
                                  "restatement (24 B QuadraticTerm per (row,i,j): 1.65 TB per update at this shape, hence the row sample)",
-                         "detail": s, "wall_s": wall},
+                         "detail": s, "full_runs_cubic_fit": fit, "wall_s": wall},
         "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -369,12 +373,12 @@ def main():
         roofline = {"bound": "tensor", "kernel": f"gram_i8_kernel<{planes},{96 if planes == 5 else 80}> (Q = 2A'A as {nprod} exact int8 digit-plane products: "
                                                  "TMA ring + tcgen05.mma kind::i8, int32 accumulators in TMEM)",
                     "achieved": i8_tops, "peak": i8_peak, "unit": "TOP/s", "frac": i8_tops / i8_peak, "traffic": GRAM_I8_DRAM_TRAFFIC_BYTES,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_o_gram_i8_ncu_full.txt "
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r02_g_i8_cfg2_ncu_full.txt "
                                       "(algorithmic: 101 MB of digit planes read + 134 MB of Q written)",
                     "algorithmic_ops": int(nprod * syrk_flops), "avg_launch_ms": i8_ms,
                     "peak_source": f"2 x bf16_tflops (burst) of MEASURED_PEAKS.json ({peak_src}): the int8 dense rate of tcgen05 is twice the bf16 rate "
                                    "(4.5 vs 2.25 POP/s nominal); MEASURED_PEAKS.json has no int8 entry.  ncu's own counter for the same launch: "
-                                   "sm__ops_path_tensor_op_utcimma_src_int8 = 71-72 % of its peak (16384 ops/clk/SM at the 1.69 GHz the SMs hold under this load), profiles/r01_o_gram_i8_ncu_full.txt",
+                                   "sm__pipe_tensor_cycles_active = 85.7 % of active cycles (r01_o: 71-72 % before the whole-warp elect.sync issue), 341 us under ncu, profiles/r02_g_i8_cfg2_ncu_full.txt",
                     "library_int8_gemm_tops_measured": lib_i8, "frac_vs_library_int8_gemm": (i8_tops / lib_i8) if lib_i8 else None,
                     "library_int8_gemm_note": "torch._int_mm (cuBLASLt) 8192^3, best of 10, measured in this run after the timed region; "
                                               "tools/probe/int8_peak.py, profiles/r01_o_int8_library_peak.json",
@@ -464,7 +468,13 @@ def main():
             per["gram"] = {"kernel": "gram_i8_fused_kernel (one CTA pair per instance: slicing + 15 int8 digit-plane products on tcgen05 + epilogue, planes never leave the chip)",
                            "bound": "hbm", "avg_launch_us": us["gram_i8_tcgen05"], "algorithmic_bytes": gbytes, "achieved_gbs": gbytes / us["gram_i8_tcgen05"] / 1e3,
                            "frac": gbytes / us["gram_i8_tcgen05"] / 1e3 / peaks["hbm_gbs"],
-                           "fp64_equivalent_tflops": c3st["gram_algorithmic_flops"] * count / us["gram_i8_tcgen05"] / 1e6}
+                           "fp64_equivalent_tflops": c3st["gram_algorithmic_flops"] * count / us["gram_i8_tcgen05"] / 1e6,
+                           "traffic": int((4352197000 + 4362385000) * count / 8192),
+                           "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the 8192-instance launch, scaled to this rank's instances: "
+                                             "profiles/r02_g_fused_cfg3_ncu_full.txt (4.35 GB read + 4.36 GB written = 1.01x the algorithmic bytes)",
+                           "limiter": "not HBM (25-32 % of the measured copy rate) and not the tensor pipe (21.8 % active): the CTA pair alternates between slicing "
+                                      "(8 warps, ~38 k clocks per instance) and the 15 x 2 digit-plane products paced by the epilogue (~31 k clocks) because the 160 KB of "
+                                      "operand panels exist once per SM -- timeline profiles/r02_e_fused_v6_timeline.txt, ablation profiles/r02_b_fused_kernel_ablation.txt"}
         elif us.get("gram_dmma"):
             gt = c3st["gram_algorithmic_flops"] * count / us["gram_dmma"] / 1e6
             per["gram"] = {"kernel": "gram_tma_kernel<SYRK,64> (fp64 DMMA)", "bound": "tensor", "avg_launch_us": us["gram_dmma"], "achieved_tflops": gt,

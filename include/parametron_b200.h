@@ -255,10 +255,13 @@ int pmb_enable_qp_pack(pmb_ctx* ctx);             /* build phase: adds the pack 
 int pmb_get_qp(pmb_ctx* ctx, pmb_qp_view* out);   /* after pmb_initialize */
 /* After pmb_enable_qp_pack (before or after pmb_initialize -- the sizes come from pmb_get_qp): pinned HOST buffers (pmb_host_alloc; sizes batch * nnzP / n / 1 / nnzA / m / m doubles, any
  * may be NULL) that every pmb_update fills as part of the update graph: the constraint pieces (A_x, l, u) leave the device as soon
- * as the constraint chain is done, concurrently with the objective chain; (P_x, q, c0) follow it.  Valid after pmb_synchronize --
- * and only then: when the objective's operand is a pinned HOST Parameter on the int8 route, the update is a pipelined schedule (chunked
- * upload || per-chunk slice + Gram || streamed P_x download) without an fp64 launch; if the error certificate refuses the operand,
- * pmb_synchronize replays the update on the fp64 kernels before it returns (synchronising the stream yourself would miss that). */
+ * as the constraint chain is done, concurrently with the objective chain; (P_x, q, c0) follow it.  Device-resident results (Q, q, c0, the
+ * packed P_x on the device) are valid in stream order after every update.  The HOST sink is valid after pmb_synchronize (or any call that
+ * returns results to the host: pmb_value, pmb_objective_value, pmb_gram_level_counts): when the objective's operand is a pinned HOST
+ * Parameter on the int8 route, the update is a pipelined schedule (chunked upload || per-chunk slice + Gram || streamed P_x download) in which
+ * P_x leaves range by range BEFORE the error certificate's verdict is final; if the verdict ends at fp64, the in-stream fp64 launch recomputes
+ * Q and P_x on the device and those calls re-download P_x into the sink before they return (a bare cudaStreamSynchronize would leave the
+ * host copy of P_x -- and only that -- from the refused int8 attempt). */
 int pmb_qp_set_host_sink(pmb_ctx* ctx, double* P_x, double* q, double* c0, double* A_x, double* l, double* u);
 
 /* ---- host staging helpers (pinned memory + stream-ordered copies; the e2e path of bench.py and the ctypes tests) -- */

@@ -145,12 +145,18 @@ __device__ __forceinline__ void load4(const double* x, int64_t r0, int64_t k, bo
 // RING (T = 256, columns of at most 4096 rows, 16-byte aligned): the columns travel global -> shared memory as 1-D bulk copies
 // (cp.async.bulk on an mbarrier, SASS UBLKCP) three columns ahead of the arithmetic, so the HBM latency is off the dependent chain
 // load -> reduce -> digits -> store of a column.
-constexpr int kI8SliceRing = 3;
+#ifndef PMB_SLICE_RING
+#define PMB_SLICE_RING 3
+#endif
+#ifndef PMB_SLICE_CTAS
+#define PMB_SLICE_CTAS 2
+#endif
+constexpr int kI8SliceRing = PMB_SLICE_RING;
 // FULL (ring only): k == kp is a multiple of 1024 and the offset vector, if any, is 16-byte aligned -- every row of every cached iteration
 // that runs exists, so the bounds tests, masked loads and their reconvergence points (about a fifth of the instructions of this issue-bound
 // kernel) are compiled out
 template <int T, bool RING, bool FULL = false>
-__global__ void __launch_bounds__(256, 2) gram_i8_slice_kernel(const GramI8SliceArgs a) {
+__global__ void __launch_bounds__(256, PMB_SLICE_CTAS) gram_i8_slice_kernel(const GramI8SliceArgs a) {
     constexpr int NP = kGramI8Planes, G = 256 / T, CIT = 4;   // CIT cached iterations of 4 rows per thread
     static_assert(!RING || T == 256, "the ring feeds one column per CTA");
     static_assert(!FULL || RING, "the full-column fast path belongs to the ring kernel");
@@ -821,7 +827,7 @@ bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t ba
     const int64_t cols = batch * (col1 - col0);
     const bool aligned = g.ldx % 2 == 0 && (((uintptr_t)g.X) & 15) == 0 && g.x_bstride % 2 == 0;
     if (sc.plan.kp > 1024 && sc.plan.kp <= 4096 && aligned && !getenv("PMB_I8_NO_RING")) {   // bulk-copy ring, 2 CTAs per SM
-        const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * 2);
+        const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * PMB_SLICE_CTAS);
         const size_t smem = (size_t)kI8SliceRing * (size_t)((g.k + 1) / 2 * 2) * 8 + 64;
         const bool galigned = !g.gvec || ((((uintptr_t)g.gvec) & 15) == 0 && g.g_bstride % 2 == 0);
         if (sc.plan.kp == g.k && g.k % 1024 == 0 && galigned && !getenv("PMB_I8_SLICE_GENERIC")) gram_i8_slice_kernel<256, true, true><<<sgrid, 256, smem, stream>>>(s);

@@ -456,3 +456,28 @@ def test_cfg2_elementwise_error_report_both_routes(dist):
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/elementwise_error_cfg2_{dist}.json", "w") as f:
         json.dump(report, f, indent=1)
+
+
+@pytest.mark.timeout(180)
+def test_cfg3_back_to_back_updates_without_synchronisation():
+    """Regression for a class of bug a single update cannot show: 600 updates of the cfg3 graph (generators -> fused int8 Gram || affine
+    assembly) queued back to back with no host synchronisation in between -- a protocol error between the warps of the persistent fused kernel
+    that needs a particular interleaving with the concurrent affine branch shows up as a hang (bounded here by the test's time-out) or a launch
+    failure (a withdrawn rewrite of the kernel failed this within ~300 updates; tools/stress_cfg3.py is the long version).  After the last
+    update the outputs equal the oracle evaluated at that update counter: nothing stale, nothing skipped.  BASELINE.json configs[2] shape,
+    2048 instances."""
+    import parametron_b200 as pm
+    n, k, m, B, U = 256, 256, 64, 2048, 600
+    model, _ = _ls_model_shard(pm, n, k, m, B, 0)
+    for _ in range(U):
+        model.update()
+    model.synchronize()
+    assert model.gram_level_counts() == (B, 0, 0)
+    ov = model.objective_view()
+    for inst in (0, 777, B - 1):
+        Q = model._d2h(ov.Q + inst * n * n * 8, n * n).reshape(n, n).T
+        q = model._d2h(ov.q + inst * n * 8, n)
+        A, b, _, _ = oracle_inputs(n, k, m, inst, U)
+        Qo, qo, _ = D.least_squares_objective(A, b, np.arange(1, n + 1), n)
+        assert_close(Q, Qo, RTOL, f"Q[{inst}] after {U} updates"); assert_close(q, qo, RTOL, f"q[{inst}]")
+    model.close()
