@@ -70,8 +70,8 @@ __device__ __forceinline__ double u53_to_f64(uint32_t hi, uint32_t lo) {
 // All blocks read the update counter, use counter + 1 as this update's id, and the block that finishes LAST (atomic ticket)
 // publishes the incremented counter -- every other block has read it by then.
 __global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int njobs, int total_blocks, int64_t batch, int64_t inst_offset,
-                                                       unsigned long long* counter, unsigned int* ticket) {
-    const uint32_t upd = (uint32_t)(*counter + 1ULL);
+                                                       unsigned long long* counter, unsigned int* ticket, int tick) {
+    const uint32_t upd = (uint32_t)(*counter + (tick ? 1ULL : 0ULL));   // tick = 0: the update's first prologue launch has already published the id
     // which job does this block belong to?
     int j = 0;
     int b = blockIdx.x;
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int 
     } else if (blockIdx.y == 0) {  // zero job: numel covers all instances
         for (int64_t i = (int64_t)b * 256 + threadIdx.x; i < job.numel; i += (int64_t)job.nblocks * 256) job.out[i] = 0.0;
     }
+    if (!tick) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -121,12 +122,12 @@ __global__ void __launch_bounds__(256) prologue_kernel(const FillJob* jobs, int 
     }
 }
 void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, int64_t inst_offset, unsigned long long* counter,
-                     unsigned int* ticket, cudaStream_t stream) {
+                     unsigned int* ticket, int tick, cudaStream_t stream) {
     if (njobs == 0 || total_blocks == 0) return;
     // at most 64 instance rows: the per-job block counts were sized for min(batch, 64) rows, and the end-of-kernel ticket is one
     // atomic per block (hundreds of thousands of blocks would serialise on it)
     int64_t by = batch < 64 ? batch : 64;
-    prologue_kernel<<<dim3((unsigned)total_blocks, (unsigned)by), 256, 0, stream>>>(jobs_dev, njobs, total_blocks, batch, inst_offset, counter, ticket);
+    prologue_kernel<<<dim3((unsigned)total_blocks, (unsigned)by), 256, 0, stream>>>(jobs_dev, njobs, total_blocks, batch, inst_offset, counter, ticket, tick);
 }
 
 // ---------------- numeric prologue ---------------------------------------------------------------

@@ -152,7 +152,7 @@ struct Step {
     const double* s1 = nullptr; int64_t s1_bs = 0;
     AffBlockDev aff{};
     GramScratch gscratch{};
-    const FillJob* jobs = nullptr; int njobs = 0, job_blocks = 0;  // ST_PROLOGUE  // ST_GRAM / ST_GEMM: k-split plan, arrival counters and partial-tile workspace
+    const FillJob* jobs = nullptr; int njobs = 0, job_blocks = 0, tick = 1;  // ST_PROLOGUE (tick = 0: the constraint branch's generators, no update tick)  // ST_GRAM / ST_GEMM: k-split plan, arrival counters and partial-tile workspace
     GramArgs gram{};
     GramI8Scratch i8{};   // ST_GRAM: certified int8-slice path (slices == nullptr: fp64 only)
     bool pipe8 = false;   // this Gram's operand is uploaded in column chunks; slice + tcgen05 launches run per chunk (build_update_graph)
@@ -222,6 +222,7 @@ struct pmb_ctx {
     unsigned long long* d_counter = nullptr;
     unsigned int* d_ticket = nullptr;
     std::vector<pmb::FillJob> fill_jobs;
+    std::vector<int> fill_job_nodes;     // Parameter node of each fill job (-1: the zeroing job); decides the branch of the job (used_main)
     // two-branch update graph: objective chain on the context stream, constraint chain on an auxiliary stream
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork0 = nullptr, ev_fork1 = nullptr, ev_join = nullptr;

@@ -235,8 +235,10 @@ struct FillJob {
     int32_t kind;
     int32_t nblocks;   // blocks of 256 threads assigned to this job
 };
+// inst_offset: global id of local instance 0 (Philox key).  tick = 1: the update's first prologue launch (update id = counter + 1, published by
+// the last block); tick = 0: a later launch of the same update (update id = counter, nothing published)
 void launch_prologue(const FillJob* jobs_dev, int njobs, int total_blocks, int64_t batch, int64_t inst_offset, unsigned long long* counter,
-                     unsigned int* ticket, cudaStream_t stream);   // inst_offset: global id of local instance 0 (Philox key)
+                     unsigned int* ticket, int tick, cudaStream_t stream);
 // out[i] = cst[i] + sum_t alpha_t * src_t[off_t + i]
 struct LinCombTermDev { const double* src; int64_t src_bstride; int64_t src_off; AlphaDev alpha; };
 void launch_lincomb(double* out, int64_t out_bstride, int64_t n, const LinCombTermDev* terms, int nterms,

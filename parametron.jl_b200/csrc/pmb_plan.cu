@@ -71,7 +71,7 @@ static void plan_numeric(pmb_ctx* c, int id) {
             n.dptr = dalloc<double>(c, c->batch * n.numel, true);
             n.owned = true;
         }
-        if (n.pmode == PMB_PARAM_UNIFORM && n.numel > 0) c->fill_jobs.push_back(FillJob{n.dptr, n.numel, n.seed, n.scale, 0, 0});
+        if (n.pmode == PMB_PARAM_UNIFORM && n.numel > 0) { c->fill_jobs.push_back(FillJob{n.dptr, n.numel, n.seed, n.scale, 0, 0}); c->fill_job_nodes.push_back(id); }
         return;
     }
     n.dptr = dalloc<double>(c, nb * n.numel);
@@ -414,6 +414,7 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
         st.push_back(z);
     } else {
         c->fill_jobs.push_back(FillJob{qc, nb * (N + 1), 0, 0.0, 1, 0});  // zeroed by the fused prologue launch
+        c->fill_job_nodes.push_back(-1);
     }
     if (qf.aff.rows == 0) qf.aff.rows = 1;
     if (!qf.aff.mats.empty() || !qf.aff.units.empty() || !qf.aff.offs.empty() || !qf.aff.coff.empty())
@@ -684,7 +685,7 @@ static int count_refs(pmb_ctx* c, int id) {
 static void run_step(pmb_ctx* c, const Step& s) {
     cudaStream_t st = c->stream;
     switch (s.type) {
-        case ST_PROLOGUE: launch_prologue(s.jobs, s.njobs, s.job_blocks, s.batch, c->inst_offset, c->d_counter, c->d_ticket, st); break;
+        case ST_PROLOGUE: launch_prologue(s.jobs, s.njobs, s.job_blocks, s.batch, c->inst_offset, c->d_counter, c->d_ticket, s.tick, st); break;
         case ST_GEMV_DOT: launch_gemv_t_dot(s.gemv, s.dot, s.batch, st); break;
         case ST_PACK_P: launch_pack_upper(s.src, s.n, s.src_bstride, s.out, s.out_bstride, s.batch, st); break;
         case ST_PACK_A:
@@ -818,6 +819,7 @@ static void capture_update_graph(pmb_ctx* ctx, bool fallback, cudaGraph_t* graph
         if (pipe) CK(cudaMemsetAsync(ctx->pipe_gate, 0, sizeof(int32_t) * (size_t)ctx->pipe_chunks, main_s));
         CK(cudaEventRecord(ctx->ev_fork0, main_s));
         CK(cudaStreamWaitEvent(aux_s, ctx->ev_fork0, 0));
+        run_phase(4, aux_s);                                         // generators of constraint-only Parameters (when split off the prologue)
         h2d(false, aux_s);                                           // constraint-only Parameters travel on the aux branch
         if (pipe || pipe8) {
             // the Gram operand: column chunks on a dedicated copy stream -- queued behind the (small) constraint Parameters so that the
@@ -1116,21 +1118,37 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
         for (size_t i = 0; i < ctx->nodes.size(); ++i) ctx->nodes[i].needed = saved[i];
     }
     if (!ctx->fill_jobs.empty()) {
-        // one fused prologue launch: Philox fills of every built-in generator, zeroing of (q, c0), update tick
-        int total = 0;
-        const int64_t cap = (int64_t)ctx->sm_count * 16;
-        for (auto& j : ctx->fill_jobs) {
-            const int64_t items = j.kind == 0 ? (j.numel + 1) / 2 : j.numel;
-            int64_t nbk = (items + 255) / 256;
-            const int64_t lim = j.kind == 0 ? std::max<int64_t>(1, cap / std::max<int64_t>(1, std::min<int64_t>(ctx->batch, 64))) : 64;
-            j.nblocks = (int32_t)std::max<int64_t>(1, std::min(nbk, lim));
-            total += j.nblocks;
+        // fused prologue launch: Philox fills of every built-in generator, zeroing of (q, c0), update tick.  PMB_PROLOGUE_SPLIT=1 (experiment,
+        // measured r02: cfg3 5.894 -> 5.827 ms, cfg2 0.4719 -> 0.4747 ms -- the generator blocks do not fit next to the persistent Gram CTAs,
+        // so little overlaps; off by default) moves the generators of Parameters that only the constraint chain reads to a second launch at
+        // the head of the constraint branch when they are large (>= 8 MB per update)
+        std::vector<FillJob> main_jobs, aux_jobs;
+        int64_t aux_bytes = 0;
+        for (size_t j = 0; j < ctx->fill_jobs.size(); ++j) {
+            const int nd = j < ctx->fill_job_nodes.size() ? ctx->fill_job_nodes[j] : -1;
+            const bool aux = nd >= 0 && !ctx->nodes[(size_t)nd].used_main && getenv("PMB_PROLOGUE_SPLIT");
+            (aux ? aux_jobs : main_jobs).push_back(ctx->fill_jobs[j]);
+            if (aux) aux_bytes += ctx->fill_jobs[j].numel * ctx->batch * (int64_t)sizeof(double);
         }
-        Step s;
-        s.type = ST_PROLOGUE; s.cls = KC_PHILOX; s.batch = ctx->batch;
-        s.jobs = upload(ctx, ctx->fill_jobs); s.njobs = (int)ctx->fill_jobs.size(); s.job_blocks = total;
-        s.phase = 0;
-        ctx->steps.insert(ctx->steps.begin(), s);
+        if (aux_bytes < ((int64_t)8 << 20) || main_jobs.empty()) { main_jobs = ctx->fill_jobs; aux_jobs.clear(); }
+        auto make = [&](std::vector<FillJob>& jobs, int tick, int phase) {
+            int total = 0;
+            const int64_t cap = (int64_t)ctx->sm_count * 16;
+            for (auto& j : jobs) {
+                const int64_t items = j.kind == 0 ? (j.numel + 1) / 2 : j.numel;
+                int64_t nbk = (items + 255) / 256;
+                const int64_t lim = j.kind == 0 ? std::max<int64_t>(1, cap / std::max<int64_t>(1, std::min<int64_t>(ctx->batch, 64))) : 64;
+                j.nblocks = (int32_t)std::max<int64_t>(1, std::min(nbk, lim));
+                total += j.nblocks;
+            }
+            Step s;
+            s.type = ST_PROLOGUE; s.cls = KC_PHILOX; s.batch = ctx->batch;
+            s.jobs = upload(ctx, jobs); s.njobs = (int)jobs.size(); s.job_blocks = total; s.tick = tick;
+            s.phase = phase;
+            return s;
+        };
+        if (!aux_jobs.empty()) ctx->steps.insert(ctx->steps.begin(), make(aux_jobs, 0, 4));   // phase 4: head of the constraint branch
+        ctx->steps.insert(ctx->steps.begin(), make(main_jobs, 1, 0));
     }
     ctx->launches_per_update = 0;
     ctx->memcpy_per_update = 0;
