@@ -481,3 +481,26 @@ def test_cfg3_back_to_back_updates_without_synchronisation():
         Qo, qo, _ = D.least_squares_objective(A, b, np.arange(1, n + 1), n)
         assert_close(Q, Qo, RTOL, f"Q[{inst}] after {U} updates"); assert_close(q, qo, RTOL, f"q[{inst}]")
     model.close()
+
+
+def test_prologue_split_option_is_bit_identical(monkeypatch):
+    """PMB_PROLOGUE_SPLIT=1 moves the generators of constraint-only Parameters (here C: 8 MB, d) to a second prologue launch on the constraint
+    branch (update id taken from the already published counter instead of counter + 1): every Parameter and every output must equal the
+    single-launch schedule bit for bit, over several updates.  Ref: each Parameter is evaluated exactly once per update!, parameter.jl:93-104."""
+    import parametron_b200 as pm
+    n, k, m = 1024, 256, 1024
+    outs = []
+    for split in (False, True):
+        if split:
+            monkeypatch.setenv("PMB_PROLOGUE_SPLIT", "1")
+        model, _ = _ls_model_shard(pm, n, k, m, 1, 0)
+        for _ in range(3):
+            model.update()
+        launches = model.stats()["kernel_launches_per_update"]
+        outs.append((model.objective_arrays() + model.block_arrays(0), launches))
+        model.close()
+    assert outs[1][1] == outs[0][1] + 1          # the second prologue launch exists
+    for a, b_ in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(np.asarray(a), np.asarray(b_))
+    A, b, Cm, d = oracle_inputs(n, k, m, 0, 3)
+    assert np.array_equal(outs[1][0][3], Cm) and np.array_equal(outs[1][0][4], -d)
