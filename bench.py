@@ -385,8 +385,12 @@ def main():
                     "fp64_equivalent_tflops": syrk_flops / ((i8_ms + slice_ms) * 1e-3) / 1e12,
                     "fp64_equivalent_note": f"SYRK-counted fp64 flops / (slice {slice_ms:.3f} ms + tcgen05 {i8_ms:.3f} ms); the fp64 DMMA pipe peaks at "
                                             f"{FP64_DMMA_PEAK_TFLOPS} TFLOP/s (profiles/r01_probe_dmma.txt), the fp64 kernel reached 33 (profiles/r01_m_*)",
-                    "slice_kernel": {"avg_launch_ms": slice_ms, "algorithmic_bytes": 8 * K_ROWS * N_VARS + 6 * K_ROWS * N_VARS,
-                                     "achieved_gbs": (14 * K_ROWS * N_VARS) / (slice_ms * 1e-3) / 1e9 if slice_ms > 0 else None, "peak_gbs": peaks["hbm_gbs"]}}
+                    "slice_kernel": {"avg_launch_ms": slice_ms, "algorithmic_bytes": 6 * K_ROWS * N_VARS,
+                                     "achieved_gbs": (6 * K_ROWS * N_VARS) / (slice_ms * 1e-3) / 1e9 if slice_ms > 0 else None, "peak_gbs": peaks["hbm_gbs"],
+                                     "note": "since r02 the Philox fill of A runs INSIDE this pass (A is a UNIFORM Parameter nothing else reads): no 134 MB write by the "
+                                             "prologue, no 134 MB read here; the pass writes the six digit planes (100 MB) and is bound by Philox integer issue "
+                                             "(41 instructions per double) plus its own latency chain, not by HBM. PMB_NO_GEN_FUSE=1 restores the separate fill "
+                                             "(prologue 45 us + slice 63 us instead of 18 + 78 us)"}}
     else:
         gram_tflops = st["gram_algorithmic_flops"] / (gram_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gram_tma_kernel<SYRK,128> (Q = 2A'A: TMA ring + warp-specialised fp64 DMMA)", "achieved": gram_tflops,
@@ -607,7 +611,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg2: n=4096, m=1024 dense A,b,C,d; min ||Ax-b||^2 s.t. Cx==d (README Example 1 shape); one instance per GPU",
-                       "parameters": "U[0,1) Philox4x32-10 regenerated on device every update (inside the timed step)",
+                       "parameters": "U[0,1) Philox4x32-10 regenerated on device every update (inside the timed step); A, read only by the int8 slice pass, is generated inside that pass and not stored (materialised on demand by pmb_param_device_ptr; PMB_GEN_MATERIALIZE=1 stores it every update, PMB_NO_GEN_FUSE=1 restores the separate fill)",
                        "l2": "inputs_exceed_L2 (A 134 MB + Q 134 MB + C 2x33.5 MB per step; fresh inputs every step)",
                        "parallelism": f"instance-shard x{world}, no collective",
                        "host_pinning": (f"rank 0 pinned to cores {pinned_cores[0]}-{pinned_cores[-1]}" if pinned_cores else "none")},

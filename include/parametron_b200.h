@@ -114,7 +114,11 @@ int pmb_param_set_uniform(pmb_ctx* ctx, pmb_node p, uint64_t seed, double scale)
 /* stream-ordered host -> device copy of a whole Parameter value (batch * rows * max(cols,1) doubles); usable after
  * pmb_initialize for PMB_PARAM_DEVICE parameters whose buffer the library owns (no pmb_param_set_device_ptr call). */
 int pmb_param_upload(pmb_ctx* ctx, pmb_node p, const double* host_values);
-/* device address of the Parameter's current value (batch-major: instance stride = rows*max(cols,1)) */
+/* device address of the Parameter's current value (batch-major: instance stride = rows*max(cols,1)); valid in stream order on the context
+ * stream.  A PMB_PARAM_UNIFORM matrix whose only reader is the int8 slice pass of the objective is generated INSIDE that pass and not written
+ * to memory by pmb_update (its values are a pure function of seed, global instance id and update counter); this call materialises the values of
+ * the LAST update into the buffer before it returns the address -- call it again after later updates instead of keeping the pointer
+ * (PMB_GEN_MATERIALIZE=1 in the environment makes every update write the buffer, as for all other Parameters). */
 int pmb_param_device_ptr(pmb_ctx* ctx, pmb_node p, double** dptr);
 
 /* constants folded at build time (ref: optimize_toplevel constant folding, lazyexpression.jl:189-192) */

@@ -34,6 +34,7 @@
 
 #include "pmb_kernels.h"
 #include "pmb_i8_ptx.h"
+#include "pmb_philox.h"
 
 namespace pmb {
 
@@ -123,6 +124,9 @@ struct GramI8SliceArgs {
     double* c0out;
     const int32_t* map;
     AlphaDev qscale, cscale;
+    // GEN: X is a UNIFORM Parameter nobody else reads -- its Philox fill runs HERE instead of in the prologue launch (same bits: pmb_philox.h); the
+    // values are still written to X (the Parameter stays readable), but never read back
+    uint64_t gen_seed; double gen_sc53; const unsigned long long* gen_counter; int64_t gen_inst_offset; int32_t gen_writeback;
 };
 
 // max of two doubles as one compare + select (fmax() expands to 8 instructions for its NaN rules: DSETP.MAX, FSEL, SEL, a predicated
@@ -155,11 +159,12 @@ constexpr int kI8SliceRing = PMB_SLICE_RING;
 // FULL (ring only): k == kp is a multiple of 1024 and the offset vector, if any, is 16-byte aligned -- every row of every cached iteration
 // that runs exists, so the bounds tests, masked loads and their reconvergence points (about a fifth of the instructions of this issue-bound
 // kernel) are compiled out
-template <int T, bool RING, bool FULL = false>
+template <int T, bool RING, bool FULL = false, bool GEN = false>
 __global__ void __launch_bounds__(256, PMB_SLICE_CTAS) gram_i8_slice_kernel(const GramI8SliceArgs a) {
     constexpr int NP = kGramI8Planes, G = 256 / T, CIT = 4;   // CIT cached iterations of 4 rows per thread
     static_assert(!RING || T == 256, "the ring feeds one column per CTA");
-    static_assert(!FULL || RING, "the full-column fast path belongs to the ring kernel");
+    static_assert(!FULL || RING || GEN, "the full-column fast path belongs to the ring and generator kernels");
+    static_assert(!GEN || (T == 256 && FULL && !RING), "the generator-fused pass is the full-column, one-column-per-CTA variant without the ring");
     extern __shared__ __align__(128) unsigned char slice_smem[];
     __shared__ __align__(8) uint64_t ring_full[kI8SliceRing];
     __shared__ double red[8][5];
@@ -182,6 +187,7 @@ __global__ void __launch_bounds__(256, PMB_SLICE_CTAS) gram_i8_slice_kernel(cons
         __syncthreads();
     }
     uint32_t ring_it = 0;
+    const uint32_t gen_upd = GEN ? (uint32_t)*a.gen_counter : 0u;   // the prologue launch of this update has already published the update id
     // per-group running statistics (thread tig == 0 only)
     int64_t acc_inst = 0;
     unsigned long long acc_n = 0;
@@ -266,7 +272,15 @@ __global__ void __launch_bounds__(256, PMB_SLICE_CTAS) gram_i8_slice_kernel(cons
                 for (int it = 0; it < CIT; ++it) {
                     const int64_t r0 = ((int64_t)it * T + tig) * 4;
                     if (FULL ? it < nit : r0 < a.k) {
-                        if (RING) {
+                        if (GEN) {
+                            // rows r0 .. r0 + 3 of column j: elements j k + r0 .. of the instance's buffer = pairs p, p + 1 (k is even)
+                            const uint64_t p0 = ((uint64_t)j * (uint64_t)a.k + (uint64_t)r0) >> 1;
+                            philox_uniform_pairs2(p0, p0 + 1, (uint32_t)(inst + a.gen_inst_offset), gen_upd, a.gen_seed, a.gen_sc53, vc[it]);
+                            if (a.gen_writeback) {
+                                double2* o = reinterpret_cast<double2*>(const_cast<double*>(x) + r0);
+                                o[0] = make_double2(vc[it][0], vc[it][1]); o[1] = make_double2(vc[it][2], vc[it][3]);
+                            }
+                        } else if (RING) {
                             const double2 p = *(const double2*)(xs + r0), q = *(const double2*)(xs + r0 + 2);   // r0 + 3 < kpe + 2 <= slot + pad
                             vc[it][0] = p.x; vc[it][2] = q.x;
                             if (k4) { vc[it][1] = p.y; vc[it][3] = q.y; }
@@ -812,6 +826,13 @@ void configure_gram_i8_kernels() {
     cudaFuncSetAttribute(gram_i8_slice_kernel<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SliceRing * 4096 * 8 + 64);
 }
 
+// the generator-fused slice pass handles whole, densely stored columns of 1024 .. 4096 rows (the full-column fast path of the slice kernel)
+bool gram_i8_slice_can_generate(const GramArgs& g, const GramI8Plan& plan) {
+    const bool aligned = g.ldx % 2 == 0 && (((uintptr_t)g.X) & 15) == 0 && g.x_bstride % 2 == 0;
+    const bool galigned = !g.gvec || ((((uintptr_t)g.gvec) & 15) == 0 && g.g_bstride % 2 == 0);
+    return plan.ok && plan.kp == g.k && g.k % 1024 == 0 && g.k >= 1024 && g.k <= 4096 && g.ldx == g.k && aligned && galigned && !g.gate && !g.packed_host;
+}
+
 bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0, int64_t col1) {
     if (!sc.plan.ok || !sc.slices || g.packed_host || g.gate) return false;
     if (col1 < 0) col1 = g.n;
@@ -826,6 +847,13 @@ bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t ba
     }
     const int64_t cols = batch * (col1 - col0);
     const bool aligned = g.ldx % 2 == 0 && (((uintptr_t)g.X) & 15) == 0 && g.x_bstride % 2 == 0;
+    if (sc.gen_counter) {   // generator-fused pass: the planner removed the operand's fill from the prologue, so this path MUST run
+        if (!gram_i8_slice_can_generate(g, sc.plan) || col0 != 0 || col1 != g.n) return false;
+        s.gen_seed = sc.gen_seed; s.gen_sc53 = sc.gen_scale * (1.0 / 9007199254740992.0); s.gen_counter = sc.gen_counter; s.gen_inst_offset = sc.gen_inst_offset; s.gen_writeback = sc.gen_writeback;
+        const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * PMB_SLICE_CTAS);
+        gram_i8_slice_kernel<256, false, true, true><<<sgrid, 256, 0, stream>>>(s);
+        return true;
+    }
     if (sc.plan.kp > 1024 && sc.plan.kp <= 4096 && aligned && !getenv("PMB_I8_NO_RING")) {   // bulk-copy ring, 2 CTAs per SM
         const int sgrid = (int)std::min<int64_t>(cols, (int64_t)sm_count * PMB_SLICE_CTAS);
         const size_t smem = (size_t)kI8SliceRing * (size_t)((g.k + 1) / 2 * 2) * 8 + 64;

@@ -1,6 +1,7 @@
 // Small kernels around the two hot kernels: Parameter generators, numeric prologue ops, reductions for the affine
 // offsets / linear objective part (warp-shuffle), scatter of the rarely used quadratic shapes.
 #include "pmb_kernels.h"
+#include "pmb_philox.h"
 
 namespace pmb {
 
@@ -27,42 +28,6 @@ __device__ __forceinline__ double block_sum_256(double v) {
     }
     __syncthreads();
     return r;
-}
-
-// ---------------- Philox4x32-10 ----------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-}
-
-// two chains, rounds interleaved
-__device__ __forceinline__ void philox4x32_10x2(uint32_t (&c)[4], uint32_t (&e)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        const uint32_t gi0 = __umulhi(0xD2511F53u, e[0]), go0 = 0xD2511F53u * e[0];
-        const uint32_t gi1 = __umulhi(0xCD9E8D57u, e[2]), go1 = 0xCD9E8D57u * e[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-        const uint32_t m0 = gi1 ^ e[1] ^ k0, m2 = gi0 ^ e[3] ^ k1;
-        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-        e[0] = m0; e[1] = go1; e[2] = m2; e[3] = go0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-}
-// (double)((hi:lo) >> 11), exactly, without the 64-bit integer conversion of the XU pipe: both words of the 53-bit integer become doubles
-// through the 2^52 mantissa trick, one fma joins them (the sum has at most 53 significant bits: no rounding)
-__device__ __forceinline__ double u53_to_f64(uint32_t hi, uint32_t lo) {
-    const uint32_t xh = hi >> 11, xl = (lo >> 11) | (hi << 21);
-    const double dh = __hiloint2double(0x43300000, (int)xh) - 4503599627370496.0;
-    const double dl = __hiloint2double(0x43300000, (int)xl) - 4503599627370496.0;
-    return fma(dh, 4294967296.0, dl);
 }
 
 // ---------------- fused prologue: every built-in Parameter generator + the zeroing of (q, c0) + the update tick -------------

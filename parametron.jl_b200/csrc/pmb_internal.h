@@ -120,6 +120,8 @@ struct Node {
     double* dptr = nullptr;
     int64_t numel = 0, bstride = 0;
     bool owned = false, needed = false;
+    const pmb::FillJob* lazy_fill = nullptr;   // UNIFORM Parameter generated inside the int8 slice pass and not written by updates: the one-job list pmb_param_device_ptr runs
+    int lazy_fill_blocks = 0;
     bool used_main = false;   // read by a numeric node or the objective chain (else: constraint chain only)
     // symbolic nodes
     std::vector<int64_t> vars;

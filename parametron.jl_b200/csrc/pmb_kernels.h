@@ -199,6 +199,10 @@ struct GramI8Scratch {
     int32_t force_ns;            // experiments: 5 / 6 = run that many planes whatever the certificate says, 0 = adaptive
     int32_t fused;               // the fused small-instance kernel (kernels_gram_i8_fused.cu) runs instead of slice + Gram launches: no planes in HBM
     unsigned long long* diag;    // host-mapped 8-word record the fused kernel fills when one of its waits times out (may be null)
+    // generator-fused slice pass: the Gram operand is a UNIFORM Parameter only this step reads; its Philox fill moves from the prologue launch
+    // into the slice kernel (gen_counter = the context's update counter, already ticked by the prologue; null: off)
+    const unsigned long long* gen_counter; uint64_t gen_seed; double gen_scale; int64_t gen_inst_offset;
+    int32_t gen_writeback;       // 1: the pass also writes the generated values to the Parameter's buffer; 0: the buffer is filled on demand (pmb_param_device_ptr)
 };
 // text for a non-empty diagnostic record of the fused kernel ("" when the record is empty)
 const char* gram_i8_fused_diag_text(const unsigned long long* diag, char* buf, size_t len);
@@ -206,6 +210,7 @@ const char* gram_i8_fused_diag_text(const unsigned long long* diag, char* buf, s
 // instance (gram_i8_mma).  false: not applicable (the caller runs the fp64 kernel alone).
 // [col0, col1): column range of this launch (upload pipelining: one slice + one Gram launch per arrived chunk); col1 < 0 = all columns.
 // The Gram launch of a range computes the tile columns whose last column lies in the range.
+bool gram_i8_slice_can_generate(const GramArgs& g, const GramI8Plan& plan);   // GramI8Scratch::gen_counter may be set for this operand
 bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0 = 0,
                           int64_t col1 = -1);
 bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0 = 0,

@@ -470,6 +470,29 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                     i8.tol = c->gram_tol;
                     i8.force_ns = c->gram_mode >= 5 ? c->gram_mode : 0;
                     ga.cert_stats = i8.stats; ga.cert_tol = i8.tol; ga.cert_force = i8.force_ns != 0;
+                    // generator fusion: the operand is a UNIFORM Parameter nothing else reads -> its Philox fill moves from the prologue launch into
+                    // the slice pass (same bits; the values are still written to the Parameter's buffer, but the slice pass no longer reads them back)
+                    if (F.whole_node >= 0 && !getenv("PMB_NO_GEN_FUSE")) {
+                        const Node& pn = c->nodes[(size_t)F.whole_node];
+                        GramArgs probe = ga; probe.gvec = F.g;  probe.g_bstride = F.gbs;
+                        if (pn.nop == NOP_PARAM && pn.pmode == PMB_PARAM_UNIFORM && pn.owned && F.k == pn.rows && F.ncols == pn.cols && F.xbs == pn.numel &&
+                            count_refs(c, F.whole_node) == 1 && gram_i8_slice_can_generate(probe, i8.plan)) {
+                            for (size_t j = 0; j < c->fill_jobs.size() && j < c->fill_job_nodes.size(); ++j)
+                                if (c->fill_job_nodes[j] == F.whole_node) {
+                                    FillJob lazy = c->fill_jobs[j];
+                                    c->fill_jobs.erase(c->fill_jobs.begin() + (long)j); c->fill_job_nodes.erase(c->fill_job_nodes.begin() + (long)j);
+                                    i8.gen_counter = c->d_counter; i8.gen_seed = pn.seed; i8.gen_scale = pn.scale; i8.gen_inst_offset = c->inst_offset;
+                                    i8.gen_writeback = getenv("PMB_GEN_MATERIALIZE") ? 1 : 0;
+                                    if (!i8.gen_writeback) {   // the buffer is filled on demand: keep the job as a one-element list for pmb_param_device_ptr
+                                        const int64_t cap = (int64_t)c->sm_count * 16;
+                                        lazy.nblocks = (int32_t)std::max<int64_t>(1, std::min<int64_t>(((lazy.numel + 1) / 2 + 255) / 256, std::max<int64_t>(1, cap / std::max<int64_t>(1, std::min<int64_t>(nb, 64)))));
+                                        Node& wn = c->nodes[(size_t)F.whole_node];
+                                        wn.lazy_fill = upload(c, std::vector<FillJob>{lazy}); wn.lazy_fill_blocks = lazy.nblocks;
+                                    }
+                                    break;
+                                }
+                        }
+                    }
                 }
             }
             // upload/compute overlap: the operand is a pinned HOST Parameter nothing else reads -> gate the kernel on chunk arrival
@@ -1261,6 +1284,8 @@ int pmb_param_device_ptr(pmb_ctx* ctx, pmb_node p, double** dptr) {
     if (!ctx->initialized) fail(PMB_ENOTINIT, "pmb_param_device_ptr before pmb_initialize");
     Node& n = node_at(ctx, p);
     if (n.nop != NOP_PARAM || !dptr) fail(PMB_EINVAL, "node %d is not a Parameter", p);
+    if (n.lazy_fill && ctx->updates > 0)   // generated inside the slice pass, never written by updates: materialise the last update's values now (same bits)
+        launch_prologue(n.lazy_fill, 1, n.lazy_fill_blocks, ctx->batch, ctx->inst_offset, ctx->d_counter, ctx->d_ticket, 0, ctx->stream);
     *dptr = n.dptr;  // null when the Parameter is not reachable from the objective or a constraint
     API_END(ctx)
 }

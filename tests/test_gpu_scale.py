@@ -504,3 +504,43 @@ def test_prologue_split_option_is_bit_identical(monkeypatch):
         assert np.array_equal(np.asarray(a), np.asarray(b_))
     A, b, Cm, d = oracle_inputs(n, k, m, 0, 3)
     assert np.array_equal(outs[1][0][3], Cm) and np.array_equal(outs[1][0][4], -d)
+
+
+def test_generator_fused_slice_pass_is_bit_identical_and_lazily_materialised(monkeypatch):
+    """A UNIFORM matrix whose only reader is the int8 slice pass of the objective is generated INSIDE that pass (no prologue fill, no
+    read-back) and its buffer is only written on demand by pmb_param_device_ptr.  The objective must equal the unfused schedule
+    (PMB_NO_GEN_FUSE=1) and the write-every-update variant (PMB_GEN_MATERIALIZE=1) bit for bit over several updates, batch 1 and batch 2
+    (per-instance Philox keys), and A.download() must return the oracle's matrix of the LAST update -- also when it is called only after
+    later updates.  Ref: each Parameter is evaluated once per update! (parameter.jl:93-104); values are what rand! would have produced."""
+    import parametron_b200 as pm
+    n, k, m = 1536, 2048, 8
+    for batch in (1, 2):
+        runs = {}
+        for tag, env in (("fused", None), ("unfused", "PMB_NO_GEN_FUSE"), ("writeback", "PMB_GEN_MATERIALIZE")):
+            monkeypatch.delenv("PMB_NO_GEN_FUSE", raising=False); monkeypatch.delenv("PMB_GEN_MATERIALIZE", raising=False)
+            if env:
+                monkeypatch.setenv(env, "1")
+            model, (A, b, Cm, d) = _ls_model_shard(pm, n, k, m, batch, 5, gram_mode=5)
+            cls = None
+            for _ in range(3):
+                model.update()
+            kt = model.stats()
+            out = model.objective_arrays()
+            Ad = A.download()                      # materialises update 3 on the fused route
+            runs[tag] = (out, Ad, kt["kernel_launches_per_update"])
+            if tag == "fused":
+                model.update(); model.update()     # two more updates without touching the Parameter ...
+                A5 = A.download()                  # ... then its values are those of update 5
+                for inst in range(batch):
+                    Ao = oracle_inputs(n, k, m, 5 + inst, 5)[0]
+                    assert np.array_equal(A5[inst] if batch > 1 else A5, Ao)
+            model.close()
+        for inst in range(batch):
+            Ao = oracle_inputs(n, k, m, 5 + inst, 3)[0]
+            for tag in runs:
+                Ad = runs[tag][1]
+                assert np.array_equal(Ad[inst] if batch > 1 else Ad, Ao), tag
+        for tag in ("unfused", "writeback"):
+            for x, y in zip(runs["fused"][0], runs[tag][0]):
+                assert np.array_equal(np.asarray(x), np.asarray(y)), tag
+        assert runs["fused"][2] == runs["unfused"][2]
