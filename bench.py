@@ -467,16 +467,18 @@ def main():
         c3lv = cm.gram_level_counts()
         us = {k_: v[0] / max(v[1], 1) * 1e3 for k_, v in c3kt.items() if v[1]}
         per = {}
-        if us.get("gram_i8_tcgen05"):   # fused small-instance kernel: reads A once (8 B / element), writes Q once (8 B / element)
-            gbytes = (8 * C3_K * C3_N + 8 * C3_N * C3_N) * count
+        if us.get("gram_i8_tcgen05"):   # fused small-instance kernel: A is generated inside the kernel (generator fusion, default), Q is written once (8 B / element)
+            gen_fused = not os.environ.get("PMB_NO_GEN_FUSE")
+            gbytes = ((0 if gen_fused else 8 * C3_K * C3_N) + 8 * C3_N * C3_N) * count
             per["gram"] = {"kernel": "gram_i8_fused_kernel (one CTA pair per instance: slicing + 15 int8 digit-plane products on tcgen05 + epilogue, planes never leave the chip)",
                            "bound": "hbm", "avg_launch_us": us["gram_i8_tcgen05"], "algorithmic_bytes": gbytes, "achieved_gbs": gbytes / us["gram_i8_tcgen05"] / 1e3,
                            "frac": gbytes / us["gram_i8_tcgen05"] / 1e3 / peaks["hbm_gbs"],
                            "fp64_equivalent_tflops": c3st["gram_algorithmic_flops"] * count / us["gram_i8_tcgen05"] / 1e6,
-                           "traffic": int((4352197000 + 4362385000) * count / 8192),
-                           "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the 8192-instance launch, scaled to this rank's instances: "
-                                             "profiles/r02_g_fused_cfg3_ncu_full.txt (4.35 GB read + 4.36 GB written = 1.01x the algorithmic bytes)",
-                           "limiter": "not HBM (25-32 % of the measured copy rate) and not the tensor pipe (21.8 % active): the CTA pair alternates between slicing "
+                           "generator_fused": gen_fused,
+                           "traffic": None,
+                           "traffic_source": "ncu of the 8192-instance launch: profiles/r02_k_fused_gen_cfg3_ncu_full.txt (generator-fused kernel: only Q is written); "
+                                             "the loading variant moved 4.35 GB read + 4.36 GB written = 1.01x its algorithmic bytes (profiles/r02_g_fused_cfg3_ncu_full.txt)",
+                           "limiter": "not HBM and not the tensor pipe (about 20 % active): the CTA pair alternates between slicing (with the Philox generation of its columns) "
                                       "(8 warps, ~38 k clocks per instance) and the 15 x 2 digit-plane products paced by the epilogue (~31 k clocks) because the 160 KB of "
                                       "operand panels exist once per SM -- timeline profiles/r02_e_fused_v6_timeline.txt, ablation profiles/r02_b_fused_kernel_ablation.txt"}
         elif us.get("gram_dmma"):

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libpmb200.so")
 SOURCES = ["kernels_affine.cu", "kernels_affine_tma.cu", "kernels_gram.cu", "kernels_gram_tma.cu", "kernels_gram_i8.cu", "kernels_gram_i8_fused.cu", "kernels_misc.cu", "kernels_export.cu", "pmb_export.cu", "pmb_build.cu", "pmb_plan.cu"]
-HEADERS = ["pmb_kernels.h", "pmb_internal.h", "pmb_host.h", "pmb_i8_ptx.h", "pmb_philox.h", os.path.join("..", "..", "include", "parametron_b200.h")]
+HEADERS = ["pmb_kernels.h", "pmb_internal.h", "pmb_host.h", "pmb_i8_ptx.h", "pmb_philox.h", "kernels_gram_i8_fused_body.inc", os.path.join("..", "..", "include", "parametron_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
          "-Xptxas", "-v", "--use_fast_math=false"]

@@ -210,7 +210,8 @@ const char* gram_i8_fused_diag_text(const unsigned long long* diag, char* buf, s
 // instance (gram_i8_mma).  false: not applicable (the caller runs the fp64 kernel alone).
 // [col0, col1): column range of this launch (upload pipelining: one slice + one Gram launch per arrived chunk); col1 < 0 = all columns.
 // The Gram launch of a range computes the tile columns whose last column lies in the range.
-bool gram_i8_slice_can_generate(const GramArgs& g, const GramI8Plan& plan);   // GramI8Scratch::gen_counter may be set for this operand
+bool gram_i8_slice_can_generate(const GramArgs& g, const GramI8Plan& plan);
+bool gram_i8_fused_can_generate(const GramArgs& g);   // same for the fused small-instance kernel   // GramI8Scratch::gen_counter may be set for this operand
 bool launch_gram_i8_slice(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0 = 0,
                           int64_t col1 = -1);
 bool launch_gram_i8_mma(const GramArgs& g, const GramI8Scratch& sc, int64_t batch, int sm_count, cudaStream_t stream, int64_t col0 = 0,

@@ -440,6 +440,31 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
             ga.scale = scaled(a, 2.0 * F.cx * F.cx); ga.accumulate = overwrite ? 0 : 1;
             // certified int8-slice path on tcgen05 (kernels_gram_i8.cu): large contractions only, fp64 kernel keeps the uncertified instances
             GramI8Scratch i8{};
+            // generator fusion (both int8 routes): the operand is a UNIFORM Parameter nothing else reads -> its Philox fill moves from the prologue
+            // launch into the pass that slices it (same bits); the Parameter's buffer is then written on demand (pmb_param_device_ptr), or by the
+            // two-kernel route's slice pass on every update with PMB_GEN_MATERIALIZE=1
+            auto try_generator_fusion = [&](bool can_write_back) {
+                if (F.whole_node < 0 || getenv("PMB_NO_GEN_FUSE")) return;
+                const bool write_back = getenv("PMB_GEN_MATERIALIZE") != nullptr;
+                if (write_back && !can_write_back) return;
+                const Node& pn = c->nodes[(size_t)F.whole_node];
+                if (!(pn.nop == NOP_PARAM && pn.pmode == PMB_PARAM_UNIFORM && pn.owned && F.k == pn.rows && F.ncols == pn.cols && F.xbs == pn.numel &&
+                      count_refs(c, F.whole_node) == 1)) return;
+                for (size_t j = 0; j < c->fill_jobs.size() && j < c->fill_job_nodes.size(); ++j)
+                    if (c->fill_job_nodes[j] == F.whole_node) {
+                        FillJob lazy = c->fill_jobs[j];
+                        c->fill_jobs.erase(c->fill_jobs.begin() + (long)j); c->fill_job_nodes.erase(c->fill_job_nodes.begin() + (long)j);
+                        i8.gen_counter = c->d_counter; i8.gen_seed = pn.seed; i8.gen_scale = pn.scale; i8.gen_inst_offset = c->inst_offset;
+                        i8.gen_writeback = write_back ? 1 : 0;
+                        if (!write_back) {   // the buffer is filled on demand: keep the job as a one-element list for pmb_param_device_ptr
+                            const int64_t cap = (int64_t)c->sm_count * 16;
+                            lazy.nblocks = (int32_t)std::max<int64_t>(1, std::min<int64_t>(((lazy.numel + 1) / 2 + 255) / 256, std::max<int64_t>(1, cap / std::max<int64_t>(1, std::min<int64_t>(nb, 64)))));
+                            Node& wn = c->nodes[(size_t)F.whole_node];
+                            wn.lazy_fill = upload(c, std::vector<FillJob>{lazy}); wn.lazy_fill_blocks = lazy.nblocks;
+                        }
+                        return;
+                    }
+            };
             // fused small-instance route (kernels_gram_i8_fused.cu): batches of instances with n, k <= 256 -- slicing, digit-plane products and
             // epilogue of one instance per CTA pair in one launch, no digit planes in HBM; q and c0 ride along
             GramArgs fz = ga;
@@ -457,6 +482,7 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                 (void)cudaGetLastError();
                 i8.diag = c->fused_diag;
                 i8.fused = 1;
+                if (gram_i8_fused_can_generate(fz)) try_generator_fusion(false);
                 ga.cert_stats = i8.stats; ga.cert_tol = i8.tol; ga.cert_force = i8.force_ns != 0; ga.cert_none = i8.stats + nb * kGramI8StatsStride;
                 fz.cert_stats = ga.cert_stats; fz.cert_tol = ga.cert_tol; fz.cert_force = ga.cert_force; fz.cert_none = ga.cert_none;
             }
@@ -470,28 +496,9 @@ static QuadTarget plan_quadratic(pmb_ctx* c, QuadForm qf, bool is_const, bool wa
                     i8.tol = c->gram_tol;
                     i8.force_ns = c->gram_mode >= 5 ? c->gram_mode : 0;
                     ga.cert_stats = i8.stats; ga.cert_tol = i8.tol; ga.cert_force = i8.force_ns != 0;
-                    // generator fusion: the operand is a UNIFORM Parameter nothing else reads -> its Philox fill moves from the prologue launch into
-                    // the slice pass (same bits; the values are still written to the Parameter's buffer, but the slice pass no longer reads them back)
-                    if (F.whole_node >= 0 && !getenv("PMB_NO_GEN_FUSE")) {
-                        const Node& pn = c->nodes[(size_t)F.whole_node];
-                        GramArgs probe = ga; probe.gvec = F.g;  probe.g_bstride = F.gbs;
-                        if (pn.nop == NOP_PARAM && pn.pmode == PMB_PARAM_UNIFORM && pn.owned && F.k == pn.rows && F.ncols == pn.cols && F.xbs == pn.numel &&
-                            count_refs(c, F.whole_node) == 1 && gram_i8_slice_can_generate(probe, i8.plan)) {
-                            for (size_t j = 0; j < c->fill_jobs.size() && j < c->fill_job_nodes.size(); ++j)
-                                if (c->fill_job_nodes[j] == F.whole_node) {
-                                    FillJob lazy = c->fill_jobs[j];
-                                    c->fill_jobs.erase(c->fill_jobs.begin() + (long)j); c->fill_job_nodes.erase(c->fill_job_nodes.begin() + (long)j);
-                                    i8.gen_counter = c->d_counter; i8.gen_seed = pn.seed; i8.gen_scale = pn.scale; i8.gen_inst_offset = c->inst_offset;
-                                    i8.gen_writeback = getenv("PMB_GEN_MATERIALIZE") ? 1 : 0;
-                                    if (!i8.gen_writeback) {   // the buffer is filled on demand: keep the job as a one-element list for pmb_param_device_ptr
-                                        const int64_t cap = (int64_t)c->sm_count * 16;
-                                        lazy.nblocks = (int32_t)std::max<int64_t>(1, std::min<int64_t>(((lazy.numel + 1) / 2 + 255) / 256, std::max<int64_t>(1, cap / std::max<int64_t>(1, std::min<int64_t>(nb, 64)))));
-                                        Node& wn = c->nodes[(size_t)F.whole_node];
-                                        wn.lazy_fill = upload(c, std::vector<FillJob>{lazy}); wn.lazy_fill_blocks = lazy.nblocks;
-                                    }
-                                    break;
-                                }
-                        }
+                    {
+                        GramArgs probe = ga; probe.gvec = F.g; probe.g_bstride = F.gbs;
+                        if (gram_i8_slice_can_generate(probe, i8.plan)) try_generator_fusion(true);
                     }
                 }
             }
@@ -1141,15 +1148,16 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
         for (size_t i = 0; i < ctx->nodes.size(); ++i) ctx->nodes[i].needed = saved[i];
     }
     if (!ctx->fill_jobs.empty()) {
-        // fused prologue launch: Philox fills of every built-in generator, zeroing of (q, c0), update tick.  PMB_PROLOGUE_SPLIT=1 (experiment,
-        // measured r02: cfg3 5.894 -> 5.827 ms, cfg2 0.4719 -> 0.4747 ms -- the generator blocks do not fit next to the persistent Gram CTAs,
-        // so little overlaps; off by default) moves the generators of Parameters that only the constraint chain reads to a second launch at
-        // the head of the constraint branch when they are large (>= 8 MB per update)
+        // fused prologue launch: Philox fills of every built-in generator, zeroing of (q, c0), update tick.  The generators of Parameters that only the
+        // constraint chain reads move to a second launch at the head of the constraint branch when they are large (>= 8 MB per update): the
+        // objective chain then starts after ITS Parameters only (with generator fusion that is just the offset vector).  Measured r02 with the
+        // fused generators: cfg3 5.460 -> 5.399 ms per sweep (1.500 -> 1.517 M instance-updates/s), cfg2 unchanged; PMB_NO_PROLOGUE_SPLIT=1 keeps
+        // the single launch (small models always do: a 2 us launch on the constraint branch would lengthen their critical path)
         std::vector<FillJob> main_jobs, aux_jobs;
         int64_t aux_bytes = 0;
         for (size_t j = 0; j < ctx->fill_jobs.size(); ++j) {
             const int nd = j < ctx->fill_job_nodes.size() ? ctx->fill_job_nodes[j] : -1;
-            const bool aux = nd >= 0 && !ctx->nodes[(size_t)nd].used_main && getenv("PMB_PROLOGUE_SPLIT");
+            const bool aux = nd >= 0 && !ctx->nodes[(size_t)nd].used_main && !getenv("PMB_NO_PROLOGUE_SPLIT");
             (aux ? aux_jobs : main_jobs).push_back(ctx->fill_jobs[j]);
             if (aux) aux_bytes += ctx->fill_jobs[j].numel * ctx->batch * (int64_t)sizeof(double);
         }

@@ -483,16 +483,17 @@ def test_cfg3_back_to_back_updates_without_synchronisation():
     model.close()
 
 
-def test_prologue_split_option_is_bit_identical(monkeypatch):
-    """PMB_PROLOGUE_SPLIT=1 moves the generators of constraint-only Parameters (here C: 8 MB, d) to a second prologue launch on the constraint
-    branch (update id taken from the already published counter instead of counter + 1): every Parameter and every output must equal the
-    single-launch schedule bit for bit, over several updates.  Ref: each Parameter is evaluated exactly once per update!, parameter.jl:93-104."""
+def test_prologue_split_is_bit_identical_to_the_single_launch(monkeypatch):
+    """The generators of constraint-only Parameters (here C: 8 MB, d) run as a second prologue launch on the constraint branch (update id taken
+    from the already published counter instead of counter + 1); PMB_NO_PROLOGUE_SPLIT=1 keeps the single launch.  Every Parameter and every
+    output must be equal bit for bit, over several updates.  Ref: each Parameter is evaluated exactly once per update!, parameter.jl:93-104."""
     import parametron_b200 as pm
     n, k, m = 1024, 256, 1024
     outs = []
-    for split in (False, True):
-        if split:
-            monkeypatch.setenv("PMB_PROLOGUE_SPLIT", "1")
+    for single in (True, False):
+        monkeypatch.delenv("PMB_NO_PROLOGUE_SPLIT", raising=False)
+        if single:
+            monkeypatch.setenv("PMB_NO_PROLOGUE_SPLIT", "1")
         model, _ = _ls_model_shard(pm, n, k, m, 1, 0)
         for _ in range(3):
             model.update()
