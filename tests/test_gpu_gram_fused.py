@@ -177,3 +177,47 @@ def test_cost_model_keeps_single_small_instances_on_fp64():
     assert lv == (0, 0, 1)
     Qo, qo, c0o = D.least_squares_objective(vals[0], vals[1], np.arange(1, 9), 8)
     assert_close(Q, Qo, RTOL, "Q")
+
+
+@pytest.mark.parametrize("n", [256, 200, 128, 100, 24])
+def test_generator_fused_variant_on_ragged_instance_widths(monkeypatch, n):
+    """gram_i8_fused_gen_kernel (the operand is a UNIFORM Parameter nothing else reads: the slicer warps generate their columns, the head of the
+    next instance is parked in shared memory while the current products run) on instance widths where the second CTA of the pair owns a
+    partial panel (200), nothing (128, 100) and where less than one parked stage exists (24); 7 instances = several per CTA pair only for the
+    first pairs.  Q bit-identical to the loading kernel fed by the prologue's fill (PMB_NO_GEN_FUSE=1), 1e-10 against the dense oracle, and the
+    Parameter reads back as the oracle's matrix (materialised on demand)."""
+    import parametron_b200 as pm
+    from oracle import philox
+    monkeypatch.setenv("PMB_GRAM_I8_FUSED", "1")
+    k, m, B, first = 256, 3, 7, 11
+    outs = {}
+    for tag in ("gen", "load"):
+        monkeypatch.delenv("PMB_NO_GEN_FUSE", raising=False)
+        if tag == "load":
+            monkeypatch.setenv("PMB_NO_GEN_FUSE", "1")
+        model = pm.Model(batch=B, instance_offset=first)
+        x = model.variables(n)
+        A = pm.Parameter(model, shape=(k, n), uniform=(77, 1.0))
+        b = pm.Parameter(model, shape=(k,), uniform=(78, 1.0))
+        Cm = pm.Parameter(model, shape=(m, n), uniform=(79, 1.0))
+        d = pm.Parameter(model, shape=(m,), uniform=(80, 2.0))
+        r = A * x - b
+        pm.objective(model, pm.Minimize, pm.dot(r, r))
+        pm.constraint(model, Cm * x, "==", d)
+        model.initialize()
+        for _ in range(3):
+            model.update()
+        assert model.gram_level_counts() == (B, 0, 0)
+        outs[tag] = (model.objective_arrays(), A.download())
+        model.close()
+    assert np.array_equal(outs["gen"][0][0], outs["load"][0][0])          # Q: exact integer accumulation, same sigma -> bit-identical
+    assert_close(outs["gen"][0][1], outs["load"][0][1], 1e-14, "q")     # q, c0: the generated column sits in registers in natural row order, the
+    assert_close(outs["gen"][0][2], outs["load"][0][2], 1e-14, "c0")    # loaded one with swapped halves in half of the lanes: fp64 sums in another order
+    assert np.array_equal(outs["gen"][1], outs["load"][1])
+    Q, q, c0 = outs["gen"][0]
+    for inst in range(B):
+        Ao = philox.uniform_matrix(k, n, 77, 1.0, first + inst, 3)
+        bo = philox.uniform(k, 78, 1.0, first + inst, 3)
+        assert np.array_equal(outs["gen"][1][inst], Ao)
+        Qo, qo, c0o = D.least_squares_objective(Ao, bo, np.arange(1, n + 1), n)
+        assert_close(Q[inst], Qo, RTOL, f"Q[{inst}]"); assert_close(q[inst], qo, RTOL, "q"); assert_close([c0[inst]], [c0o], RTOL, "c0")
