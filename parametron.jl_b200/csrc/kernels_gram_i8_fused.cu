@@ -9,20 +9,28 @@
 // on top of the 8 B read of X and the 8 B write of H) and the fp64 DMMA route is compute-bound at ~4 ms per 8192 instances.  Here a
 // CTA PAIR (cluster of 2 = one TPC, tcgen05 cta_group::2) owns one instance at a time and keeps everything on chip:
 //
-//   warp 0   producer   X columns of the CTA's half (128 columns) travel global -> shared as 1-D bulk copies (UBLKCP), 8 columns per
-//                       stage, 3 stages ahead; the offset vector g rides along with the first stage of an instance
-//   warps 2-9 workers   (a) one column per warp and stage: largest magnitude / 2-norm / 1-norm / X'g by warp shuffles, fixed-point
-//                       digits, five int8 planes written straight into the 128-byte-swizzled K-major operand layout tcgen05 reads
-//                       (160 KB per CTA: 5 planes x 2 k-blocks x 128 columns x 128 B); the per-instance statistics of the error
-//                       certificate are exchanged between the two CTAs through distributed shared memory
-//                       (b) epilogue: tcgen05.ld, exact combination of the five int32 levels, sigma_i sigma_j scaling, stores
-//   warp 1   MMA issuer (leader CTA only) tcgen05.mma.cta_group::2.kind::i8, M = 256 (CTA r supplies rows 128 r ..), N = 128 (each CTA
-//                       supplies 64 of its columns), K = 32: the 15 digit-plane products of an output half go out as three units
-//                       {level 0, 1}, {2, 3}, {4} of at most 256 TMEM columns, double-buffered against the epilogue
+//   warps 0-7   epilogue   tcgen05.ld, exact integer combination of the five int32 levels (carried between the units in packed form), ONE
+//                          rounding to fp64, sigma_i sigma_j scaling, 256-bit streaming stores                              (144 registers)
+//   warps 8-15  slicers    one column per warp and stage: largest magnitude / 2-norm / 1-norm / X'g by warp reductions, fixed-point
+//                          digits, five int8 planes written straight into the 128-byte-swizzled K-major operand layout tcgen05 reads
+//                          (160 KB per CTA: 5 planes x 2 k-blocks x 128 columns x 128 B); the per-instance statistics of the error
+//                          certificate are exchanged between the two CTAs through distributed shared memory              (72 registers)
+//   warp 16     producer   X columns of the CTA's half (128 columns) travel global -> shared as 1-D bulk copies (UBLKCP), 8 columns per
+//                          stage, 3 stages ahead; the offset vector g rides along
+//   warp 17     MMA issuer (leader CTA only, whole warp, elect.sync) tcgen05.mma.cta_group::2.kind::i8, M = 256 (CTA r supplies rows
+//                          128 r ..), N = 128 (each CTA supplies 64 of its columns), K = 32: the 15 digit-plane products of an output
+//                          half go out as three units {level 4}, {2, 3}, {0, 1} into two 256-column TMEM regions
+//   warps 18-19 idle (setmaxnreg works on groups of four); with -DFZ_WATCHDOG warp 18 watches the others' milestones
 //
-// HBM traffic per instance is the algorithmic minimum (read X once, write H once); the full square is computed (no mirrored writes).
-// The certificate is evaluated per instance inside the kernel (5 planes or "not certified"); uncertified instances are left to the
-// fp64 kernel that follows in the update graph (GramArgs::cert_stats), exactly as on the two-kernel route.
+// Two kernels are compiled from one body (kernels_gram_i8_fused_body.inc):
+//   gram_i8_fused_kernel      the operand X is read from memory (HBM traffic = the algorithmic minimum: X once, H once)
+//   gram_i8_fused_gen_kernel  X is a UNIFORM Parameter nothing else reads: the slicers generate their columns with Philox (pmb_philox.h, the
+//                             same bits as the prologue's fill), nothing is loaded, and -- since nothing has to arrive -- they slice the
+//                             first four stages of the NEXT instance while the products of the current one still read the operand panels,
+//                             parking digits and sigma in the 48 KB the loading variant uses for its ring
+// The full square is computed (no mirrored writes).  The certificate is evaluated per instance inside the kernel (5 planes or "not
+// certified"); uncertified instances are left to the fp64 kernel that follows in the update graph (GramArgs::cert_stats), exactly as on
+// the two-kernel route.  Measured variants that did not make it are kept as text under tools/probe/attic/ (DESIGN.md section 4).
 #include <cuda.h>
 
 #include <algorithm>
