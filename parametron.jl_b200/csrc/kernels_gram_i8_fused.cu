@@ -27,7 +27,8 @@
 //   gram_i8_fused_gen_kernel  X is a UNIFORM Parameter nothing else reads: the slicers generate their columns with Philox (pmb_philox.h, the
 //                             same bits as the prologue's fill), nothing is loaded, and -- since nothing has to arrive -- they slice the
 //                             first four stages of the NEXT instance while the products of the current one still read the operand panels,
-//                             parking digits and sigma in the 48 KB the loading variant uses for its ring
+//                             parking digits and sigma in the 48 KB the loading variant uses for its ring; the epilogue warps, idle until the
+//                             next instance is sliced, slice one column of its last six stages themselves
 // The full square is computed (no mirrored writes).  The certificate is evaluated per instance inside the kernel (5 planes or "not
 // certified"); uncertified instances are left to the fp64 kernel that follows in the update graph (GramArgs::cert_stats), exactly as on
 // the two-kernel route.  Measured variants that did not make it are kept as text under tools/probe/attic/ (DESIGN.md section 4).
