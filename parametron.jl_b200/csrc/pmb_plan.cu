@@ -1122,9 +1122,32 @@ int pmb_initialize(pmb_ctx* ctx, const int64_t* varmap) {
             con.Qc = T.Q; con.C = T.q; con.d = T.c0; con.nterms = 0;
             continue;
         }
-        con.C = dalloc<double>(ctx, ctx->batch * con.rows * N, true);
         con.d = dalloc<double>(ctx, ctx->batch * con.rows, true);
         con.nterms = aff_nterms(con.form);
+        // Zero-copy block: `M * x` over ALL variables in optimizer order with unit coefficient, M a matrix Parameter the library fills only inside
+        // pmb_update (UNIFORM generator or HOST upload) -- the coefficient block IS the Parameter's buffer (same column-major m x N layout, same
+        // instance stride): the view points at it and only the offsets d are assembled.  Caller-written device Parameters keep the copy (the block
+        // must stay the snapshot update! took).  PMB_NO_BLOCK_ALIAS=1: always copy
+        bool aliased = false;
+        if (!con.is_const && con.form.mats.size() == 1 && con.form.units.empty() && !getenv("PMB_NO_BLOCK_ALIAS")) {
+            const MatTerm& mt = con.form.mats[0];
+            const Node& sn = ctx->nodes[(size_t)mt.mat];
+            bool ident = mt.a.node < 0 && mt.a.c == 1.0 && mt.row_off == 0 && mt.rows == con.rows && mt.src_col_off == 0 && mt.cols == N &&
+                         sn.nop == NOP_PARAM && sn.kind == PMB_KIND_NUM_MATRIX && sn.bsr_b == 0 && sn.rows == con.rows && sn.cols == N && sn.owned && sn.dptr &&
+                         !sn.lazy_fill && (sn.pmode == PMB_PARAM_UNIFORM || sn.pmode == PMB_PARAM_HOST) && (int64_t)mt.vars.size() == N;
+            for (int64_t j = 0; ident && j < N; ++j) ident = optcol(ctx, mt.vars[(size_t)j]) == (int32_t)j;
+            if (ident) {
+                AffForm only_off = con.form;
+                only_off.mats.clear();
+                con.C = sn.dptr;
+                AffBlockDev b = lower_aff(ctx, only_off, nullptr, 0, con.d, con.rows, true, nullptr);
+                ctx->steps.push_back(affine_step(b, ctx->batch));
+                ctx->affine_bytes += 16 * con.rows;
+                aliased = true;
+            }
+        }
+        if (aliased) continue;
+        con.C = dalloc<double>(ctx, ctx->batch * con.rows * N, true);
         AffBlockDev b = lower_aff(ctx, con.form, con.C, con.rows * N, con.d, con.rows, false, nullptr);
         (con.is_const ? ctx->init_steps : ctx->steps).push_back(affine_step(b, ctx->batch));
         if (!con.is_const) ctx->affine_bytes += 16 * (int64_t)b.ntouched * con.rows + 16 * con.rows;

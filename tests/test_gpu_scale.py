@@ -76,7 +76,8 @@ def test_cfg2_full_size_against_dense_oracle():
     rhs = float(np.sum((A @ xs - b) ** 2))
     assert abs(lhs - rhs) <= 1e-9 * abs(rhs)
     st = model.stats()
-    assert st["affine_algorithmic_bytes"] == 16 * m * n + 16 * m
+    # the block C x == d aliases the (library-filled) Parameter: only the offsets are assembled; with the copy it is 16 m n + 16 m
+    assert st["affine_algorithmic_bytes"] == (16 * m * n + 16 * m if os.environ.get("PMB_NO_BLOCK_ALIAS") else 16 * m)
     assert st["gram_algorithmic_flops"] == k * n * (n + 1) + 2 * k * n + 2 * k
     assert model.block_view(0).nterms == m * n
 
@@ -545,3 +546,50 @@ def test_generator_fused_slice_pass_is_bit_identical_and_lazily_materialised(mon
             for x, y in zip(runs["fused"][0], runs[tag][0]):
                 assert np.array_equal(np.asarray(x), np.asarray(y)), tag
         assert runs["fused"][2] == runs["unfused"][2]
+
+
+def test_identity_constraint_block_aliases_the_parameter_buffer(monkeypatch):
+    """`C x == d` over all variables in optimizer order with unit coefficient, C a Parameter the library fills only inside update (UNIFORM
+    generator, HOST upload): the coefficient block is the Parameter's own buffer -- no copy launch, the view points at it -- and only the
+    offsets -d are assembled.  A permuted variable map, a scaled block and PMB_NO_BLOCK_ALIAS=1 keep the copy; values are identical in all
+    cases.  Ref: the block is what moi_interop.jl:64-81 would emit for C * x - d (coefficients C[row, col], constants -d)."""
+    import parametron_b200 as pm
+    n, k, m, B = 96, 64, 40, 3
+
+    def build(perm=None, scale=None, host=False):
+        model = pm.Model(batch=B, instance_offset=2)
+        x = model.variables(n)
+        A = pm.Parameter(model, shape=(k, n), uniform=(1, 1.0)); b = pm.Parameter(model, shape=(k,), uniform=(2, 1.0))
+        if host:
+            rng = np.random.default_rng(5)
+            Cv = rng.random((B, m, n)); dv = rng.random((B, m))
+            Cm = pm.Parameter(model, val=Cv); d = pm.Parameter(model, val=dv)
+        else:
+            Cm = pm.Parameter(model, shape=(m, n), uniform=(3, 1.0)); d = pm.Parameter(model, shape=(m,), uniform=(4, 2.0))
+        r = A * x - b
+        pm.objective(model, pm.Minimize, pm.dot(r, r))
+        pm.constraint(model, (scale * (Cm * x)) if scale else (Cm * x), "==", d)
+        model.initialize(idxmap=perm)
+        for _ in range(2):
+            model.update()
+        v = model.block_view(0)
+        out = (int(v.C), int(Cm.device_ptr), model.block_arrays(0), Cm.download() if not host else Cv)
+        model.close()
+        return out
+
+    ptr, pptr, (Cb, db), Cp = build()
+    assert ptr == pptr and np.array_equal(Cb, Cp)                 # the view IS the Parameter's buffer
+    for inst in range(B):
+        _, _, Co, do = oracle_inputs(n, k, m, 2 + inst, 2, seeds=(1, 2, 3, 4))
+        assert np.array_equal(Cb[inst], Co) and np.array_equal(db[inst], -do)
+    monkeypatch.setenv("PMB_NO_BLOCK_ALIAS", "1")
+    ptr2, pptr2, (Cb2, db2), _ = build()
+    assert ptr2 != pptr2 and np.array_equal(Cb2, Cb) and np.array_equal(db2, db)
+    monkeypatch.delenv("PMB_NO_BLOCK_ALIAS")
+    perm = np.random.default_rng(0).permutation(n) + 1
+    ptr3, pptr3, (Cb3, _), _ = build(perm=perm)
+    assert ptr3 != pptr3 and np.array_equal(Cb3[:, :, perm - 1], Cb)
+    ptr4, pptr4, (Cb4, _), _ = build(scale=2.0)
+    assert ptr4 != pptr4 and np.array_equal(Cb4, 2.0 * Cb)
+    ptr5, pptr5, (Cb5, _), Cv = build(host=True)
+    assert ptr5 == pptr5 and np.array_equal(Cb5, Cv)
