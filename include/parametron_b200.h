@@ -179,7 +179,10 @@ typedef struct {
     int32_t bucket;      /* index into the reference's fixed bucket order (moi_interop.jl:180-193) */
     int64_t rows;        /* m_i */
     int64_t nvars;       /* N */
-    double* C;           /* device, m_i x N column-major (ld = m_i), batch stride m_i*N; columns are OPTIMIZER indices */
+    double* C;           /* device, m_i x N column-major (ld = m_i), batch stride m_i*N; columns are OPTIMIZER indices.  READ-ONLY for the caller:
+                          * when the block is `M * x` over all variables in optimizer order with unit coefficient and M is a Parameter the library
+                          * fills only inside pmb_update (PMB_PARAM_UNIFORM / PMB_PARAM_HOST), this IS the Parameter's buffer (no copy is made;
+                          * PMB_NO_BLOCK_ALIAS=1 in the environment restores the copy) */
     double* d;           /* device, m_i, batch stride m_i   (the block is  C x + d  in the set) */
     int64_t nterms;      /* number of reference LinearTerms per instance (static sparsity bookkeeping) */
     /* sparse form (block built from one BSR matrix): C is NULL; coefficient e of an instance is vals[e] at
